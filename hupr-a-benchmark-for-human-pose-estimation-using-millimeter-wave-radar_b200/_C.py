@@ -10,11 +10,30 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libhupr_b200.so")
 _lib = None
 
+class ConvDesc(ctypes.Structure):
+    """Mirror of ``hupr_conv_desc`` (include/hupr_b200.h) — field order must match the C struct."""
+    _fields_ = [
+        ("a_hi", ctypes.c_void_p), ("a_lo", ctypes.c_void_p),
+        ("n", ctypes.c_int), ("d", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int), ("ca", ctypes.c_int),
+        ("a_ch_off", ctypes.c_int), ("cin", ctypes.c_int),
+        ("w_hi", ctypes.c_void_p), ("w_lo", ctypes.c_void_p),
+        ("cout", ctypes.c_int),
+        ("kd", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
+        ("pd", ctypes.c_int), ("ph", ctypes.c_int), ("pw", ctypes.c_int),
+        ("w_batched", ctypes.c_int),
+        ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("slope", ctypes.c_void_p),
+        ("r_hi", ctypes.c_void_p), ("r_lo", ctypes.c_void_p), ("r_ld", ctypes.c_int), ("r_ch_off", ctypes.c_int),
+        ("o_hi", ctypes.c_void_p), ("o_lo", ctypes.c_void_p), ("o_ld", ctypes.c_int), ("o_ch_off", ctypes.c_int),
+        ("o_f32", ctypes.c_void_p), ("o_f32_ld", ctypes.c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/hupr_b200.h
 SIGNATURES = {
     "hupr_version": (ctypes.c_int, []),
     "hupr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
 }
 
 
@@ -47,3 +66,8 @@ def stream_ptr():
 
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
+
+
+def optr(t):
+    """Raw pointer value of an optional tensor (None -> NULL), for Structure fields."""
+    return None if t is None else t.data_ptr()

@@ -10,10 +10,11 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libhupr_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
+    "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177", "-I", INCLUDE,
 ]
 
 
@@ -32,7 +33,8 @@ def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
+    deps = (sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
+            + glob.glob(os.path.join(INCLUDE, "*.h")))
     return any(os.path.getmtime(p) > t for p in deps)
 
 

@@ -3,12 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "hupr_internal.h"
+#ifndef HUPR_OK
 #define HUPR_OK 0
 #define HUPR_ERR_BAD_ARG (-1)
 #define HUPR_ERR_ALIGNMENT (-2)
 #define HUPR_ERR_CUDA (-3)
 #define HUPR_ERR_ARCH (-4)
 #define HUPR_ERR_WORKSPACE (-5)
+#endif
 
 namespace hupr {
 

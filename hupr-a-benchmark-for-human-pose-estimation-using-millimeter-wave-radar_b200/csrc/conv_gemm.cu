@@ -1,0 +1,418 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// One kernel serves every dense contraction of MSCSA-PRGCN (reference models/layers.py):
+//   Conv3d 3x3x3 (layers.py:45-63,195-206), temporal-merge Conv3d (T,1,1) (:208-210), Conv2d 3x3 (:24-32,81-95),
+//   1x1 q/k projections (:116-123), the head conv (:94) and both attention matmuls (:126-133).
+//
+// Formulation:  D[pos, co] = sum_{tap} sum_{ci} A[pos + off(tap), ci] * W[tap][co][ci]
+//   * activations are channels-last ([N][D][H][W][C]) bf16; fp32-equivalent accuracy comes from a hi/lo split
+//     (x = hi + lo, both bf16) and three tensor-core products per k-step (hi*hi + lo*hi + hi*lo), fp32 accumulate in TMEM;
+//   * no im2col buffer: for every filter tap the TMA engine loads the shifted [BH x BW] x 64-channel box straight from
+//     the activation tensor (5-D tiled tensor map, SWIZZLE_128B, out-of-bounds = zero fill gives the conv padding);
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+//     warps 2..5 = epilogue (tcgen05.ld -> scale/shift (+residual) -> PReLU-style slope -> bf16 hi/lo or fp32 stores);
+//   * mbarrier ring (full/empty) between TMA and MMA, tcgen05.commit releases stages and publishes the accumulator.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "hupr_internal.h"
+
+namespace hupr {
+
+constexpr int BM = 128;   // output positions per CTA tile (TMEM lanes)
+constexpr int BK = 64;    // channels per k-block = one 128-byte swizzle row of bf16
+constexpr int kConvThreads = 192;
+
+template <int BN, int NPROD>
+struct ConvCfg {
+    static constexpr int kPlanes = (NPROD == 3) ? 2 : 1;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+    static constexpr int kStages = (200 * 1024 / kStageBytes) > 6 ? 6 : (200 * 1024 / kStageBytes);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct ConvParams {
+    int n, d_in, h, w, d_out;
+    int kd, kh, kw, pd, ph, pw;
+    int cin_blocks, a_ch_off, w_batched;
+    int bw, bh, tiles_w, tiles_h;
+    int cout;
+    const float* scale;
+    const float* shift;
+    const float* slope;
+    const __nv_bfloat16* r_hi;
+    const __nv_bfloat16* r_lo;
+    int r_ld, r_ch_off;
+    __nv_bfloat16* o_hi;
+    __nv_bfloat16* o_lo;
+    int o_ld, o_ch_off;
+    float* o_f32;
+    int o_f32_ld;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p) {
+    using Cfg = ConvCfg<BN, NPROD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Cfg::kStages;
+    uint64_t* accum_full = bars + 2 * Cfg::kStages;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int od = t % p.d_out;
+    const int n = t / p.d_out;
+    const int w0 = tw * p.bw, h0 = th * p.bh;
+    const int n0 = blockIdx.y * BN;
+    const int num_kb = p.kd * p.kh * p.kw * p.cin_blocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmB_hi);
+        if (NPROD == 3) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp), BN fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+                const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                mbar_expect_tx(&full[s], Cfg::kStageBytes);
+                const int ac = p.a_ch_off + cb * BK, aw = w0 + tkw - p.pw, ah = h0 + tkh - p.ph, ad = od + tkd - p.pd;
+                const int b2 = p.w_batched ? n : tap;
+                tma_load_5d(st, &tmA_hi, &full[s], ac, aw, ah, ad, n);
+                tma_load_3d(st + Cfg::kPlanes * Cfg::kABytes, &tmB_hi, &full[s], cb * BK, n0, b2);
+                if (NPROD == 3) {
+                    tma_load_5d(st + Cfg::kABytes, &tmA_lo, &full[s], ac, aw, ah, ad, n);
+                    tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK, n0, b2);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint64_t da_hi = make_smem_desc(st);
+                const uint64_t db_hi = make_smem_desc(st + Cfg::kPlanes * Cfg::kABytes);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
+                    if (NPROD == 3) {
+                        const uint64_t da_lo = make_smem_desc(st + Cfg::kABytes);
+                        const uint64_t db_lo = make_smem_desc(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+                        umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
+                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+                    }
+                }
+                tc_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
+            }
+            tc_commit(accum_full);      // accumulator complete
+        }
+    } else {
+        // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ow = w0 + row % p.bw, oh = h0 + row / p.bw;
+        const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
+            const int ch0 = n0 + c * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(acc[j]);
+                const float sc = p.scale ? __ldg(p.scale + ch0 + j) : 1.0f;
+                const float sh = p.shift ? __ldg(p.shift + ch0 + j) : 0.0f;
+                v[j] = fmaf(x, sc, sh);
+            }
+            if (p.r_hi) {
+                const uint4* rh = reinterpret_cast<const uint4*>(p.r_hi + pos * p.r_ld + p.r_ch_off + ch0);
+                const uint4* rl = p.r_lo ? reinterpret_cast<const uint4*>(p.r_lo + pos * p.r_ld + p.r_ch_off + ch0) : nullptr;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 a = __ldg(rh + g);
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[g * 8 + 2 * e] += __uint_as_float(aw[e] << 16);
+                        v[g * 8 + 2 * e + 1] += __uint_as_float(aw[e] & 0xFFFF0000u);
+                    }
+                    if (rl) {
+                        const uint4 b = __ldg(rl + g);
+                        const uint32_t bw_[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[g * 8 + 2 * e] += __uint_as_float(bw_[e] << 16);
+                            v[g * 8 + 2 * e + 1] += __uint_as_float(bw_[e] & 0xFFFF0000u);
+                        }
+                    }
+                }
+            }
+            if (p.slope) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sl = __ldg(p.slope + ch0 + j);
+                    v[j] = v[j] > 0.0f ? v[j] : v[j] * sl;
+                }
+            }
+            if (p.o_f32) {
+                float4* dst = reinterpret_cast<float4*>(p.o_f32 + pos * p.o_f32_ld + ch0);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+            if (p.o_hi) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __nv_bfloat16 h0b = __float2bfloat16_rn(v[2 * j]), h1b = __float2bfloat16_rn(v[2 * j + 1]);
+                    const __nv_bfloat16 l0b = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0b));
+                    const __nv_bfloat16 l1b = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1b));
+                    hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                    lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                }
+                uint4* dh = reinterpret_cast<uint4*>(p.o_hi + pos * p.o_ld + p.o_ch_off + ch0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dh[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+                if (p.o_lo) {
+                    uint4* dl = reinterpret_cast<uint4*>(p.o_lo + pos * p.o_ld + p.o_ch_off + ch0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dl[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int encode_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int bh) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return HUPR_ERR_CUDA;
+    cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2, (cuuint64_t)d * h * w * ca * 2};
+    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+static int encode_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int taps, int bn) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return HUPR_ERR_CUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+template <int BN, int NPROD>
+static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const ConvParams& p, int m_tiles, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN, NPROD>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+            cudaSuccess)
+            return HUPR_ERR_CUDA;
+        configured = true;
+    }
+    dim3 grid(m_tiles, p.cout / BN, 1);
+    conv_gemm_kernel<BN, NPROD><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+}  // namespace hupr
+
+extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
+    using namespace hupr;
+    if (!d || !d->a_hi || !d->w_hi) return HUPR_ERR_BAD_ARG;
+    if ((d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
+    if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > d->ca) return HUPR_ERR_BAD_ARG;
+    if (d->cout <= 0 || d->cout % 64) return HUPR_ERR_BAD_ARG;
+    if (d->kd <= 0 || d->kh <= 0 || d->kw <= 0) return HUPR_ERR_BAD_ARG;
+    if (d->kh != 2 * d->ph + 1 || d->kw != 2 * d->pw + 1) return HUPR_ERR_BAD_ARG;   // H, W are 'same' convolutions
+    const int d_out = d->d + 2 * d->pd - d->kd + 1;
+    if (d_out <= 0) return HUPR_ERR_BAD_ARG;
+    const int taps = d->kd * d->kh * d->kw;
+    if (d->w_batched && taps != 1) return HUPR_ERR_BAD_ARG;
+    if (!d->o_hi && !d->o_f32) return HUPR_ERR_BAD_ARG;
+    if (d->o_hi && (d->o_ld % 8 || d->o_ch_off % 8 || d->o_ch_off + d->cout > d->o_ld)) return HUPR_ERR_BAD_ARG;
+    if (d->o_f32 && (d->o_f32_ld % 4 || d->cout > d->o_f32_ld)) return HUPR_ERR_BAD_ARG;
+    if (d->r_hi && (d->r_ld % 8 || d->r_ch_off % 8 || d->r_ch_off + d->cout > d->r_ld)) return HUPR_ERR_BAD_ARG;
+    // spatial tiling of the 128 output positions of one CTA
+    const int bw = d->w < BM ? d->w : BM;
+    if (BM % bw || d->w % bw) return HUPR_ERR_BAD_ARG;
+    const int bh = BM / bw;
+    if (d->h % bh) return HUPR_ERR_BAD_ARG;
+    const uintptr_t align_or = (uintptr_t)d->a_hi | (uintptr_t)d->a_lo | (uintptr_t)d->w_hi | (uintptr_t)d->w_lo | (uintptr_t)d->o_hi |
+                               (uintptr_t)d->o_lo | (uintptr_t)d->o_f32 | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo;
+    if (align_or & 15) return HUPR_ERR_ALIGNMENT;
+
+    ConvParams p;
+    p.n = d->n; p.d_in = d->d; p.h = d->h; p.w = d->w; p.d_out = d_out;
+    p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+    p.cin_blocks = d->cin / BK; p.a_ch_off = d->a_ch_off; p.w_batched = d->w_batched;
+    p.bw = bw; p.bh = bh; p.tiles_w = d->w / bw; p.tiles_h = d->h / bh;
+    p.cout = d->cout;
+    p.scale = d->scale; p.shift = d->shift; p.slope = d->slope;
+    p.r_hi = (const __nv_bfloat16*)d->r_hi; p.r_lo = (const __nv_bfloat16*)d->r_lo; p.r_ld = d->r_ld; p.r_ch_off = d->r_ch_off;
+    p.o_hi = (__nv_bfloat16*)d->o_hi; p.o_lo = (__nv_bfloat16*)d->o_lo; p.o_ld = d->o_ld; p.o_ch_off = d->o_ch_off;
+    p.o_f32 = d->o_f32; p.o_f32_ld = d->o_f32_ld;
+
+    const int bn = (d->cout % 128 == 0) ? 128 : 64;
+    const int wdim2 = d->w_batched ? d->n : taps;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    if ((rc = encode_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
+    if ((rc = encode_wgt_map(&b_hi, d->w_hi, d->cin, d->cout, wdim2, bn)) != HUPR_OK) return rc;
+    const bool split = d->a_lo != nullptr;
+    if (split) {
+        if ((rc = encode_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
+        if ((rc = encode_wgt_map(&b_lo, d->w_lo, d->cin, d->cout, wdim2, bn)) != HUPR_OK) return rc;
+    } else {
+        a_lo = a_hi;
+        b_lo = b_hi;
+    }
+    const long long m_tiles_ll = (long long)d->n * d_out * p.tiles_h * p.tiles_w;
+    if (m_tiles_ll > 2147483647LL) return HUPR_ERR_BAD_ARG;
+    const int m_tiles = (int)m_tiles_ll;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (bn == 128) return split ? launch_conv<128, 3>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<128, 1>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    return split ? launch_conv<64, 3>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+}
