@@ -56,7 +56,82 @@ def make_dca():
     print("dca", ref.shape)
 
 
-TARGETS = {"cascade": make_cascade, "dca": make_dca}
+MODEL_SAMPLE = (slice(None), slice(None), slice(None), slice(3, None, 7), slice(2, None, 5))
+
+
+def tensor_stats(t):
+    t = t.double()
+    return np.array([float(t.sum()), float((t * t).sum()), float(t.abs().max())], dtype=np.float64)
+
+
+def make_model():
+    """Reference HuPRNet (eval) on the oracle's seeded weights/inputs -> strided samples + checksums."""
+    import torch
+    from . import model as om
+    cls = ref_shim.load_model_classes()
+    net = cls["HuPRNet"](ref_shim.load_cfg()).eval()
+    out = {}
+    for batch, seed in ((1, 0), (2, 5)):
+        sd = om.make_state_dict(seed)
+        assert list(net.state_dict().keys()) == list(sd.keys())
+        net.load_state_dict(sd)
+        hori, vert = om.make_vrdae(batch, seed)
+        with torch.no_grad():
+            heat, gcn = net(hori, vert)
+            ra = net.forward_chirp(hori, vert)[0]
+            feats = net.RAradarEncoder(ra)
+        key = "b%d_s%d" % (batch, seed)
+        out[key + "_heatmap"] = heat.numpy()[MODEL_SAMPLE]
+        out[key + "_gcn"] = gcn.numpy()[MODEL_SAMPLE]
+        out[key + "_heatmap_stats"] = tensor_stats(heat)
+        out[key + "_gcn_stats"] = tensor_stats(gcn)
+        out[key + "_chirp_stats"] = tensor_stats(ra)
+        for i, f in enumerate(feats):
+            out[key + "_enc%d_stats" % i] = tensor_stats(f)
+            out[key + "_enc%d" % i] = f.numpy()[:, ::8, ::5, ::5]
+        print("model", key, out[key + "_heatmap_stats"], out[key + "_gcn_stats"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "model_reference.npz"), **out)
+
+
+def make_loss():
+    """Reference LossComputer / generateTarget / get_max_preds on seeded predictions and joints."""
+    import torch
+    LossComputer, generateTarget, get_max_preds = ref_shim.load_misc()
+    lc = LossComputer(ref_shim.load_cfg(), torch.device("cpu"))
+    g = torch.Generator().manual_seed(42)
+    b = 3
+    heat = torch.rand((b, 14, 1, 64, 64), generator=g) * 0.98 + 0.01
+    gcn = torch.rand((b, 1, 14, 64, 64), generator=g) * 0.98 + 0.01
+    # joints include border / out-of-range cases so that the Gaussian clipping branches are covered
+    gt = torch.randint(0, 256, (b, 14, 2), generator=g)
+    gt[0, 0] = torch.tensor([0, 0]); gt[0, 1] = torch.tensor([255, 255]); gt[0, 2] = torch.tensor([3, 250])
+    gt[1, 0] = torch.tensor([300, 10]); gt[1, 1] = torch.tensor([-40, 100]); gt[1, 2] = torch.tensor([283, 128])
+    loss, loss2, pred2d, gt2d = lc.computeLoss((heat, gcn), gt)
+    targets = np.stack([generateTarget(gt[i], 14, 64, 256)[0] for i in range(b)])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "loss_reference.npz"), seed=np.array(42), gt=gt.numpy(),
+                        loss=np.array(float(loss)), loss2=np.array(float(loss2)), pred2d=pred2d, gt2d=gt2d,
+                        targets_sample=targets[:, :, ::3, ::3], targets_sum=np.array(targets.astype(np.float64).sum()),
+                        targets_nonzero=np.array(int((targets > 0).sum())))
+    print("loss", float(loss), float(loss2))
+
+
+def make_loader():
+    """Reference Normalize (through torchvision ToTensor, as getTransformFunc builds it) on cascade cubes."""
+    import torchvision.transforms as transforms
+    Normalize = ref_shim.load_normalize()
+    tf = transforms.Compose([transforms.ToTensor(), Normalize()])
+    cube = cascade.generate_heatmap(cascade.synth_frame(2, 0))
+    out = np.zeros((8, 2, 64, 64, 8), dtype=np.float32)
+    for s, d in enumerate(range(4, 12)):
+        out[s, 0] = tf(cube[d].real).permute(1, 2, 0).numpy()
+        out[s, 1] = tf(cube[d].imag).permute(1, 2, 0).numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "loader_reference.npz"), frame=np.array([2, 0]),
+                        sample=out[:, :, ::4, ::4, :], sums=out.astype(np.float64).sum(axis=(2, 3)),
+                        sqsums=(out.astype(np.float64) ** 2).sum(axis=(2, 3)))
+    print("loader", out.shape, np.isfinite(out).all())
+
+
+TARGETS = {"cascade": make_cascade, "dca": make_dca, "model": make_model, "loss": make_loss, "loader": make_loader}
 
 
 def main(argv):
