@@ -25,8 +25,12 @@ class ConvDesc(ctypes.Structure):
         ("r_hi", ctypes.c_void_p), ("r_lo", ctypes.c_void_p), ("r_ld", ctypes.c_int), ("r_ch_off", ctypes.c_int),
         ("o_hi", ctypes.c_void_p), ("o_lo", ctypes.c_void_p), ("o_ld", ctypes.c_int), ("o_ch_off", ctypes.c_int),
         ("o_f32", ctypes.c_void_p), ("o_f32_ld", ctypes.c_int),
+        ("w_ld", ctypes.c_int), ("w_ch_off", ctypes.c_int),
     ]
 
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
 
 # name -> (restype, argtypes); must list every symbol of include/hupr_b200.h
 SIGNATURES = {
@@ -34,6 +38,15 @@ SIGNATURES = {
     "hupr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
+    "hupr_window_normalize": (ctypes.c_int, [_P, _P, _I, _P, _P]),
+    "hupr_mnet_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
+    "hupr_resample_linear": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "hupr_softmax_rows": (ctypes.c_int, [_P, _P, _P, ctypes.c_longlong, _I, _P]),
+    "hupr_transpose_split": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "hupr_prgcn_workspace_bytes": (ctypes.c_size_t, [_I]),
+    "hupr_prgcn_fwd": (ctypes.c_int, [_P, _I, ctypes.POINTER(_P), ctypes.POINTER(_P), _P, _P, ctypes.c_size_t, _P, _P, _I, _P]),
+    "hupr_keypoints_argmax": (ctypes.c_int, [_P, _I, _P, _P, _P]),
+    "hupr_heatmap_loss_fwd": (ctypes.c_int, [_P, _P, _P, _I, _P, ctypes.c_size_t, _P, _P, _P, _P]),
 }
 
 

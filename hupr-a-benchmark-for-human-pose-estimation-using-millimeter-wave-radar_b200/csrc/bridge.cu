@@ -1,0 +1,337 @@
+// HBM-bound kernels either side of the tensor-core contractions (sm_100a):
+//   hupr_window_normalize  loader bridge: cascade cubes -> standardised VRDAE windows
+//                          (/root/reference/datasets/base.py:13-24, datasets/dataset.py:120-150)
+//   hupr_mnet_fwd          elevation mean + the (chirp, re/im)->(channel, depth) view + MNet
+//                          (/root/reference/models/networks.py:23-33, models/chirp_networks.py:11-21)
+//   hupr_resample_linear   bi/tri-linear align_corners=True resampling of split channels-last tensors
+//                          (/root/reference/models/layers.py:84,89,199,204)
+//   hupr_softmax_rows      softmax over the key axis of the attention logits (layers.py:131)
+//   hupr_transpose_split   [n][s][c] -> [n][c][s] (V operand of the second attention matmul, layers.py:132)
+#include "common.cuh"
+#include "split.cuh"
+
+namespace hupr {
+
+constexpr int kPlaneCells = 64 * 64;          // (range, azimuth) cells per Doppler plane
+constexpr int kPlaneF4 = kPlaneCells * 8 / 2; // float4 (= 2 complex) per Doppler plane
+constexpr int kNormThreads = 512;
+
+// Reduce 4 per-thread values over all threads that share (tid & 3); result broadcast to every thread.
+__device__ __forceinline__ void reduce_by_quad(float (&v)[4], float* scratch /* [16 warps][4][4] */) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();   // scratch may still be read from a previous reduction
+    if (lane < 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scratch[(warp * 4 + lane) * 4 + k] = v[k];
+    }
+    __syncthreads();
+    const int q = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kNormThreads / 32; ++w) s += scratch[(w * 4 + q) * 4 + k];
+        v[k] = s;
+    }
+}
+
+// One CTA per (window slot, kept Doppler row).  The 256 KiB plane is read three times (mean, centred variance, write);
+// passes 2 and 3 hit L2.  Thread t owns float4 index t + 512*k, i.e. a fixed elevation pair 2*(t&3), 2*(t&3)+1.
+__global__ void __launch_bounds__(kNormThreads)
+window_normalize_kernel(const float4* __restrict__ cube, const int* __restrict__ slot_fs, float* __restrict__ vrdae) {
+    __shared__ float scratch[(kNormThreads / 32) * 16];
+    const int c = blockIdx.x;                       // kept Doppler row 0..7 -> cube row 4 + c (dataset.py:145)
+    const int slot = blockIdx.y;
+    const int fs = __ldg(slot_fs + slot);
+    const float4* plane = cube + ((size_t)fs * 16 + 4 + c) * kPlaneF4;
+    const int tid = threadIdx.x;
+
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < kPlaneF4 / kNormThreads; ++k) {
+        const float4 v = __ldg(plane + tid + k * kNormThreads);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    reduce_by_quad(s, scratch);
+    float mean[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mean[k] = s[k] * (1.0f / kPlaneCells);
+
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < kPlaneF4 / kNormThreads; ++k) {
+        const float4 v = __ldg(plane + tid + k * kNormThreads);
+        const float d0 = v.x - mean[0], d1 = v.y - mean[1], d2 = v.z - mean[2], d3 = v.w - mean[3];
+        q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+    }
+    reduce_by_quad(q, scratch);
+    float rstd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rstd[k] = 1.0f / sqrtf(q[k] * (1.0f / (kPlaneCells - 1)));   // unbiased std (base.py:23)
+
+    float2* out_re = reinterpret_cast<float2*>(vrdae + ((size_t)(slot * 8 + c) * 2 + 0) * (kPlaneCells * 8));
+    float2* out_im = reinterpret_cast<float2*>(vrdae + ((size_t)(slot * 8 + c) * 2 + 1) * (kPlaneCells * 8));
+#pragma unroll 8
+    for (int k = 0; k < kPlaneF4 / kNormThreads; ++k) {
+        const int i = tid + k * kNormThreads;
+        const float4 v = __ldg(plane + i);
+        out_re[i] = make_float2((v.x - mean[0]) * rstd[0], (v.z - mean[2]) * rstd[2]);
+        out_im[i] = make_float2((v.y - mean[1]) * rstd[1], (v.w - mean[3]) * rstd[3]);
+    }
+}
+
+// One thread per (slot, range, azimuth) position: 16 plane means over elevation, 32 output channels.
+__global__ void __launch_bounds__(256)
+mnet_kernel(const float* __restrict__ vrdae, const float* __restrict__ weight, const float* __restrict__ bias,
+            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int n_slots) {
+    __shared__ float sW[32 * 4 + 32];
+    if (threadIdx.x < 160) sW[threadIdx.x] = threadIdx.x < 128 ? __ldg(weight + threadIdx.x) : __ldg(bias + threadIdx.x - 128);
+    __syncthreads();
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= (size_t)n_slots * kPlaneCells) return;
+    const size_t slot = gid / kPlaneCells;
+    const int pos = (int)(gid % kPlaneCells);
+    const float4* base = reinterpret_cast<const float4*>(vrdae + slot * (16 * kPlaneCells * 8) + (size_t)pos * 8);
+    float m[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 a = __ldg(base + (size_t)j * (kPlaneCells * 2));
+        const float4 b = __ldg(base + (size_t)j * (kPlaneCells * 2) + 1);
+        m[j] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * 0.125f;
+    }
+    // plane j = chirp f * 2 + (re|im); the reference's .view makes channel 0 = planes 0..7, channel 1 = planes 8..15 (depth = j & 7)
+    __nv_bfloat16* oh = out_hi + gid * 32;
+    __nv_bfloat16* ol = out_lo ? out_lo + gid * 32 : nullptr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = g * 8 + i;
+            const float w00 = sW[o * 4], w01 = sW[o * 4 + 1], w10 = sW[o * 4 + 2], w11 = sW[o * 4 + 3], b = sW[128 + o];
+            float best = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float y = fmaf(w11, m[9 + 2 * t], fmaf(w10, m[8 + 2 * t], fmaf(w01, m[2 * t + 1], w00 * m[2 * t]))) + b;
+                best = fmaxf(best, y);
+            }
+            v[i] = best;
+        }
+        store8(oh + g * 8, ol ? ol + g * 8 : nullptr, v);
+    }
+}
+
+struct ResampleParams {
+    int n, di, hi, wi, dout, ho, wo, c8;      // c8 = channels / 8
+    int in_ld, in_off, out_ld, out_off;
+    float sd, sh, sw;                         // align_corners scales (in-1)/(out-1)
+};
+
+__global__ void __launch_bounds__(256)
+resample_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, const ResampleParams p) {
+    const size_t total = (size_t)p.n * p.dout * p.ho * p.wo * p.c8;
+    for (size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (size_t)gridDim.x * 256) {
+        size_t t = gid;
+        const int cg = (int)(t % p.c8); t /= p.c8;
+        const int ow = (int)(t % p.wo); t /= p.wo;
+        const int oh = (int)(t % p.ho); t /= p.ho;
+        const int od = (int)(t % p.dout);
+        const int n = (int)(t / p.dout);
+        const float fd = p.sd * od, fh = p.sh * oh, fw = p.sw * ow;
+        const int d0 = (int)fd, h0 = (int)fh, w0 = (int)fw;
+        const int d1 = d0 + (d0 < p.di - 1), h1 = h0 + (h0 < p.hi - 1), w1 = w0 + (w0 < p.wi - 1);
+        const float ld1 = fd - d0, lh1 = fh - h0, lw1 = fw - w0;
+        const float ld0 = 1.f - ld1, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const int ds[2] = {d0, d1}, hs[2] = {h0, h1}, ws[2] = {w0, w1};
+        const float wd[2] = {ld0, ld1}, wh[2] = {lh0, lh1}, ww[2] = {lw0, lw1};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (a == 1 && p.di == 1) break;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float wgt = (p.di == 1 ? 1.f : wd[a]) * wh[b] * ww[c];
+                    const size_t off = ((((size_t)n * p.di + ds[a]) * p.hi + hs[b]) * p.wi + ws[c]) * p.in_ld + p.in_off + cg * 8;
+                    float v[8];
+                    load8(in_hi + off, in_lo ? in_lo + off : nullptr, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, v[i], acc[i]);
+                }
+            }
+        }
+        const size_t ooff = ((((size_t)n * p.dout + od) * p.ho + oh) * p.wo + ow) * p.out_ld + p.out_off + cg * 8;
+        store8(out_hi + ooff, out_lo ? out_lo + ooff : nullptr, acc);
+    }
+}
+
+// One CTA (256 threads) per row; cols in {256, 512, ..., 4096} (multiple of 4, <= 4096).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo, int cols) {
+    __shared__ float red[8];
+    const size_t row = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(logits + row * cols);
+    const int nvec = cols >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 v[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * 256;
+        if (i < nvec) {
+            v[k] = __ldg(src + i);
+            mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * 256;
+        if (i < nvec) {
+            v[k].x = expf(v[k].x - mx); v[k].y = expf(v[k].y - mx); v[k].z = expf(v[k].z - mx); v[k].w = expf(v[k].w - mx);
+            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    const float inv = 1.0f / sum;
+    uint2* dh = reinterpret_cast<uint2*>(p_hi + row * cols);
+    uint2* dl = p_lo ? reinterpret_cast<uint2*>(p_lo + row * cols) : nullptr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * 256;
+        if (i < nvec) {
+            uint32_t h0, l0, h1, l1;
+            split2(v[k].x * inv, v[k].y * inv, h0, l0);
+            split2(v[k].z * inv, v[k].w * inv, h1, l1);
+            dh[i] = make_uint2(h0, h1);
+            if (dl) dl[i] = make_uint2(l0, l1);
+        }
+    }
+}
+
+// in [n][s][in_ld] (channels in_off .. in_off + c) -> out [n][c][s]; 32x32 tiles, block (32, 8).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int s, int c, int in_ld, int in_off) {
+    __shared__ uint16_t tile[32][34];
+    const int n = blockIdx.z;
+    const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) tile[j][tx] = in[((size_t)n * s + s0 + j) * in_ld + in_off + c0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) out[((size_t)n * c + c0 + j) * s + s0 + tx] = tile[tx][j];
+}
+
+static int check_sm100() {
+    static int cached = -100;
+    if (cached == -100) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
+        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
+    }
+    return cached;
+}
+
+static inline int launch_status() { return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA; }
+
+}  // namespace hupr
+
+using namespace hupr;
+
+extern "C" int hupr_window_normalize(const void* cube, const int32_t* slot_fs, int n_slots, float* vrdae, void* stream) {
+    if (n_slots < 0) return HUPR_ERR_BAD_ARG;
+    if (n_slots == 0) return HUPR_OK;
+    if (!cube || !slot_fs || !vrdae) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)cube | (uintptr_t)vrdae) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    window_normalize_kernel<<<dim3(8, n_slots), kNormThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<const float4*>(cube), slot_fs, vrdae);
+    return launch_status();
+}
+
+extern "C" int hupr_mnet_fwd(const float* vrdae, const float* weight, const float* bias, void* out_hi, void* out_lo,
+                             int n_slots, void* stream) {
+    if (n_slots < 0) return HUPR_ERR_BAD_ARG;
+    if (n_slots == 0) return HUPR_OK;
+    if (!vrdae || !weight || !bias || !out_hi) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)vrdae | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const size_t total = (size_t)n_slots * kPlaneCells;
+    mnet_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        vrdae, weight, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, n_slots);
+    return launch_status();
+}
+
+extern "C" int hupr_resample_linear(const void* in_hi, const void* in_lo, int n, int di, int hi, int wi, int c, int in_ld, int in_ch_off,
+                                    void* out_hi, void* out_lo, int dout, int ho, int wo, int out_ld, int out_ch_off, void* stream) {
+    if (!in_hi || !out_hi || n <= 0 || di <= 0 || hi <= 0 || wi <= 0 || dout <= 0 || ho <= 0 || wo <= 0 || c <= 0) return HUPR_ERR_BAD_ARG;
+    if (c % 8 || in_ld % 8 || out_ld % 8 || in_ch_off % 8 || out_ch_off % 8 || in_ch_off + c > in_ld || out_ch_off + c > out_ld)
+        return HUPR_ERR_BAD_ARG;
+    if ((in_lo == nullptr) != (out_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)in_hi | (uintptr_t)in_lo | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    ResampleParams p;
+    p.n = n; p.di = di; p.hi = hi; p.wi = wi; p.dout = dout; p.ho = ho; p.wo = wo; p.c8 = c / 8;
+    p.in_ld = in_ld; p.in_off = in_ch_off; p.out_ld = out_ld; p.out_off = out_ch_off;
+    p.sd = dout > 1 ? (float)(di - 1) / (float)(dout - 1) : 0.f;
+    p.sh = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) : 0.f;
+    p.sw = wo > 1 ? (float)(wi - 1) / (float)(wo - 1) : 0.f;
+    const size_t total = (size_t)n * dout * ho * wo * p.c8;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                                       (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, p);
+    return launch_status();
+}
+
+extern "C" int hupr_softmax_rows(const float* logits, void* p_hi, void* p_lo, long long rows, int cols, void* stream) {
+    if (rows < 0 || rows > 2147483647LL) return HUPR_ERR_BAD_ARG;
+    if (rows == 0) return HUPR_OK;
+    if (!logits || !p_hi || cols <= 0 || cols % 4 || cols > 4096) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)logits | (uintptr_t)p_hi | (uintptr_t)p_lo) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo, cols);
+    return launch_status();
+}
+
+extern "C" int hupr_transpose_split(const void* in_hi, const void* in_lo, int n, int s, int c, int in_ld, int in_ch_off,
+                                    void* out_hi, void* out_lo, void* stream) {
+    if (!in_hi || !out_hi || n <= 0 || s <= 0 || c <= 0 || s % 32 || c % 32 || in_ch_off < 0 || in_ch_off + c > in_ld) return HUPR_ERR_BAD_ARG;
+    if ((in_lo == nullptr) != (out_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    if (n > 65535 || c / 32 > 65535) return HUPR_ERR_BAD_ARG;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const dim3 grid(s / 32, c / 32, n), block(32, 8);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_hi, (uint16_t*)out_hi, s, c, in_ld, in_ch_off);
+    if (in_lo) transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
+    return launch_status();
+}

@@ -327,11 +327,11 @@ static int encode_act_map(CUtensorMap* map, const void* base, int ca, int w, int
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-static int encode_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int taps, int bn) {
+static int encode_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int taps, int bn, int ld) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return HUPR_ERR_CUDA;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)cout * ld * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -363,7 +363,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     if (!d || !d->a_hi || !d->w_hi) return HUPR_ERR_BAD_ARG;
     if ((d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
     if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
-    if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > d->ca) return HUPR_ERR_BAD_ARG;
+    if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > ((d->ca + BK - 1) / BK) * BK) return HUPR_ERR_BAD_ARG;
     if (d->cout <= 0 || d->cout % 64) return HUPR_ERR_BAD_ARG;
     if (d->kd <= 0 || d->kh <= 0 || d->kw <= 0) return HUPR_ERR_BAD_ARG;
     if (d->kh != 2 * d->ph + 1 || d->kw != 2 * d->pw + 1) return HUPR_ERR_BAD_ARG;   // H, W are 'same' convolutions
@@ -400,11 +400,15 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = encode_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
-    if ((rc = encode_wgt_map(&b_hi, d->w_hi, d->cin, d->cout, wdim2, bn)) != HUPR_OK) return rc;
+    const int w_ld = d->w_ld ? d->w_ld : d->cin;
+    if (w_ld % 8 || d->w_ch_off % 8 || d->w_ch_off < 0 || d->w_ch_off + d->cin > w_ld) return HUPR_ERR_BAD_ARG;
+    const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
+    const __nv_bfloat16* w_lo = d->w_lo ? static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off : nullptr;
+    if ((rc = encode_wgt_map(&b_hi, w_hi, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
     const bool split = d->a_lo != nullptr;
     if (split) {
         if ((rc = encode_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
-        if ((rc = encode_wgt_map(&b_lo, d->w_lo, d->cin, d->cout, wdim2, bn)) != HUPR_OK) return rc;
+        if ((rc = encode_wgt_map(&b_lo, w_lo, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
     } else {
         a_lo = a_hi;
         b_lo = b_hi;

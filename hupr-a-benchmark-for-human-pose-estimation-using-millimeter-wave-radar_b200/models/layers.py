@@ -1,0 +1,251 @@
+"""Weight packing and the launch sequences of the encoder / decoder stages (the reference's models/layers.py,
+models/chirp_networks.py and models/gcn_networks.py, restated as kernel launches).
+
+Layout conventions:
+  * activations: channels-last ``[B, D, H, W, C]`` bf16 hi/lo split tensors (``ops.SplitTensor``), value = hi + lo;
+  * conv weights: ``[taps, cout, cin]`` split tensors, cin/cout zero-padded to multiples of 64;
+  * eval-mode BatchNorm is applied as an fp32 per-channel scale/shift in the conv epilogue (weights are not rescaled);
+  * the two convolutions that read the same input in a residual block (``main.0`` and ``downsample.0``) are one launch
+    with their filters concatenated along cout; a per-channel slope array gives ReLU/PReLU to the first half and identity to
+    the second half, and the block's second conv fuses ``+ residual`` and the final activation into its epilogue.
+"""
+import torch
+
+from .. import ops
+from ..ops import SplitTensor
+
+BN_EPS = 1e-5
+
+
+def pad64(c):
+    return -(-c // 64) * 64
+
+
+def pack_conv(weights, cin_pad, cout_pads, split=True):
+    """List of torch conv weights ``[Cout, Cin, *k]`` (same Cin, same kernel) -> SplitTensor ``[taps, sum(cout_pads), cin_pad]``."""
+    mats = []
+    for w, cp in zip(weights, cout_pads):
+        cout, cin = w.shape[:2]
+        taps = w[0, 0].numel()
+        m = torch.zeros(taps, cp, cin_pad, dtype=torch.float32, device=w.device)
+        m[:, :cout, :cin] = w.detach().float().reshape(cout, cin, taps).permute(2, 0, 1)
+        mats.append(m)
+    return SplitTensor.from_float(torch.cat(mats, dim=1), split)
+
+
+def bn_affine(sd, prefix):
+    scale = sd[prefix + ".weight"].float() / torch.sqrt(sd[prefix + ".running_var"].float() + BN_EPS)
+    shift = sd[prefix + ".bias"].float() - sd[prefix + ".running_mean"].float() * scale
+    return scale, shift
+
+
+class Block(object):
+    """Packed residual block: conv1 || downsample, then conv2 (+ residual, activation)."""
+    __slots__ = ("w1", "scale1", "shift1", "slope1", "w2", "scale2", "shift2", "slope2", "cin", "cmid", "taps", "pad")
+
+
+def pack_block3d(sd, prefix, cin, cout, split):
+    b = Block()
+    b.cin, b.cmid, b.taps, b.pad = pad64(cin), cout, (3, 3, 3), (1, 1, 1)
+    b.w1 = pack_conv([sd[prefix + ".main.0.weight"], sd[prefix + ".downsample.0.weight"]], b.cin, [cout, cout], split)
+    s1, h1 = bn_affine(sd, prefix + ".main.1")
+    sd_, hd = bn_affine(sd, prefix + ".downsample.1")
+    b.scale1, b.shift1 = torch.cat([s1, sd_]).contiguous(), torch.cat([h1, hd]).contiguous()
+    b.slope1 = torch.cat([torch.zeros_like(s1), torch.ones_like(sd_)]).contiguous()      # ReLU | identity
+    b.w2 = pack_conv([sd[prefix + ".main.3.weight"]], cout, [cout], split)
+    b.scale2, b.shift2 = (t.contiguous() for t in bn_affine(sd, prefix + ".main.4"))
+    b.slope2 = torch.zeros_like(b.scale2)
+    return b
+
+
+def pack_block2d(sd, prefix, cin, cout, split):
+    b = Block()
+    cp = pad64(cout)
+    b.cin, b.cmid, b.taps, b.pad = cin, cp, (1, 3, 3), (0, 1, 1)
+    w_main = sd[prefix + ".main.0.weight"].unsqueeze(2)
+    w_ds = sd[prefix + ".downsample.0.weight"].unsqueeze(2)
+    b.w1 = pack_conv([w_main, w_ds], cin, [cp, cp], split)
+    dev = w_main.device
+    b.scale1 = b.shift1 = b.scale2 = b.shift2 = None
+    b.slope1 = torch.cat([sd[prefix + ".main.1.weight"].float().expand(cp), torch.ones(cp, device=dev)]).contiguous()   # PReLU | identity
+    b.w2 = pack_conv([sd[prefix + ".main.2.weight"].unsqueeze(2)], cp, [cp], split)
+    b.slope2 = sd[prefix + ".relu.weight"].float().expand(cp).contiguous()
+    return b
+
+
+def run_block(x, blk, tmp, out, o_ch_off=0):
+    """x -> out[..., o_ch_off : o_ch_off + cmid];  tmp is a ``[..., 2*cmid]`` scratch tensor."""
+    c = blk.cmid
+    ops.conv_gemm(x, blk.cin, blk.w1, 2 * c, kernel=blk.taps, pad=blk.pad, scale=blk.scale1, shift=blk.shift1,
+                  slope=blk.slope1, out=tmp)
+    ops.conv_gemm(tmp, c, blk.w2, c, kernel=blk.taps, pad=blk.pad, scale=blk.scale2, shift=blk.shift2, slope=blk.slope2,
+                  residual=tmp, r_ch_off=c, out=out, o_ch_off=o_ch_off)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- encoder (layers.py:186-217)
+class EncoderWeights(object):
+    def __init__(self, sd, prefix, nf, group_frames, split):
+        self.l1_w = pack_conv([sd[prefix + ".layer1.0.weight"]], pad64(nf), [2 * nf], split)
+        self.l1_shift = sd[prefix + ".layer1.0.bias"].float().contiguous()
+        self.blocks = [pack_block3d(sd, prefix + ".layer1.1", 2 * nf, 2 * nf, split),
+                       pack_block3d(sd, prefix + ".layer2.1", 2 * nf, 4 * nf, split),
+                       pack_block3d(sd, prefix + ".layer2.2", 4 * nf, 4 * nf, split),
+                       pack_block3d(sd, prefix + ".layer3.1", 4 * nf, 8 * nf, split),
+                       pack_block3d(sd, prefix + ".layer3.2", 8 * nf, 8 * nf, split)]
+        self.merge = [pack_conv([sd[prefix + ".l1temporalMerge.weight"]], 2 * nf, [2 * nf], split),
+                      pack_conv([sd[prefix + ".l2temporalMerge.weight"]], 4 * nf, [4 * nf], split),
+                      pack_conv([sd[prefix + ".temporalMerge.weight"]], 8 * nf, [8 * nf], split)]
+        self.nf, self.g = nf, group_frames
+
+
+class EncoderBuffers(object):
+    def __init__(self, b, nf, g, dev, split):
+        mk = lambda *shape: SplitTensor.empty(shape, dev, split)
+        self.l1a = mk(b, g, 64, 64, 2 * nf)
+        self.t1 = mk(b, g, 64, 64, 4 * nf)
+        self.l1 = mk(b, g, 64, 64, 2 * nf)
+        self.l2in = mk(b, g // 2, 32, 32, 2 * nf)
+        self.t2 = mk(b, g // 2, 32, 32, 8 * nf)
+        self.l2a = mk(b, g // 2, 32, 32, 4 * nf)
+        self.l2 = mk(b, g // 2, 32, 32, 4 * nf)
+        self.l3in = mk(b, g // 4, 16, 16, 4 * nf)
+        self.t3 = mk(b, g // 4, 16, 16, 16 * nf)
+        self.l3a = mk(b, g // 4, 16, 16, 8 * nf)
+        self.l3 = mk(b, g // 4, 16, 16, 8 * nf)
+        self.f1 = mk(b, 1, 64, 64, 2 * nf)
+        self.f2 = mk(b, 1, 32, 32, 4 * nf)
+        self.f3 = mk(b, 1, 16, 16, 8 * nf)
+
+
+def run_encoder(x, w, bf):
+    """x: SplitTensor ``[B, G, 64, 64, nf]`` chirp features -> (f1, f2, f3) temporal-merged maps."""
+    nf, g = w.nf, w.g
+    ops.conv_gemm(x, pad64(nf), w.l1_w, 2 * nf, kernel=(3, 3, 3), pad=(1, 1, 1), shift=w.l1_shift, out=bf.l1a)
+    run_block(bf.l1a, w.blocks[0], bf.t1, bf.l1)
+    ops.resample_linear(bf.l1, 2 * nf, bf.l2in)
+    run_block(bf.l2in, w.blocks[1], bf.t2, bf.l2a)
+    run_block(bf.l2a, w.blocks[2], bf.t2, bf.l2)
+    ops.resample_linear(bf.l2, 4 * nf, bf.l3in)
+    run_block(bf.l3in, w.blocks[3], bf.t3, bf.l3a)
+    run_block(bf.l3a, w.blocks[4], bf.t3, bf.l3)
+    ops.conv_gemm(bf.l1, 2 * nf, w.merge[0], 2 * nf, kernel=(g, 1, 1), out=bf.f1)
+    ops.conv_gemm(bf.l2, 4 * nf, w.merge[1], 4 * nf, kernel=(g // 2, 1, 1), out=bf.f2)
+    ops.conv_gemm(bf.l3, 8 * nf, w.merge[2], 8 * nf, kernel=(g // 4, 1, 1), out=bf.f3)
+    return bf.f1, bf.f2, bf.f3
+
+
+# ---------------------------------------------------------------------------------------------- decoder (layers.py:72-184)
+PROJ_HORI = ("phi_cross_hori", "theta_cross_hori", "phi_self_hori", "theta_self_hori")
+PROJ_VERT = ("phi_cross_vert", "theta_cross_vert", "phi_self_vert", "theta_self_vert")
+
+
+class DecoderWeights(object):
+    def __init__(self, sd, nf, keypoints, split):
+        p = "radarDecoder."
+        self.nf = nf
+        self.proj_hori, self.proj_vert = [], []
+        for level, c in enumerate((8 * nf, 4 * nf, 2 * nf)):
+            for names, dst in ((PROJ_HORI, self.proj_hori), (PROJ_VERT, self.proj_vert)):
+                ws = [sd[p + "%s.%d.weight" % (n, level)].unsqueeze(2) for n in names]
+                dst.append(pack_conv(ws, c, [c] * 4, split))
+        self.blocks = [pack_block2d(sd, p + "decoderLayer3.0", 32 * nf, 8 * nf, split),
+                       pack_block2d(sd, p + "decoderLayer3.1", 8 * nf, 4 * nf, split),
+                       pack_block2d(sd, p + "decoderLayer2.0", 20 * nf, 4 * nf, split),
+                       pack_block2d(sd, p + "decoderLayer2.1", 4 * nf, 2 * nf, split),
+                       pack_block2d(sd, p + "decoderLayer1.0", 10 * nf, 2 * nf, split),
+                       pack_block2d(sd, p + "decoderLayer1.1", 2 * nf, nf, split)]
+        self.head = pack_conv([sd[p + "decoderLayer1.2.weight"].unsqueeze(2)], pad64(nf), [pad64(keypoints)], split)
+        self.gcn_w = [sd[p + "gcn.L%d.weight" % i].float().contiguous() for i in (1, 2, 3)]
+        self.gcn_b = [sd[p + "gcn.L%d.bias" % i].float().contiguous() for i in (1, 2, 3)]
+
+
+class DecoderBuffers(object):
+    def __init__(self, b, nf, keypoints, dev, split):
+        mk = lambda *shape: SplitTensor.empty(shape, dev, split)
+        self.levels = []
+        for c, hw, prev in ((8 * nf, 16, 0), (4 * nf, 32, 4 * nf), (2 * nf, 64, 2 * nf)):
+            s = hw * hw
+            self.levels.append(dict(c=c, hw=hw, s=s, prev=prev,
+                                    proj_ra=mk(b, 1, 1, s, 4 * c), proj_re=mk(b, 1, 1, s, 4 * c),
+                                    vt_ra=mk(b, c, s), vt_re=mk(b, c, s),
+                                    cat=mk(b, 1, hw, hw, prev + 4 * c)))
+        smax = 64 * 64
+        self.logits = torch.empty(b * smax * smax, dtype=torch.float32, device=dev)
+        self.probs = mk(b * smax * smax)
+        self.t3a, self.o3a = mk(b, 1, 16, 16, 16 * nf), mk(b, 1, 16, 16, 8 * nf)
+        self.t3b, self.o3b = mk(b, 1, 16, 16, 8 * nf), mk(b, 1, 16, 16, 4 * nf)
+        self.t2a, self.o2a = mk(b, 1, 32, 32, 8 * nf), mk(b, 1, 32, 32, 4 * nf)
+        self.t2b, self.o2b = mk(b, 1, 32, 32, 2 * pad64(2 * nf)), mk(b, 1, 32, 32, pad64(2 * nf))
+        self.t1a, self.o1a = mk(b, 1, 64, 64, 2 * pad64(2 * nf)), mk(b, 1, 64, 64, pad64(2 * nf))
+        self.t1b, self.o1b = mk(b, 1, 64, 64, 2 * pad64(nf)), mk(b, 1, 64, 64, pad64(nf))
+        self.logits_out = torch.empty((b, 64 * 64, pad64(keypoints)), dtype=torch.float32, device=dev)
+        self.gcn_ws = torch.empty(max(ops.prgcn_workspace_bytes(b) // 4, 4), dtype=torch.float32, device=dev)
+        self.heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
+        self.gcn_heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
+
+
+def _view(t, shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return SplitTensor(t.hi[:n].view(shape), None if t.lo is None else t.lo[:n].view(shape))
+
+
+def run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, out, o_off, residual):
+    """layers.py:126-133 with Q = q_src[..., q_off:+C], K = k_src[..., k_off:+C], V = v:
+    logits[n, m] = <Q[n], K[m]>;  P = softmax over keys m;  out[n] = sum_m P[n, m] V[m]  (+ V[n] for the cross branches)."""
+    b = v.hi.shape[0]
+    c, s = lv["c"], lv["s"]
+    logits = bf.logits[:b * s * s].view(b, 1, 1, s, s)
+    probs = _view(bf.probs, (b, 1, 1, s, s))
+    ops.conv_gemm(q_src, c, SplitTensor(k_src.hi.view(b, s, 4 * c), None if k_src.lo is None else k_src.lo.view(b, s, 4 * c)), s,
+                  a_ch_off=q_off, w_batched=True, w_ld=4 * c, w_ch_off=k_off, out_f32=logits)
+    ops.softmax_rows(logits, probs)
+    ops.conv_gemm(probs, s, vt, c, w_batched=True, residual=v if residual else None, out=out, o_ch_off=o_off)
+
+
+def run_attention_level(bf, lv, w_hori, w_vert, ra, re):
+    """One scale of the cross/self attention (layers.py:138-149): fills cat[..., prev : prev + 4C] with
+    (ra_cross, ra_self, re_cross, re_self)."""
+    c, prev = lv["c"], lv["prev"]
+    b, hw = ra.hi.shape[0], lv["hw"]
+    ra_s = SplitTensor(ra.hi.view(b, 1, 1, lv["s"], c), None if ra.lo is None else ra.lo.view(b, 1, 1, lv["s"], c))
+    re_s = SplitTensor(re.hi.view(b, 1, 1, lv["s"], c), None if re.lo is None else re.lo.view(b, 1, 1, lv["s"], c))
+    ops.conv_gemm(ra_s, c, w_hori, 4 * c, out=lv["proj_ra"])     # channels: phi_c_hori | theta_c_hori | phi_s_hori | theta_s_hori
+    ops.conv_gemm(re_s, c, w_vert, 4 * c, out=lv["proj_re"])     #           phi_c_vert | theta_c_vert | phi_s_vert | theta_s_vert
+    ops.transpose_split(ra_s, c, lv["vt_ra"])
+    ops.transpose_split(re_s, c, lv["vt_re"])
+    cat = lv["cat"]
+    cat_s = SplitTensor(cat.hi.view(b, 1, 1, lv["s"], prev + 4 * c), None if cat.lo is None else cat.lo.view(b, 1, 1, lv["s"], prev + 4 * c))
+    pra, pre = lv["proj_ra"], lv["proj_re"]
+    # ra_cross: k = phi_c_hori(ra), q = theta_c_vert(re), v = ra, + ra
+    run_attention(bf, lv, pre, c, pra, 0, ra_s, lv["vt_ra"], cat_s, prev, True)
+    # ra_self : k = phi_s_hori(ra), q = theta_s_hori(ra), v = ra
+    run_attention(bf, lv, pra, 3 * c, pra, 2 * c, ra_s, lv["vt_ra"], cat_s, prev + c, False)
+    # re_cross: k = phi_c_vert(re), q = theta_c_hori(ra), v = re, + re
+    run_attention(bf, lv, pra, c, pre, 0, re_s, lv["vt_re"], cat_s, prev + 2 * c, True)
+    # re_self : k = phi_s_vert(re), q = theta_s_vert(re), v = re
+    run_attention(bf, lv, pre, 3 * c, pre, 2 * c, re_s, lv["vt_re"], cat_s, prev + 3 * c, False)
+    return cat
+
+
+def run_decoder(w, bf, feats_ra, feats_re, adj):
+    """feats_* = (f1, f2, f3).  Returns (heatmap, gcn_heatmap) float32 ``[B, 14, 64, 64]``."""
+    nf = w.nf
+    l3, l2, l1 = bf.levels
+    cat3 = run_attention_level(bf, l3, w.proj_hori[0], w.proj_vert[0], feats_ra[2], feats_re[2])
+    run_block(cat3, w.blocks[0], bf.t3a, bf.o3a)
+    run_block(bf.o3a, w.blocks[1], bf.t3b, bf.o3b)
+    ops.resample_linear(bf.o3b, 4 * nf, l2["cat"])
+    cat2 = run_attention_level(bf, l2, w.proj_hori[1], w.proj_vert[1], feats_ra[1], feats_re[1])
+    run_block(cat2, w.blocks[2], bf.t2a, bf.o2a)
+    run_block(bf.o2a, w.blocks[3], bf.t2b, bf.o2b)
+    ops.resample_linear(bf.o2b, 2 * nf, l1["cat"])
+    cat1 = run_attention_level(bf, l1, w.proj_hori[2], w.proj_vert[2], feats_ra[0], feats_re[0])
+    run_block(cat1, w.blocks[4], bf.t1a, bf.o1a)
+    run_block(bf.o1a, w.blocks[5], bf.t1b, bf.o1b)
+    b = bf.o1b.hi.shape[0]
+    ops.conv_gemm(bf.o1b, pad64(nf), w.head, bf.logits_out.shape[-1], out_f32=bf.logits_out.view(b, 1, 64, 64, -1))
+    ops.prgcn_fwd(bf.logits_out, w.gcn_w, w.gcn_b, adj, bf.gcn_ws, bf.heatmap, bf.gcn_heatmap)
+    return bf.heatmap, bf.gcn_heatmap

@@ -41,7 +41,7 @@ class SplitTensor(object):
 
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -59,6 +59,7 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.kd, desc.kh, desc.kw = kernel
     desc.pd, desc.ph, desc.pw = pad
     desc.w_batched = 1 if w_batched else 0
+    desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
     desc.scale, desc.shift, desc.slope = _C.optr(scale), _C.optr(shift), _C.optr(slope)
     if residual is not None:
         desc.r_hi, desc.r_lo = residual.hi.data_ptr(), _C.optr(residual.lo)
@@ -71,3 +72,101 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     with torch.cuda.device(a.hi.device):
         _C.check(_C.lib().hupr_conv_gemm(desc, _C.stream_ptr()), "hupr_conv_gemm")
     return out if out is not None else out_f32
+
+
+def _call(name, *args):
+    _C.check(getattr(_C.lib(), name)(*args), name)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def window_normalize(cube, slot_fs, out=None):
+    """cube complex64 [n_fs,16,64,64,8], slot_fs int32 [n_slots] -> float32 [n_slots, 8, 2, 64, 64, 8] (hupr_window_normalize)."""
+    if cube.dtype != torch.complex64 or not cube.is_contiguous() or slot_fs.dtype != torch.int32:
+        raise TypeError("window_normalize expects a contiguous complex64 cube tensor and int32 slot indices")
+    n_slots = slot_fs.numel()
+    if out is None:
+        out = torch.empty((n_slots, 8, 2, 64, 64, 8), dtype=torch.float32, device=cube.device)
+    with torch.cuda.device(cube.device):
+        _call("hupr_window_normalize", _p(cube), _p(slot_fs), n_slots, _p(out), _C.stream_ptr())
+    return out
+
+
+def mnet_fwd(vrdae, weight, bias, out):
+    """vrdae float32 [..., 8, 2, 64, 64, 8] (n_slots leading elements) -> SplitTensor [n_slots, 64, 64, 32] (hupr_mnet_fwd)."""
+    n_slots = vrdae.numel() // (8 * 2 * 64 * 64 * 8)
+    with torch.cuda.device(vrdae.device):
+        _call("hupr_mnet_fwd", _p(vrdae), _p(weight), _p(bias), _p(out.hi), _p(out.lo), n_slots, _C.stream_ptr())
+    return out
+
+
+def resample_linear(x, c, out, in_ch_off=0, out_ch_off=0):
+    """align_corners=True bi/tri-linear resampling of channels [in_ch_off, +c) of x into channels [out_ch_off, +c) of out."""
+    n, di, hi, wi, ild = x.hi.shape
+    n2, do, ho, wo, old = out.hi.shape
+    with torch.cuda.device(x.hi.device):
+        _call("hupr_resample_linear", _p(x.hi), _p(x.lo), n, di, hi, wi, c, ild, in_ch_off,
+              _p(out.hi), _p(out.lo), do, ho, wo, old, out_ch_off, _C.stream_ptr())
+    return out
+
+
+def softmax_rows(logits, out):
+    """float32 [rows, cols] -> SplitTensor [rows, cols] (softmax along the last axis)."""
+    cols = logits.shape[-1]
+    rows = logits.numel() // cols
+    with torch.cuda.device(logits.device):
+        _call("hupr_softmax_rows", _p(logits), _p(out.hi), _p(out.lo), rows, cols, _C.stream_ptr())
+    return out
+
+
+def transpose_split(x, c, out, in_ch_off=0):
+    """SplitTensor [n, .., s positions .., ld] channels [in_ch_off, +c) -> SplitTensor [n, c, s]."""
+    n, ld = x.hi.shape[0], x.hi.shape[-1]
+    s = x.hi.numel() // (n * ld)
+    with torch.cuda.device(x.hi.device):
+        _call("hupr_transpose_split", _p(x.hi), _p(x.lo), n, s, c, ld, in_ch_off, _p(out.hi), _p(out.lo), _C.stream_ptr())
+    return out
+
+
+def prgcn_workspace_bytes(batch):
+    return int(_C.lib().hupr_prgcn_workspace_bytes(batch))
+
+
+def prgcn_fwd(logits, weights, biases, adj, workspace, heatmap, gcn_heatmap):
+    """logits float32 channels-last [B, 4096, ld] -> heatmap, gcn_heatmap float32 [B, 14, 64, 64] (hupr_prgcn_fwd)."""
+    import ctypes
+    batch, ld = logits.shape[0], logits.shape[-1]
+    wp = (ctypes.c_void_p * 3)(*[w.data_ptr() for w in weights])
+    bp = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in biases])
+    with torch.cuda.device(logits.device):
+        _call("hupr_prgcn_fwd", _p(logits), ld, wp, bp, _p(adj), _p(workspace), workspace.numel() * workspace.element_size(),
+              _p(heatmap), _p(gcn_heatmap), batch, _C.stream_ptr())
+    return heatmap, gcn_heatmap
+
+
+def keypoints_argmax(maps, preds=None, maxvals=None):
+    """float32 [..., 64, 64] -> float32 [..., 2] (x, y) of the first maximum (hupr_keypoints_argmax)."""
+    lead = maps.shape[:-2]
+    n_maps = maps.numel() // 4096
+    if preds is None:
+        preds = torch.empty(tuple(lead) + (2,), dtype=torch.float32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        _call("hupr_keypoints_argmax", _p(maps), n_maps, _p(preds), _p(maxvals), _C.stream_ptr())
+    return preds
+
+
+def heatmap_loss_fwd(heatmap, gcn_heatmap, joints, want_targets=False):
+    """Returns (losses float32 [3] = {loss, loss2, loss1}, gt2d float32 [B,14,2], targets or None) — hupr_heatmap_loss_fwd."""
+    batch = joints.shape[0]
+    dev = heatmap.device
+    joints = joints.to(device=dev, dtype=torch.int64).contiguous()
+    ws = torch.empty(batch * 14 * 2, dtype=torch.float64, device=dev)
+    losses = torch.empty(3, dtype=torch.float32, device=dev)
+    gt2d = torch.empty((batch, 14, 2), dtype=torch.float32, device=dev)
+    targets = torch.empty((batch, 14, 64, 64), dtype=torch.float32, device=dev) if want_targets else None
+    with torch.cuda.device(dev):
+        _call("hupr_heatmap_loss_fwd", _p(heatmap), _p(gcn_heatmap), _p(joints), batch, _p(ws), ws.numel() * 8,
+              _p(losses), _p(targets), _p(gt2d), _C.stream_ptr())
+    return losses, gt2d, targets

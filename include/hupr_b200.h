@@ -58,8 +58,10 @@ int hupr_fft_cascade_i16(const int16_t* adc, void* cube, int n_frame_sensors, vo
  * results (the reference computes in fp32); with a_lo = w_lo = NULL a single bf16 product is used.
  * Filter taps: kd x kh x kw with paddings pd, ph, pw; H and W must be 'same' (k = 2p+1); D_out = D + 2pd - kd + 1.
  * Weights: bf16 [kd*kh*kw][cout][cin] (cin contiguous); with w_batched = 1 (taps must be 1) the first weight dim is the
- * sample index instead (per-sample B operand: the attention matmuls).
- * cin, cout must be multiples of 64 (pad with zero weights / channels); W must divide 128 or be a multiple of 128.
+ * sample index instead (per-sample B operand: the attention matmuls).  With w_ld != 0 the weight rows are w_ld elements apart and
+ * start at column w_ch_off (a channel slice of a wider channels-last tensor used as the B operand).
+ * cin, cout must be multiples of 64 (pad with zero weights); the contracted slice may run up to 63 channels past `ca` —
+ * those channels read as zero (TMA out-of-bounds fill), e.g. ca = 32, cin = 64.  W must divide 128 or be a multiple of 128.
  */
 typedef struct hupr_conv_desc {
     const void* a_hi; const void* a_lo;      /* [n][d][h][w][ca] bf16 */
@@ -73,9 +75,68 @@ typedef struct hupr_conv_desc {
     const void* r_hi; const void* r_lo; int r_ld, r_ch_off;       /* residual [positions][r_ld] bf16 split, may be NULL */
     void* o_hi; void* o_lo; int o_ld, o_ch_off;                   /* bf16 split output [positions][o_ld], may be NULL */
     float* o_f32; int o_f32_ld;                                   /* fp32 output [positions][o_f32_ld], may be NULL */
+    int w_ld, w_ch_off;                                           /* weight row stride / first column in elements (0, 0 = dense [..][cout][cin]) */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loader bridge.  Replaces Normalize.__call__ + the window assembly of HuPR3D_horivert.__getitem__
+ *   /root/reference/datasets/base.py:13-24, /root/reference/datasets/dataset.py:120-150
+ * cube    : float2 [n_frame_sensors][16][64][64][8] (output of hupr_fft_cascade_i16)
+ * slot_fs : int32 [n_slots]  frame-sensor index feeding window slot s = sample*8 + group_frame (the clamped window
+ *           of dataset.py:126-138 is computed by the caller; it is an integer index map)
+ * vrdae   : float [n_slots][8 kept Doppler rows 4..11][2 re,im][64 range][64 azimuth][8 elevation]; every
+ *           (slot, row, re|im, elevation) plane is standardised over its 64x64 cells: (x - mean) / unbiased std.
+ */
+int hupr_window_normalize(const void* cube, const int32_t* slot_fs, int n_slots, float* vrdae, void* stream);
+
+/* Chirp encoder.  Replaces HuPRNet.forward_chirp (one sensor) + MNet.forward
+ *   /root/reference/models/networks.py:23-33, /root/reference/models/chirp_networks.py:11-21
+ * vrdae  : float [n_slots][8][2][64][64][8];  weight: float [32][2][2] (temporalConvWx1x1.weight), bias: float [32]
+ * out    : bf16 split channels-last [n_slots][64][64][32]  (= [B][D=8][H][W][32]); out_lo may be NULL.
+ */
+int hupr_mnet_fwd(const float* vrdae, const float* weight, const float* bias, void* out_hi, void* out_lo, int n_slots, void* stream);
+
+/* Bi/tri-linear resampling with align_corners=True on split channels-last tensors.  Replaces nn.Upsample / F.interpolate
+ *   /root/reference/models/layers.py:84,89,199,204
+ * in  : [n][di][hi][wi][in_ld] channels in_ch_off .. +c ;  out : [n][dout][ho][wo][out_ld] channels out_ch_off .. +c
+ */
+int hupr_resample_linear(const void* in_hi, const void* in_lo, int n, int di, int hi, int wi, int c, int in_ld, int in_ch_off,
+                         void* out_hi, void* out_lo, int dout, int ho, int wo, int out_ld, int out_ch_off, void* stream);
+
+/* Row softmax of the attention logits (/root/reference/models/layers.py:131; rows = queries, columns = keys).
+ * logits: float [rows][cols] -> p: bf16 split [rows][cols]; cols multiple of 4, <= 4096. */
+int hupr_softmax_rows(const float* logits, void* p_hi, void* p_lo, long long rows, int cols, void* stream);
+
+/* [n][s][in_ld](channels in_ch_off..+c) -> [n][c][s]: V operand of the second attention matmul (layers.py:132). */
+int hupr_transpose_split(const void* in_hi, const void* in_lo, int n, int s, int c, int in_ld, int in_ch_off,
+                         void* out_hi, void* out_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heatmap head + pose-refinement GCN.  Replaces PRGCN.forward and the final sigmoid of HuPRNet.forward
+ *   /root/reference/models/gcn_networks.py:6-64, /root/reference/models/layers.py:97-112, /root/reference/models/networks.py:40
+ * logits      : float channels-last [batch][64*64][ld], first 14 channels are the keypoint logits
+ * weights[l]  : float [1024][1024] (gcn.L{1,2,3}.weight), biases[l]: float [1024][14]; adj: float [14][14]
+ * heatmap     : float [batch][14][64][64] = sigmoid(logits);  gcn_heatmap: float [batch][14][64][64]
+ * workspace   : hupr_prgcn_workspace_bytes(batch) bytes, 16-B aligned.  weights/biases are HOST arrays of 3 device pointers.
+ */
+size_t hupr_prgcn_workspace_bytes(int batch);
+int hupr_prgcn_fwd(const float* logits, int ld, const float* const* weights, const float* const* biases, const float* adj,
+                   void* workspace, size_t ws_bytes, float* heatmap, float* gcn_heatmap, int batch, void* stream);
+
+/* Keypoint decode.  Replaces get_max_preds (/root/reference/misc/metrics.py:10-38).
+ * maps: float [n_maps][64*64] -> preds float [n_maps][2] = (x, y) of the first maximum, zeroed where max <= 0; maxvals may be NULL. */
+int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds, float* maxvals, void* stream);
+
+/* Heatmap loss.  Replaces LossComputer.computeLoss + generateTarget
+ *   /root/reference/misc/losses.py:23-48, /root/reference/misc/utils.py:6-65
+ * heatmap, gcn_heatmap: float [batch][14][64][64] (post-sigmoid); joints: int64 [batch][14][2] image pixels (256-px frame)
+ * losses : float [3] = {loss1 + loss2, loss2, loss1} (mean BCE, logs clamped at -100)
+ * targets: optional float [batch][14][64][64] Gaussian targets; gt2d: optional float [batch][14][2] target argmax (x, y)
+ * workspace: batch*14*2 doubles. */
+int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch,
+                          void* workspace, size_t ws_bytes, float* losses, float* targets, float* gt2d, void* stream);
 
 #ifdef __cplusplus
 }
