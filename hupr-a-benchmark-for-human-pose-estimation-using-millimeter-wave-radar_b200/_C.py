@@ -29,6 +29,18 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class AttnDesc(ctypes.Structure):
+    """Mirror of ``hupr_attn_desc``."""
+    _fields_ = [
+        ("q_hi", ctypes.c_void_p), ("q_lo", ctypes.c_void_p), ("q_ld", ctypes.c_int), ("q_off", ctypes.c_int),
+        ("k_hi", ctypes.c_void_p), ("k_lo", ctypes.c_void_p), ("k_ld", ctypes.c_int), ("k_off", ctypes.c_int),
+        ("vt_hi", ctypes.c_void_p), ("vt_lo", ctypes.c_void_p),
+        ("r_hi", ctypes.c_void_p), ("r_lo", ctypes.c_void_p), ("r_ld", ctypes.c_int), ("r_off", ctypes.c_int),
+        ("o_hi", ctypes.c_void_p), ("o_lo", ctypes.c_void_p), ("o_ld", ctypes.c_int), ("o_off", ctypes.c_int),
+        ("batch", ctypes.c_int), ("s", ctypes.c_int), ("c", ctypes.c_int),
+    ]
+
+
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 
@@ -36,8 +48,10 @@ _I = ctypes.c_int
 SIGNATURES = {
     "hupr_version": (ctypes.c_int, []),
     "hupr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "hupr_launch_count": (ctypes.c_longlong, []),
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
+    "hupr_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttnDesc), ctypes.c_void_p]),
     "hupr_window_normalize": (ctypes.c_int, [_P, _P, _I, _P, _P]),
     "hupr_mnet_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "hupr_resample_linear": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -257,7 +257,10 @@ static int check_sm100() {
     return cached;
 }
 
-static inline int launch_status() { return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA; }
+static inline int launch_status(int n = 1) {
+    note_launches(n);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
 
 }  // namespace hupr
 
@@ -333,5 +336,5 @@ extern "C" int hupr_transpose_split(const void* in_hi, const void* in_lo, int n,
     const dim3 grid(s / 32, c / 32, n), block(32, 8);
     transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_hi, (uint16_t*)out_hi, s, c, in_ld, in_ch_off);
     if (in_lo) transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
-    return launch_status();
+    return launch_status(in_lo ? 2 : 1);
 }

@@ -1,5 +1,15 @@
 // Miscellaneous C-ABI entry points (version, error strings).
+#include <atomic>
+
 #include "common.cuh"
+
+static std::atomic<long long> g_launches{0};
+
+namespace hupr {
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace hupr
+
+extern "C" long long hupr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int hupr_version(void) { return 100; }
 

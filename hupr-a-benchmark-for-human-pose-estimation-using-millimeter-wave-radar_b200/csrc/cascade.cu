@@ -322,5 +322,6 @@ extern "C" int hupr_fft_cascade_i16(const int16_t* adc, void* cube, int n_frame_
     if (clusters > n_frame_sensors) clusters = n_frame_sensors;
     cascade_kernel<<<2 * clusters, kCascadeThreads, SM_CASCADE_TOTAL, static_cast<cudaStream_t>(stream)>>>(
         adc, static_cast<float2*>(cube), n_frame_sensors);
+    note_launches(1);
     return (cudaGetLastError() == cudaSuccess) ? HUPR_OK : HUPR_ERR_CUDA;
 }

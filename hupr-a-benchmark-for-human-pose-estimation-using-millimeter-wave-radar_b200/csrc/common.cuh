@@ -15,6 +15,8 @@
 
 namespace hupr {
 
+void note_launches(int n);   // capi.cu: kernel-launch counter behind hupr_launch_count()
+
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

@@ -306,6 +306,7 @@ extern "C" int hupr_prgcn_fwd(const float* logits, int ld, const float* const* w
     gcn_layer_kernel<<<grid, 128, 0, s>>>(weights[1], buf1, biases[1], adj, buf0, ncol, 1, 1);
     gcn_layer_kernel<<<grid, 128, 0, s>>>(weights[2], buf0, biases[2], adj, buf1, ncol, 0, 0);
     gcn_post_kernel<<<(batch * kJ * 4096 + 255) / 256, 256, 0, s>>>(buf1, ncol, gcn_heatmap, batch);
+    note_launches(5);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
@@ -316,6 +317,7 @@ extern "C" int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds
     int rc = heads_check_sm100();
     if (rc != HUPR_OK) return rc;
     argmax_kernel<<<n_maps, 256, 0, (cudaStream_t)stream>>>(maps, preds, maxvals);
+    note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
@@ -332,5 +334,6 @@ extern "C" int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heat
     cudaStream_t s = (cudaStream_t)stream;
     loss_partial_kernel<<<maps, 256, 0, s>>>(heatmap, gcn_heatmap, joints, static_cast<double*>(workspace), targets, gt2d);
     loss_final_kernel<<<1, 256, 0, s>>>(static_cast<const double*>(workspace), maps, losses);
+    note_launches(2);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

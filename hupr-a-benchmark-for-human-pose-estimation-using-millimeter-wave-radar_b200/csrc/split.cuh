@@ -9,12 +9,13 @@ __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bflo
 __device__ __forceinline__ float bf16_lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
-// Split two floats into packed (hi, lo) bf16x2 words: element 0 in the low half.
+// Split two floats into packed (hi, lo) bf16x2 words: element 0 in the low half (one cvt.rn.bf16x2.f32 per plane).
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const uint32_t ha = bf16_bits(a), hb = bf16_bits(b);
-    const float ra = a - __uint_as_float(ha << 16), rb = b - __uint_as_float(hb << 16);
-    hi = ha | (hb << 16);
-    lo = bf16_bits(ra) | (bf16_bits(rb) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // 8 channels (16 B of hi + 16 B of lo) -> 8 floats.  lo may be null (single-bf16 tensors).

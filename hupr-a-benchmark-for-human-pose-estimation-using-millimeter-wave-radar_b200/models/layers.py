@@ -170,7 +170,7 @@ class DecoderBuffers(object):
                                     proj_ra=mk(b, 1, 1, s, 4 * c), proj_re=mk(b, 1, 1, s, 4 * c),
                                     vt_ra=mk(b, c, s), vt_re=mk(b, c, s),
                                     cat=mk(b, 1, hw, hw, prev + 4 * c)))
-        smax = 64 * 64
+        smax = 64 * 64 if not split else 32 * 32      # level 1 (S = 4096) runs fused when split; scratch covers the unfused levels
         self.logits = torch.empty(b * smax * smax, dtype=torch.float32, device=dev)
         self.probs = mk(b * smax * smax)
         self.t3a, self.o3a = mk(b, 1, 16, 16, 16 * nf), mk(b, 1, 16, 16, 8 * nf)
@@ -197,6 +197,9 @@ def run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, out, o_off, residua
     logits[n, m] = <Q[n], K[m]>;  P = softmax over keys m;  out[n] = sum_m P[n, m] V[m]  (+ V[n] for the cross branches)."""
     b = v.hi.shape[0]
     c, s = lv["c"], lv["s"]
+    if c == 64 and v.lo is not None:      # fused flash-style kernel (level 1: S = 4096, 88 % of the attention FLOPs)
+        ops.attention_fwd(q_src, q_off, k_src, k_off, vt, c, out, o_off, residual=v if residual else None)
+        return
     logits = bf.logits[:b * s * s].view(b, 1, 1, s, s)
     probs = _view(bf.probs, (b, 1, 1, s, s))
     ops.conv_gemm(q_src, c, SplitTensor(k_src.hi.view(b, s, 4 * c), None if k_src.lo is None else k_src.lo.view(b, s, 4 * c)), s,

@@ -2,7 +2,37 @@
 memory and streams; every arithmetic op here is a call into libhupr_b200.so."""
 import torch
 
+import contextlib
+
 from . import _C
+
+_PROFILE = None     # list of [name, flops, start_event, stop_event] while a profile is being recorded
+
+
+def profile_begin():
+    """Start recording one (name, algorithmic FLOPs, CUDA-event duration) entry per library call (bench.py's breakdown)."""
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end():
+    """Stop recording; returns ``[(name, flops, milliseconds), ...]`` in call order."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return [(name, flops, start.elapsed_time(stop)) for name, flops, start, stop in rec]
+
+
+@contextlib.contextmanager
+def _timed(name, flops=0):
+    if _PROFILE is None:
+        yield
+        return
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    yield
+    stop.record()
+    _PROFILE.append([name, flops, start, stop])
 
 
 class SplitTensor(object):
@@ -69,13 +99,39 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
         desc.o_ld, desc.o_ch_off = out.hi.shape[-1], o_ch_off
     if out_f32 is not None:
         desc.o_f32, desc.o_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
-    with torch.cuda.device(a.hi.device):
+    d_out = d + 2 * pad[0] - kernel[0] + 1
+    flops = 2.0 * n * d_out * h * w * cout * cin * kernel[0] * kernel[1] * kernel[2]
+    tag = "conv_gemm.%s" % ("attn" if w_batched else ("k%dx%dx%d" % tuple(kernel)))
+    with torch.cuda.device(a.hi.device), _timed(tag, flops):
         _C.check(_C.lib().hupr_conv_gemm(desc, _C.stream_ptr()), "hupr_conv_gemm")
     return out if out is not None else out_f32
 
 
+def attention_fwd(q, q_off, k, k_off, vt, c, out, o_off, residual=None, r_off=0):
+    """Fused attention (hupr_attention_fwd): q, k SplitTensors ``[B, .., S, ld]``, vt ``[B, c, S]``, out ``[B, .., S, ld_o]``."""
+    b = q.hi.shape[0]
+    s = vt.hi.shape[-1]
+    desc = _C.AttnDesc()
+    desc.q_hi, desc.q_lo, desc.q_ld, desc.q_off = q.hi.data_ptr(), _C.optr(q.lo), q.hi.shape[-1], q_off
+    desc.k_hi, desc.k_lo, desc.k_ld, desc.k_off = k.hi.data_ptr(), _C.optr(k.lo), k.hi.shape[-1], k_off
+    desc.vt_hi, desc.vt_lo = vt.hi.data_ptr(), _C.optr(vt.lo)
+    if residual is not None:
+        desc.r_hi, desc.r_lo, desc.r_ld, desc.r_off = residual.hi.data_ptr(), _C.optr(residual.lo), residual.hi.shape[-1], r_off
+    desc.o_hi, desc.o_lo, desc.o_ld, desc.o_off = out.hi.data_ptr(), _C.optr(out.lo), out.hi.shape[-1], o_off
+    desc.batch, desc.s, desc.c = b, s, c
+    with torch.cuda.device(q.hi.device), _timed("attention_fwd", 4.0 * b * s * s * c):
+        _C.check(_C.lib().hupr_attention_fwd(desc, _C.stream_ptr()), "hupr_attention_fwd")
+    return out
+
+
+def launch_count():
+    """Kernels launched by libhupr_b200.so in this process so far (hupr_launch_count)."""
+    return int(_C.lib().hupr_launch_count())
+
+
 def _call(name, *args):
-    _C.check(getattr(_C.lib(), name)(*args), name)
+    with _timed(name[5:]):
+        _C.check(getattr(_C.lib(), name)(*args), name)
 
 
 def _p(t):

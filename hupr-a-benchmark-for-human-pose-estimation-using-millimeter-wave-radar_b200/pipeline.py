@@ -1,0 +1,87 @@
+"""End-to-end radar -> pose stream on one B200: DCA1000 int16 words -> FFT cascade -> window/standardise -> HuPRNet ->
+argmax keypoints, with every intermediate resident in HBM and the whole step replayed as one CUDA graph.
+
+This is the composition the reference spreads over two programs and the file system
+(/root/reference/preprocessing/process_iwr1843.py:184-196 -> .npy files -> datasets/dataset.py:120-159 ->
+tools/run.py:35-58); the arithmetic of each stage is unchanged, only the hand-offs stay on the device.
+"""
+import torch
+
+from . import ops
+from .preprocessing.process_iwr1843 import FRAME_WORDS, cascade_i16
+
+GROUP = 8
+
+
+def window_slots(n_windows, n_frames, first_cube=0, group=GROUP):
+    """Cube index per window slot for a contiguous stream: window b covers frames b .. b+group-1 (centre frame b + group/2,
+    i.e. the reference window [index-4, index+3] of dataset.py:126-138 away from the capture boundaries)."""
+    if n_windows + group - 1 > n_frames:
+        raise ValueError("%d windows need %d frames, got %d" % (n_windows, n_windows + group - 1, n_frames))
+    b = torch.arange(n_windows, dtype=torch.int32).view(-1, 1)
+    g = torch.arange(group, dtype=torch.int32).view(1, -1)
+    return (first_cube + b + g).reshape(-1).contiguous()
+
+
+class RadarPoseStream(object):
+    """Fixed-shape streaming step: ``n_windows`` poses from ``n_windows + 7`` consecutive radar frames (hori + vert)."""
+
+    def __init__(self, model, n_windows, device="cuda", use_graph=True):
+        self.model = model
+        self.n_windows = n_windows
+        self.n_frames = n_windows + GROUP - 1
+        self.device = torch.device(device)
+        dev = self.device
+        nfs = 2 * self.n_frames
+        self.adc = torch.zeros((nfs, FRAME_WORDS), dtype=torch.int16, device=dev)          # [hori frames | vert frames]
+        self.cubes = torch.empty((nfs, 16, 64, 64, 8), dtype=torch.complex64, device=dev)
+        self.slots_hori = window_slots(n_windows, self.n_frames, 0).to(dev)
+        self.slots_vert = window_slots(n_windows, self.n_frames, self.n_frames).to(dev)
+        self.vrdae_hori = torch.empty((n_windows, GROUP, 8, 2, 64, 64, 8), dtype=torch.float32, device=dev)
+        self.vrdae_vert = torch.empty_like(self.vrdae_hori)
+        self.keypoints = torch.empty((n_windows, 14, 2), dtype=torch.float32, device=dev)
+        self.maxvals = torch.empty((n_windows, 14), dtype=torch.float32, device=dev)
+        self.heatmap = None
+        self.gcn_heatmap = None
+        self.launches_per_step = 0
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _step_eager(self):
+        cascade_i16(self.adc, self.cubes)
+        ops.window_normalize(self.cubes, self.slots_hori, self.vrdae_hori)
+        ops.window_normalize(self.cubes, self.slots_vert, self.vrdae_vert)
+        heat, gcn = self.model(self.vrdae_hori, self.vrdae_vert)
+        self.heatmap, self.gcn_heatmap = heat, gcn
+        ops.keypoints_argmax(gcn.view(self.n_windows, 14, 64, 64), self.keypoints, self.maxvals)
+
+    def prepare(self):
+        """Warm up (lazy weight packing, function attributes) and capture the step into a CUDA graph."""
+        with torch.cuda.device(self.device):
+            self._step_eager()
+            before = ops.launch_count()
+            self._step_eager()
+            self.launches_per_step = ops.launch_count() - before
+            torch.cuda.synchronize()
+            if self.use_graph:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step_eager()
+                self.graph = graph
+                torch.cuda.synchronize()
+        return self
+
+    def step(self):
+        """Run one step on the current contents of ``self.adc``; results land in ``self.keypoints`` (device)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_eager()
+        return self.keypoints
+
+    def __call__(self, adc_hori, adc_vert):
+        """adc_hori / adc_vert: int16 ``[n_frames, FRAME_WORDS]`` (host pinned or device) -> keypoints ``[n_windows, 14, 2]`` (device)."""
+        n = self.n_frames
+        self.adc[:n].copy_(adc_hori.view(n, FRAME_WORDS), non_blocking=True)
+        self.adc[n:].copy_(adc_vert.view(n, FRAME_WORDS), non_blocking=True)
+        return self.step()

@@ -43,7 +43,8 @@ def cascade_i16(adc, out=None):
         out = torch.empty((n,) + CUBE_SHAPE, dtype=torch.complex64, device=adc.device)
     elif out.dtype != torch.complex64 or out.numel() != n * 16 * 64 * 64 * 8 or not out.is_contiguous():
         raise ValueError("out must be a contiguous complex64 tensor [n,16,64,64,8]")
-    with torch.cuda.device(adc.device):
+    from .. import ops
+    with torch.cuda.device(adc.device), ops._timed("fft_cascade_i16"):
         _C.check(_C.lib().hupr_fft_cascade_i16(_C.ptr(adc), _C.ptr(out), n, _C.stream_ptr()),
                  "hupr_fft_cascade_i16")
     return out

@@ -30,6 +30,9 @@ extern "C" {
 /* Library version: major*10000 + minor*100 + patch. */
 int hupr_version(void);
 
+/* Number of kernels this library has launched in the calling process (all entry points, all streams). */
+long long hupr_launch_count(void);
+
 /* Human-readable text for an error code (static storage). */
 const char* hupr_error_string(int code);
 
@@ -79,6 +82,27 @@ typedef struct hupr_conv_desc {
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused spatial attention (flash-style: the [S, S] logits never leave the SM).  Replaces
+ * MultiScaleCrossSelfAttentionPRGCN.attention  /root/reference/models/layers.py:126-133 (+ the residual add of :146,148)
+ *   out[b, n, :] = sum_m softmax_m( <Q[b, n, :], K[b, m, :]> ) * V[b, m, :]  (+ R[b, n, :])        no 1/sqrt(d) scale
+ * q, k : bf16 split, rows [batch][s][q_ld | k_ld], the c contracted channels start at q_off | k_off
+ * vt   : bf16 split [batch][c][s]  (V transposed: hupr_transpose_split)
+ * r    : optional residual rows [batch][s][r_ld] at r_off;  o: output rows [batch][s][o_ld] at o_off (bf16 split)
+ * Supported: c == 64, s a multiple of 128, all four lo planes present (other shapes: HUPR_ERR_BAD_ARG — compose
+ * hupr_conv_gemm(w_batched) + hupr_softmax_rows instead).
+ */
+typedef struct hupr_attn_desc {
+    const void* q_hi; const void* q_lo; int q_ld, q_off;
+    const void* k_hi; const void* k_lo; int k_ld, k_off;
+    const void* vt_hi; const void* vt_lo;
+    const void* r_hi; const void* r_lo; int r_ld, r_off;
+    void* o_hi; void* o_lo; int o_ld, o_off;
+    int batch, s, c;
+} hupr_attn_desc;
+
+int hupr_attention_fwd(const hupr_attn_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Loader bridge.  Replaces Normalize.__call__ + the window assembly of HuPR3D_horivert.__getitem__

@@ -219,3 +219,32 @@ def test_forward_requires_eval_and_cuda():
     net = HuPRNet(make_cfg())
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 8, 8, 2, 64, 64, 8), torch.zeros(1, 8, 8, 2, 64, 64, 8))
+
+
+@pytest.mark.parametrize("batch,s,residual", [(1, 128, False), (2, 512, True), (1, 4096, True)])
+def test_fused_attention_matches_torch(batch, s, residual):
+    """hupr_attention_fwd vs softmax(QK^T)V in float64; logits are un-scaled and large (|logit| up to ~60) like the network's."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    torch.manual_seed(7)
+    c = 64
+    proj_q = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * 1.5
+    proj_k = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * 1.5
+    v = torch.randn(batch, 1, 1, s, c, device="cuda")
+    PQ, PK, V = SplitTensor.from_float(proj_q), SplitTensor.from_float(proj_k), SplitTensor.from_float(v)
+    VT = SplitTensor.empty((batch, c, s), "cuda")
+    ops.transpose_split(V, c, VT)
+    out = SplitTensor.empty((batch, 1, 1, s, 3 * c), "cuda", zero=True)
+    ops.attention_fwd(PQ, 3 * c, PK, 2 * c, VT, c, out, c, residual=V if residual else None)
+    torch.cuda.synchronize()
+    q = PQ.float()[:, 0, 0, :, 3 * c:].double()
+    k = PK.float()[:, 0, 0, :, 2 * c:3 * c].double()
+    vv = V.float()[:, 0, 0].double()
+    ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ vv
+    if residual:
+        ref = ref + vv
+    got = out.float()[:, 0, 0]
+    err = rel_err(got[..., c:2 * c], ref)
+    print("fused attention rel err %.3g" % err)
+    assert err < 1e-4      # logits have std ~18 here: their 2^-17-relative product error shows up as a relative error of P
+    assert not got[..., :c].any() and not got[..., 2 * c:].any()

@@ -1,0 +1,33 @@
+"""Small driver for ncu captures of the two tensor-core kernels (run under `ncu --set full -k regex:... -c 1`)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hupr_b200 import ops
+from hupr_b200.ops import SplitTensor
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+b = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+torch.manual_seed(0)
+if which in ("conv128", "all"):
+    x = SplitTensor.from_float(torch.randn(b, 8, 64, 64, 64, device="cuda"))
+    w = SplitTensor.from_float(torch.randn(27, 128, 64, device="cuda") * 0.02)
+    out = SplitTensor.empty((b, 8, 64, 64, 128), "cuda")
+    for _ in range(3):
+        ops.conv_gemm(x, 64, w, 128, kernel=(3, 3, 3), pad=(1, 1, 1), out=out)
+if which in ("conv64", "all"):
+    x = SplitTensor.from_float(torch.randn(b, 8, 64, 64, 128, device="cuda"))
+    w = SplitTensor.from_float(torch.randn(27, 64, 64, device="cuda") * 0.02)
+    out = SplitTensor.empty((b, 8, 64, 64, 64), "cuda")
+    for _ in range(3):
+        ops.conv_gemm(x, 64, w, 64, kernel=(3, 3, 3), pad=(1, 1, 1), residual=x, r_ch_off=64, out=out)
+if which in ("attn", "all"):
+    s, c = 4096, 64
+    pq = SplitTensor.from_float(torch.randn(b, 1, 1, s, 4 * c, device="cuda"))
+    v = SplitTensor.from_float(torch.randn(b, 1, 1, s, c, device="cuda"))
+    vt = SplitTensor.empty((b, c, s), "cuda")
+    ops.transpose_split(v, c, vt)
+    out = SplitTensor.empty((b, 1, 1, s, 4 * c), "cuda")
+    for _ in range(3):
+        ops.attention_fwd(pq, c, pq, 0, vt, c, out, 0, residual=v)
+torch.cuda.synchronize()
+print("done")
