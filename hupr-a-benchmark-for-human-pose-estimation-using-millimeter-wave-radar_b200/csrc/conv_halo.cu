@@ -1,0 +1,256 @@
+// 3-tap-in-H implicit-GEMM convolution with halo reuse (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same contract as conv_gemm.cu (hupr_conv_gemm dispatches here for kh == 3 split-bf16 convolutions, i.e. every 3x3x3
+// Conv3d and 3x3 Conv2d of MSCSA-PRGCN, /root/reference/models/layers.py:24-32,45-63).  The generic kernel re-reads the
+// activation tile once per filter tap and the weight tile once per 128 output rows; at ~85 B/cycle/SM of operand traffic
+// that saturates the L2 -> SM path (ncu: tensor pipe 38 % active).  This kernel halves the traffic per FLOP:
+//   * one CTA owns 256 output positions (bh x bw, two 128-row TMEM accumulators) so every weight tile feeds two MMAs;
+//   * for each (kd, kw, 32-channel block) ONE activation box of bh+2 rows is loaded; the three kh taps of both
+//     accumulators are sub-views of it (start address + kh*bw rows — legal because bw*64 B is a multiple of the swizzle
+//     atom), i.e. 6 tile-taps per load instead of 1;
+//   * k-blocks are 32 channels (64-byte rows, SWIZZLE_64B) so that a stage (halo box + 3 weight tiles, hi and lo planes)
+//     stays under 96 KiB and two to three stages fit.
+// Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
+#include "tc.cuh"
+#include "conv_common.cuh"
+
+namespace hupr {
+
+constexpr int HK = 32;             // channels per k-block (64-byte swizzled rows)
+constexpr int HM = 256;            // output positions per CTA
+constexpr int kHaloThreads = 192;
+
+struct HaloGeom {
+    int halo_rows;                 // (bh + 2) * bw
+    int a_plane_bytes;             // halo_rows * 64
+    int b_tile_bytes;              // BN * 64
+    int stage_bytes;               // 2 * a_plane_bytes + 6 * b_tile_bytes
+    int stages;
+    int tap_stride_bytes;          // bw * 64: one h-row of the halo
+    int acc_stride_bytes;          // (bh / 2) * bw * 64: first row of accumulator 1
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: 8 rows * 64 B
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p,
+                 const HaloGeom g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + 4;
+    uint64_t* accum_full = bars + 8;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    int t = blockIdx.x;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int od = t % p.d_out;
+    const int n = t / p.d_out;
+    const int h0 = th * p.bh;
+    const int n0 = blockIdx.y * BN;
+    const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        fence_mbar_init();
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int gi = 0; gi < groups; ++gi) {
+                const int s = gi % g.stages;
+                const uint32_t ph = (uint32_t)(gi / g.stages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                const int cb = gi % p.cin_blocks;
+                const int tkw = (gi / p.cin_blocks) % p.kw, tkd = gi / (p.cin_blocks * p.kw);
+                uint8_t* st = smem + s * g.stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
+                const int ac = p.a_ch_off + cb * HK;
+                tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                uint8_t* sb = st + 2 * g.a_plane_bytes;
+#pragma unroll
+                for (int tkh = 0; tkh < 3; ++tkh) {
+                    const int tap = (tkd * 3 + tkh) * p.kw + tkw;
+                    tma_load_3d(sb + tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
+                    tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int gi = 0; gi < groups; ++gi) {
+                const int s = gi % g.stages;
+                const uint32_t ph = (uint32_t)(gi / g.stages) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * g.stage_bytes);
+                const uint32_t sb = st + 2 * g.a_plane_bytes;
+#pragma unroll
+                for (int tkh = 0; tkh < 3; ++tkh) {
+                    const uint64_t db_hi = make_smem_desc_sw64(sb + tkh * g.b_tile_bytes);
+                    const uint64_t db_lo = make_smem_desc_sw64(sb + (3 + tkh) * g.b_tile_bytes);
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
+                        const uint64_t da_hi = make_smem_desc_sw64(st + aoff);
+                        const uint64_t da_lo = make_smem_desc_sw64(st + g.a_plane_bytes + aoff);
+                        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+#pragma unroll
+                        for (int k = 0; k < HK / 16; ++k) {
+                            const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
+                            umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, (gi | tkh | k) != 0);
+                            umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                            umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                        }
+                    }
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(accum_full);
+        }
+    } else {
+        // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31, accumulator 0 then 1 =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = 0; a < 2; ++a) {
+            const int ow = row % p.bw, oh = h0 + a * (p.bh / 2) + row / p.bw;
+            const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), acc);
+                conv_epilogue32(p, acc, pos, n0 + c * 32);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    }
+}
+
+static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return HUPR_ERR_CUDA;
+    cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2, (cuuint64_t)d * h * w * ca * 2};
+    cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bw, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int taps, int bn, int ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return HUPR_ERR_CUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)cout * ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)HK, (cuuint32_t)bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem_max = 232448;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) return HUPR_ERR_CUDA;
+        configured = true;
+    }
+    const int smem = g.stages * g.stage_bytes + 1024 + 256;
+    if (smem > smem_max) return HUPR_ERR_BAD_ARG;
+    dim3 grid(m_tiles, p.cout / BN, 1);
+    conv_halo_kernel<BN><<<grid, kHaloThreads, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p, g);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+// Returns HUPR_OK after launching, or a positive value (1) if the shape is not handled here (caller falls through to the
+// generic kernel).  Arguments were validated by hupr_conv_gemm.
+int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream) {
+    if (d->a_lo == nullptr || d->w_batched) return 1;
+    if (d->kh != 3 || d->ph != 1 || d->kw != 2 * d->pw + 1) return 1;
+    if (d->w != 16 && d->w != 32 && d->w != 64) return 1;
+    const int bw = d->w, bh = HM / bw;
+    if (d->h % bh) return 1;
+    const int d_out = base.d_out;
+    const int m_tiles = d->n * d_out * (d->h / bh);
+    const int bn = (d->cout % 128 == 0) ? 128 : 64;
+    if (m_tiles * (d->cout / bn) < 120) return 1;      // too few CTAs to fill the machine: the 128-row generic tiles spread wider
+    // contracted channels actually present in memory (the generic kernel lets cin run past ca into zero fill)
+    int cin_eff = d->cin;
+    if (d->a_ch_off + cin_eff > d->ca) cin_eff = d->ca - d->a_ch_off;
+    if (cin_eff <= 0 || cin_eff % HK) return 1;
+
+    ConvParams p = base;
+    p.bw = bw; p.bh = bh; p.tiles_w = 1; p.tiles_h = d->h / bh;
+    p.cin_blocks = cin_eff / HK;
+    HaloGeom g;
+    g.halo_rows = (bh + 2) * bw;
+    g.a_plane_bytes = g.halo_rows * 64;
+    g.b_tile_bytes = bn * 64;
+    g.stage_bytes = 2 * g.a_plane_bytes + 6 * g.b_tile_bytes;
+    g.stages = (232448 - 1024 - 256) / g.stage_bytes;
+    if (g.stages > 4) g.stages = 4;
+    if (g.stages < 2) return 1;
+    g.tap_stride_bytes = bw * 64;
+    g.acc_stride_bytes = (bh / 2) * bw * 64;
+    if (g.a_plane_bytes % 1024 || g.b_tile_bytes % 1024) return 1;
+
+    const int taps = d->kd * d->kh * d->kw;
+    const int w_ld = d->w_ld ? d->w_ld : d->cin;
+    const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
+    const __nv_bfloat16* w_lo = static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
+    return bn == 128 ? launch_halo<128>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
+                     : launch_halo<64>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
+}
+
+}  // namespace hupr

@@ -61,6 +61,13 @@ def test_plain_gemm_split(m, n, k):
     (1, 320, 64, 1, 64, 64, (1, 3, 3), (0, 1, 1)),      # decoder 2-D conv
     (1, 64, 32, 1, 64, 64, (1, 3, 3), (0, 1, 1)),       # Cout padded 32 -> 64
     (2, 256, 256, 1, 16, 16, (1, 1, 1), (0, 0, 0)),     # 1x1 projection
+    # shapes large enough for the halo-reuse kernel (conv_halo.cu: >= 120 CTAs of 256 positions), all three widths
+    (2, 64, 128, 8, 64, 64, (3, 3, 3), (1, 1, 1)),
+    (3, 64, 64, 8, 64, 64, (3, 3, 3), (1, 1, 1)),
+    (8, 64, 128, 4, 32, 32, (3, 3, 3), (1, 1, 1)),
+    (32, 128, 256, 2, 16, 16, (3, 3, 3), (1, 1, 1)),
+    (8, 320, 64, 1, 64, 64, (1, 3, 3), (0, 1, 1)),
+    (8, 96, 64, 1, 64, 64, (1, 3, 3), (0, 1, 1)),       # cin a multiple of 32 only
 ])
 def test_conv_matches_torch(shape):
     from hupr_b200.ops import SplitTensor, conv_gemm
@@ -69,11 +76,13 @@ def test_conv_matches_torch(shape):
     x = torch.randn(n, cin, d, h, w, device="cuda")
     wt = torch.randn(cout, cin, *kernel, device="cuda") / (cin * kernel[0] * kernel[1] * kernel[2]) ** 0.5
     cin_p, cout_p = -(-cin // 64) * 64, -(-cout // 64) * 64
+    if cin == 96:
+        cin_p = 96
     A = SplitTensor.from_float(to_cl(x, cin_p))
-    W = pack_weight(wt, cin_p, cout_p)
+    W = pack_weight(wt, -(-cin_p // 64) * 64, cout_p)
     d_out = d + 2 * pad[0] - kernel[0] + 1
     out = SplitTensor.empty((n, d_out, h, w, cout_p), "cuda")
-    conv_gemm(A, cin_p, W, cout_p, kernel=kernel, pad=pad, out=out)
+    conv_gemm(A, -(-cin_p // 64) * 64, W, cout_p, kernel=kernel, pad=pad, out=out)
     torch.cuda.synchronize()
     ref = F.conv3d(x.double(), wt.double(), padding=pad).float()
     got = out.float()[..., :cout].permute(0, 4, 1, 2, 3)
@@ -81,10 +90,11 @@ def test_conv_matches_torch(shape):
     assert not out.float()[..., cout:].any()
 
 
-def test_fused_epilogue_scale_shift_residual_slope_and_channel_offsets():
+@pytest.mark.parametrize("n,d,h,w", [(1, 2, 16, 16), (4, 4, 64, 64)])     # generic kernel / halo-reuse kernel
+def test_fused_epilogue_scale_shift_residual_slope_and_channel_offsets(n, d, h, w):
     from hupr_b200.ops import SplitTensor, conv_gemm
     torch.manual_seed(2)
-    n, cin, cout, d, h, w = 1, 64, 128, 2, 16, 16
+    cin, cout = 64, 128
     x = torch.randn(n, cin, d, h, w, device="cuda")
     wt = torch.randn(cout, cin, 3, 3, 3, device="cuda") / (cin * 27) ** 0.5
     scale = torch.rand(cout, device="cuda") + 0.5

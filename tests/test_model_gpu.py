@@ -248,3 +248,19 @@ def test_fused_attention_matches_torch(batch, s, residual):
     print("fused attention rel err %.3g" % err)
     assert err < 1e-4      # logits have std ~18 here: their 2^-17-relative product error shows up as a relative error of P
     assert not got[..., :c].any() and not got[..., 2 * c:].any()
+
+
+def test_loss_computer_mirror_matches_reference_golden(golden_dir):
+    """LossComputer(cfg, device).computeLoss keeps the reference's call signature and 4-tuple (losses.py:23-45)."""
+    from hupr_b200.misc import LossComputer, get_max_preds
+    g = np.load(os.path.join(golden_dir, "loss_reference.npz"))
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    b = g["gt"].shape[0]
+    heat = (torch.rand((b, 14, 1, 64, 64), generator=gen) * 0.98 + 0.01).cuda()
+    gcn = (torch.rand((b, 1, 14, 64, 64), generator=gen) * 0.98 + 0.01).cuda()
+    lc = LossComputer(make_cfg(), torch.device("cuda"))
+    loss, loss2, pred2d, gt2d = lc.computeLoss((heat, gcn), torch.from_numpy(g["gt"]))
+    assert abs(float(loss) - float(g["loss"])) < 2e-6 * float(g["loss"]) and abs(float(loss2) - float(g["loss2"])) < 2e-6 * float(g["loss2"])
+    assert pred2d.dtype == np.float32 and np.array_equal(pred2d, g["pred2d"]) and np.array_equal(gt2d, g["gt2d"])
+    preds, maxvals = get_max_preds(gcn.view(b, 14, 64, 64))
+    assert np.array_equal(preds, g["pred2d"]) and maxvals.shape == (b, 14, 1)
