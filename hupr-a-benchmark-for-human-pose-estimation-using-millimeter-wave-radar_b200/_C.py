@@ -26,6 +26,7 @@ class ConvDesc(ctypes.Structure):
         ("o_hi", ctypes.c_void_p), ("o_lo", ctypes.c_void_p), ("o_ld", ctypes.c_int), ("o_ch_off", ctypes.c_int),
         ("o_f32", ctypes.c_void_p), ("o_f32_ld", ctypes.c_int),
         ("w_ld", ctypes.c_int), ("w_ch_off", ctypes.c_int),
+        ("a_n_stride", ctypes.c_longlong),
     ]
 
 
@@ -53,6 +54,9 @@ SIGNATURES = {
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
     "hupr_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttnDesc), ctypes.c_void_p]),
     "hupr_window_normalize": (ctypes.c_int, [_P, _P, _I, _P, _P]),
+    "hupr_frame_features_workspace_bytes": (ctypes.c_size_t, [_I]),
+    "hupr_plane_stats": (ctypes.c_int, [_P, _I, _P, ctypes.c_size_t, _P]),
+    "hupr_frame_features": (ctypes.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "hupr_mnet_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "hupr_resample_linear": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "hupr_softmax_rows": (ctypes.c_int, [_P, _P, _P, ctypes.c_longlong, _I, _P]),

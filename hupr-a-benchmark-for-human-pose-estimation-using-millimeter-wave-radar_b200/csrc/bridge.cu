@@ -126,6 +126,94 @@ mnet_kernel(const float* __restrict__ vrdae, const float* __restrict__ weight, c
     }
 }
 
+// ---- streaming variant: consecutive windows share 7 of 8 frames, and both the standardisation and MNet are
+// per-frame operations, so the stream computes them once per frame-sensor instead of once per window slot. ------------------------
+// Plane statistics: one CTA per (frame-sensor, kept Doppler row) -> mean and 1/std (unbiased) of the 16 (re|im, elevation) planes.
+__global__ void __launch_bounds__(kNormThreads)
+plane_stats_kernel(const float4* __restrict__ cube, float* __restrict__ stats /* [n_fs][8][2 mean|rstd][4 quad][4] */) {
+    __shared__ float scratch[(kNormThreads / 32) * 16];
+    const int c = blockIdx.x, fs = blockIdx.y;
+    const float4* plane = cube + ((size_t)fs * 16 + 4 + c) * kPlaneF4;
+    const int tid = threadIdx.x;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < kPlaneF4 / kNormThreads; ++k) {
+        const float4 v = __ldg(plane + tid + k * kNormThreads);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    reduce_by_quad(s, scratch);
+    float mean[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mean[k] = s[k] * (1.0f / kPlaneCells);
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < kPlaneF4 / kNormThreads; ++k) {
+        const float4 v = __ldg(plane + tid + k * kNormThreads);
+        const float d0 = v.x - mean[0], d1 = v.y - mean[1], d2 = v.z - mean[2], d3 = v.w - mean[3];
+        q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+    }
+    reduce_by_quad(q, scratch);
+    if (tid < 4) {   // thread t holds the statistics of float4 lane pattern (t & 3): components (re e0, im e0, re e1, im e1), e0 = 2t
+        float* dst = stats + ((size_t)(fs * 8 + c) * 2) * 16 + tid * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dst[k] = mean[k];
+            dst[16 + k] = 1.0f / sqrtf(q[k] * (1.0f / (kPlaneCells - 1)));
+        }
+    }
+}
+
+// One thread per (frame-sensor, range, azimuth): standardise with the plane statistics, mean over elevation, MNet.
+__global__ void __launch_bounds__(256)
+frame_features_kernel(const float4* __restrict__ cube, const float* __restrict__ stats, const float* __restrict__ weight,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                      int fs0, int n_fs) {
+    __shared__ float sW[32 * 4 + 32];
+    __shared__ float sStat[8 * 32];
+    if (threadIdx.x < 160) sW[threadIdx.x] = threadIdx.x < 128 ? __ldg(weight + threadIdx.x) : __ldg(bias + threadIdx.x - 128);
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;       // 4096 positions per frame-sensor, 256 | 4096 -> one fs per CTA
+    const int fs = fs0 + (int)(gid / kPlaneCells);
+    const int pos = (int)(gid % kPlaneCells);
+    sStat[threadIdx.x] = __ldg(stats + (size_t)fs * 256 + threadIdx.x);
+    __syncthreads();
+    float m[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4* src = cube + ((size_t)fs * 16 + 4 + c) * kPlaneF4 + (size_t)pos * 4;
+        const float* mean = sStat + c * 32;
+        const float* rstd = mean + 16;
+        float re = 0.f, im = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float4 v = __ldg(src + t);
+            re += (v.x - mean[t * 4]) * rstd[t * 4] + (v.z - mean[t * 4 + 2]) * rstd[t * 4 + 2];
+            im += (v.y - mean[t * 4 + 1]) * rstd[t * 4 + 1] + (v.w - mean[t * 4 + 3]) * rstd[t * 4 + 3];
+        }
+        m[2 * c] = re * 0.125f;
+        m[2 * c + 1] = im * 0.125f;
+    }
+    const size_t o = ((size_t)(fs - fs0) * kPlaneCells + pos) * 32;
+    __nv_bfloat16* oh = out_hi + o;
+    __nv_bfloat16* ol = out_lo ? out_lo + o : nullptr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int oc = g * 8 + i;
+            const float w00 = sW[oc * 4], w01 = sW[oc * 4 + 1], w10 = sW[oc * 4 + 2], w11 = sW[oc * 4 + 3], b = sW[128 + oc];
+            float best = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float y = fmaf(w11, m[9 + 2 * t], fmaf(w10, m[8 + 2 * t], fmaf(w01, m[2 * t + 1], w00 * m[2 * t]))) + b;
+                best = fmaxf(best, y);
+            }
+            v[i] = best;
+        }
+        store8(oh + g * 8, ol ? ol + g * 8 : nullptr, v);
+    }
+}
+
 struct ResampleParams {
     int n, di, hi, wi, dout, ho, wo, c8;      // c8 = channels / 8
     int in_ld, in_off, out_ld, out_off;
@@ -275,6 +363,37 @@ extern "C" int hupr_window_normalize(const void* cube, const int32_t* slot_fs, i
     if (rc != HUPR_OK) return rc;
     window_normalize_kernel<<<dim3(8, n_slots), kNormThreads, 0, (cudaStream_t)stream>>>(
         static_cast<const float4*>(cube), slot_fs, vrdae);
+    return launch_status();
+}
+
+extern "C" size_t hupr_frame_features_workspace_bytes(int n_frame_sensors) {
+    return n_frame_sensors > 0 ? (size_t)n_frame_sensors * 256 * sizeof(float) : 0;
+}
+
+extern "C" int hupr_plane_stats(const void* cube, int n_frame_sensors, void* workspace, size_t ws_bytes, void* stream) {
+    if (n_frame_sensors < 0) return HUPR_ERR_BAD_ARG;
+    if (n_frame_sensors == 0) return HUPR_OK;
+    if (!cube || !workspace) return HUPR_ERR_BAD_ARG;
+    if (ws_bytes < hupr_frame_features_workspace_bytes(n_frame_sensors)) return HUPR_ERR_WORKSPACE;
+    if (((uintptr_t)cube | (uintptr_t)workspace) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    plane_stats_kernel<<<dim3(8, n_frame_sensors), kNormThreads, 0, (cudaStream_t)stream>>>(static_cast<const float4*>(cube),
+                                                                                          static_cast<float*>(workspace));
+    return launch_status();
+}
+
+extern "C" int hupr_frame_features(const void* cube, const void* stats, int first_frame_sensor, int n_frame_sensors, const float* weight,
+                                   const float* bias, void* out_hi, void* out_lo, void* stream) {
+    if (n_frame_sensors < 0 || first_frame_sensor < 0) return HUPR_ERR_BAD_ARG;
+    if (n_frame_sensors == 0) return HUPR_OK;
+    if (!cube || !stats || !weight || !bias || !out_hi) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)cube | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) return HUPR_ERR_ALIGNMENT;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    frame_features_kernel<<<n_frame_sensors * (kPlaneCells / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const float4*>(cube), static_cast<const float*>(stats), weight, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+        first_frame_sensor, n_frame_sensors);
     return launch_status();
 }
 

@@ -163,11 +163,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static int encode_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int bh) {
+static int encode_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int bh, long long n_stride) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return HUPR_ERR_CUDA;
     cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
-    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2, (cuuint64_t)d * h * w * ca * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2,
+                             (cuuint64_t)(n_stride > 0 ? n_stride : (long long)d * h * w * ca) * 2};
     cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
@@ -215,6 +216,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     if (!d || !d->a_hi || !d->w_hi) return HUPR_ERR_BAD_ARG;
     if ((d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
     if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
+    if (d->a_n_stride < 0 || d->a_n_stride % 8) return HUPR_ERR_BAD_ARG;
     if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > ((d->ca + BK - 1) / BK) * BK) return HUPR_ERR_BAD_ARG;
     if (d->cout <= 0 || d->cout % 64) return HUPR_ERR_BAD_ARG;
     if (d->kd <= 0 || d->kh <= 0 || d->kw <= 0) return HUPR_ERR_BAD_ARG;
@@ -255,7 +257,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     const int wdim2 = d->w_batched ? d->n : taps;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
-    if ((rc = encode_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
+    if ((rc = encode_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh, d->a_n_stride)) != HUPR_OK) return rc;
     const int w_ld = d->w_ld ? d->w_ld : d->cin;
     if (w_ld % 8 || d->w_ch_off % 8 || d->w_ch_off < 0 || d->w_ch_off + d->cin > w_ld) return HUPR_ERR_BAD_ARG;
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
@@ -263,7 +265,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     if ((rc = encode_wgt_map(&b_hi, w_hi, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
     const bool split = d->a_lo != nullptr;
     if (split) {
-        if ((rc = encode_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
+        if ((rc = encode_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh, d->a_n_stride)) != HUPR_OK) return rc;
         if ((rc = encode_wgt_map(&b_lo, w_lo, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
     } else {
         a_lo = a_hi;

@@ -164,11 +164,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
 }
 
-static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h) {
+static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h, long long n_stride) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return HUPR_ERR_CUDA;
     cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
-    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2, (cuuint64_t)d * h * w * ca * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2,
+                             (cuuint64_t)(n_stride > 0 ? n_stride : (long long)d * h * w * ca) * 2};
     cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bw, (cuuint32_t)box_h, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
@@ -245,8 +246,8 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     const __nv_bfloat16* w_lo = static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
-    if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2)) != HUPR_OK) return rc;
-    if ((rc = encode_halo_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
     return bn == 128 ? launch_halo<128>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)

@@ -178,6 +178,11 @@ class HuPRNet(nn.Module):
             self._plans = {batch: plan}      # one live plan: the buffers are sized by batch
         return pk, plan
 
+    def chirp_weights(self):
+        """(RAchirpNet weight, bias, REchirpNet weight, bias) as contiguous float32 device tensors (the MNet kernels' inputs)."""
+        pk = self._packed or self._pack()
+        return pk["RAchirpNet"] + pk["REchirpNet"]
+
     # ------------------------------------------------------------------------------------------ forward
     def forward_chirp(self, VRDAEmaps_hori, VRDAEmaps_vert):
         """networks.py:23-33.  Returns channels-last split tensors ``[B, G, 64, 64, numFilters]`` (the reference returns the

@@ -90,6 +90,10 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.pd, desc.ph, desc.pw = pad
     desc.w_batched = 1 if w_batched else 0
     desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
+    if a.hi.stride(0) != d * h * w * ca:        # overlapping sliding-window view over a frame stream
+        if tuple(a.hi.stride()[1:]) != (h * w * ca, w * ca, ca, 1) or (a.lo is not None and a.lo.stride() != a.hi.stride()):
+            raise ValueError("conv_gemm: only the sample stride of A may be non-dense")
+        desc.a_n_stride = a.hi.stride(0)
     desc.scale, desc.shift, desc.slope = _C.optr(scale), _C.optr(shift), _C.optr(slope)
     if residual is not None:
         desc.r_hi, desc.r_lo = residual.hi.data_ptr(), _C.optr(residual.lo)
@@ -147,6 +151,23 @@ def window_normalize(cube, slot_fs, out=None):
         out = torch.empty((n_slots, 8, 2, 64, 64, 8), dtype=torch.float32, device=cube.device)
     with torch.cuda.device(cube.device):
         _call("hupr_window_normalize", _p(cube), _p(slot_fs), n_slots, _p(out), _C.stream_ptr())
+    return out
+
+
+def plane_stats(cube, ws=None):
+    """cube complex64 [n,16,64,64,8] -> per-plane mean / rstd workspace (hupr_plane_stats)."""
+    n = cube.shape[0]
+    if ws is None:
+        ws = torch.empty(n * 256, dtype=torch.float32, device=cube.device)
+    with torch.cuda.device(cube.device):
+        _call("hupr_plane_stats", _p(cube), n, _p(ws), ws.numel() * 4, _C.stream_ptr())
+    return ws
+
+
+def frame_features(cube, stats, first, count, weight, bias, out):
+    """Frame-sensors [first, first+count) of cube -> SplitTensor [count, 64, 64, 32] chirp features (hupr_frame_features)."""
+    with torch.cuda.device(cube.device):
+        _call("hupr_frame_features", _p(cube), _p(stats), first, count, _p(weight), _p(bias), _p(out.hi), _p(out.lo), _C.stream_ptr())
     return out
 
 

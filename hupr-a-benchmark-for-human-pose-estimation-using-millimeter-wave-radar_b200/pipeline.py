@@ -8,6 +8,7 @@ tools/run.py:35-58); the arithmetic of each stage is unchanged, only the hand-of
 import torch
 
 from . import ops
+from .ops import SplitTensor
 from .preprocessing.process_iwr1843 import FRAME_WORDS, cascade_i16
 
 GROUP = 8
@@ -26,7 +27,10 @@ def window_slots(n_windows, n_frames, first_cube=0, group=GROUP):
 class RadarPoseStream(object):
     """Fixed-shape streaming step: ``n_windows`` poses from ``n_windows + 7`` consecutive radar frames (hori + vert)."""
 
-    def __init__(self, model, n_windows, device="cuda", use_graph=True):
+    def __init__(self, model, n_windows, device="cuda", use_graph=True, per_frame=True):
+        """``per_frame=True`` (default): standardisation + MNet run once per frame-sensor and the windows are overlapping strided
+        views of the per-frame features (same arithmetic, 8x less pre-encoder work).  ``per_frame=False``
+        materialises the reference's ``[B,8,8,2,64,64,8]`` network inputs and calls ``model(hori, vert)``."""
         self.model = model
         self.n_windows = n_windows
         self.n_frames = n_windows + GROUP - 1
@@ -37,8 +41,19 @@ class RadarPoseStream(object):
         self.cubes = torch.empty((nfs, 16, 64, 64, 8), dtype=torch.complex64, device=dev)
         self.slots_hori = window_slots(n_windows, self.n_frames, 0).to(dev)
         self.slots_vert = window_slots(n_windows, self.n_frames, self.n_frames).to(dev)
-        self.vrdae_hori = torch.empty((n_windows, GROUP, 8, 2, 64, 64, 8), dtype=torch.float32, device=dev)
-        self.vrdae_vert = torch.empty_like(self.vrdae_hori)
+        self.per_frame = per_frame
+        if per_frame:
+            split = model.split
+            self.stats = torch.empty(nfs * 256, dtype=torch.float32, device=dev)
+            self.feat_hori = SplitTensor.empty((self.n_frames, 64, 64, 32), dev, split)
+            self.feat_vert = SplitTensor.empty((self.n_frames, 64, 64, 32), dev, split)
+            frame = 64 * 64 * 32
+            view = lambda t: None if t is None else t.as_strided((n_windows, GROUP, 64, 64, 32), (frame, frame, 64 * 32, 32, 1))
+            self.win_hori = SplitTensor(view(self.feat_hori.hi), view(self.feat_hori.lo))
+            self.win_vert = SplitTensor(view(self.feat_vert.hi), view(self.feat_vert.lo))
+        else:
+            self.vrdae_hori = torch.empty((n_windows, GROUP, 8, 2, 64, 64, 8), dtype=torch.float32, device=dev)
+            self.vrdae_vert = torch.empty_like(self.vrdae_hori)
         self.keypoints = torch.empty((n_windows, 14, 2), dtype=torch.float32, device=dev)
         self.maxvals = torch.empty((n_windows, 14), dtype=torch.float32, device=dev)
         self.heatmap = None
@@ -49,9 +64,17 @@ class RadarPoseStream(object):
 
     def _step_eager(self):
         cascade_i16(self.adc, self.cubes)
-        ops.window_normalize(self.cubes, self.slots_hori, self.vrdae_hori)
-        ops.window_normalize(self.cubes, self.slots_vert, self.vrdae_vert)
-        heat, gcn = self.model(self.vrdae_hori, self.vrdae_vert)
+        if self.per_frame:
+            ops.plane_stats(self.cubes, self.stats)
+            wh, bh, wv, bv = self.model.chirp_weights()
+            ops.frame_features(self.cubes, self.stats, 0, self.n_frames, wh, bh, self.feat_hori)
+            ops.frame_features(self.cubes, self.stats, self.n_frames, self.n_frames, wv, bv, self.feat_vert)
+            heat, gcn = self.model.forward_features(self.win_hori, self.win_vert)
+            heat, gcn = heat.unsqueeze(2), gcn.unsqueeze(1)
+        else:
+            ops.window_normalize(self.cubes, self.slots_hori, self.vrdae_hori)
+            ops.window_normalize(self.cubes, self.slots_vert, self.vrdae_vert)
+            heat, gcn = self.model(self.vrdae_hori, self.vrdae_vert)
         self.heatmap, self.gcn_heatmap = heat, gcn
         ops.keypoints_argmax(gcn.view(self.n_windows, 14, 64, 64), self.keypoints, self.maxvals)
 

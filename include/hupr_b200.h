@@ -79,6 +79,8 @@ typedef struct hupr_conv_desc {
     void* o_hi; void* o_lo; int o_ld, o_ch_off;                   /* bf16 split output [positions][o_ld], may be NULL */
     float* o_f32; int o_f32_ld;                                   /* fp32 output [positions][o_f32_ld], may be NULL */
     int w_ld, w_ch_off;                                           /* weight row stride / first column in elements (0, 0 = dense [..][cout][cin]) */
+    long long a_n_stride;                                         /* elements between samples of A (0 = dense d*h*w*ca); smaller values give
+                                                                     overlapping sliding windows over a frame stream */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
@@ -121,6 +123,18 @@ int hupr_window_normalize(const void* cube, const int32_t* slot_fs, int n_slots,
  * out    : bf16 split channels-last [n_slots][64][64][32]  (= [B][D=8][H][W][32]); out_lo may be NULL.
  */
 int hupr_mnet_fwd(const float* vrdae, const float* weight, const float* bias, void* out_hi, void* out_lo, int n_slots, void* stream);
+
+/* Streaming variant of the two entry points above: standardisation and MNet are per-frame operations and
+ * consecutive windows share 7 of 8 frames, so a stream computes them once per frame-sensor.  Same arithmetic as
+ * hupr_window_normalize + hupr_mnet_fwd (datasets/base.py:13-24, models/networks.py:23-33, models/chirp_networks.py:11-21).
+ *   hupr_plane_stats     cube float2 [n][16][64][64][8] -> workspace: mean and 1/std of the 16 (re|im, elevation) planes of the 8
+ *                        kept Doppler rows of every frame-sensor (hupr_frame_features_workspace_bytes(n) bytes)
+ *   hupr_frame_features  frame-sensors [first, first+n) -> bf16 split features [n][64][64][32] with one sensor's MNet weights
+ * A window [B][8][64][64][32] is then an overlapping strided view of the feature buffer (hupr_conv_desc.a_n_stride). */
+size_t hupr_frame_features_workspace_bytes(int n_frame_sensors);
+int hupr_plane_stats(const void* cube, int n_frame_sensors, void* workspace, size_t ws_bytes, void* stream);
+int hupr_frame_features(const void* cube, const void* stats, int first_frame_sensor, int n_frame_sensors, const float* weight,
+                        const float* bias, void* out_hi, void* out_lo, void* stream);
 
 /* Bi/tri-linear resampling with align_corners=True on split channels-last tensors.  Replaces nn.Upsample / F.interpolate
  *   /root/reference/models/layers.py:84,89,199,204
