@@ -63,6 +63,9 @@ SIGNATURES = {
     "hupr_transpose_split": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "hupr_prgcn_workspace_bytes": (ctypes.c_size_t, [_I]),
     "hupr_prgcn_fwd": (ctypes.c_int, [_P, _I, ctypes.POINTER(_P), ctypes.POINTER(_P), _P, _P, ctypes.c_size_t, _P, _P, _I, _P]),
+    "hupr_gcn_nodes": (ctypes.c_int, [_P, _I, _P, _P, _P, _P, _I, _P]),
+    "hupr_gcn_mix": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
+    "hupr_gcn_heads": (ctypes.c_int, [_P, _I, _P, _I, _P]),
     "hupr_keypoints_argmax": (ctypes.c_int, [_P, _I, _P, _P, _P]),
     "hupr_heatmap_loss_fwd": (ctypes.c_int, [_P, _P, _P, _I, _P, ctypes.c_size_t, _P, _P, _P, _P]),
 }

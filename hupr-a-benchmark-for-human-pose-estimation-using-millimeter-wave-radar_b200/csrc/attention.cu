@@ -22,18 +22,28 @@
 namespace hupr {
 
 constexpr int AT_BM = 128;       // queries per CTA
-constexpr int AT_BKV = 128;      // keys per block
-constexpr int AT_D = 64;         // head dim = channels (level-1 maps of mscsa_prgcn.yaml)
-constexpr int AT_THREADS = 320;      // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter: each owns half of the columns)
-constexpr int AT_TILE = AT_BM * 128;                    // 16 KiB: [128 rows][64 bf16] swizzled tile
-constexpr int AT_SM_Q = 0;                              // Q_hi, Q_lo
-constexpr int AT_SM_KV = 2 * AT_TILE;                   // 2 stages x {K_hi, K_lo, Vt_hi (2 x 8 KiB), Vt_lo}
-constexpr int AT_STAGE = 4 * AT_TILE;
-constexpr int AT_SM_P = AT_SM_KV + 2 * AT_STAGE;        // P_hi (2 tiles), P_lo (2 tiles)
-constexpr int AT_SM_BAR = AT_SM_P + 4 * AT_TILE;
-constexpr int AT_SM_X = AT_SM_BAR + 128;                // float [2 parity][2 halves][128 rows] row-max exchange
-constexpr int AT_SM_END = AT_SM_X + 2048;
-constexpr int AT_SMEM = 232448;                         // the 227 KiB per-CTA maximum: AT_SM_END + 896 B of alignment slack
+constexpr int AT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter: each owns half of the columns)
+constexpr int AT_SMEM = 232448;  // the 227 KiB per-CTA maximum: layout end + 896 B of alignment slack
+
+// D = head dim = channels, BKV = keys per block.  (64, 128) serves level 1 (S = 4096), (128, 64) level 2 (S = 1024) of
+// mscsa_prgcn.yaml; both fill the same 224 KiB of shared memory.
+template <int D, int BKV>
+struct AttnCfg {
+    static constexpr int kQPlane = (D / 64) * AT_BM * 128;        // Q: D/64 swizzle atoms of [128 rows][128 B]
+    static constexpr int kKPlane = (D / 64) * BKV * 128;          // K block: D/64 atoms of [BKV rows][128 B]
+    static constexpr int kVPlane = (BKV / 64) * D * 128;          // V^T block: BKV/64 atoms of [D rows][128 B]
+    static constexpr int kPPlane = (BKV / 64) * AT_BM * 128;      // P: BKV/64 atoms of [128 rows][128 B]
+    static constexpr int kSmQ = 0;                                // Q_hi, Q_lo
+    static constexpr int kSmKV = 2 * kQPlane;                     // 2 stages x {K_hi, K_lo, Vt_hi, Vt_lo}
+    static constexpr int kStage = 2 * kKPlane + 2 * kVPlane;
+    static constexpr int kSmP = kSmKV + 2 * kStage;               // P_hi, P_lo
+    static constexpr int kSmBar = kSmP + 2 * kPPlane;
+    static constexpr int kSmX = kSmBar + 128;                     // float [2 parity][2 halves][128 rows] row-max exchange
+    static constexpr int kSmEnd = kSmX + 2048;
+    static constexpr int kTmemO = 2 * BKV;                        // S0 = [0, BKV), S1 = [BKV, 2 BKV), O = [2 BKV, 2 BKV + D)
+    static constexpr int kTmemCols = (2 * BKV + D) <= 256 ? 256 : 512;
+    static_assert(kSmEnd + 896 <= AT_SMEM, "attention shared-memory plan does not fit");
+};
 
 struct AttnParams {
     int nkv;                      // key blocks
@@ -53,14 +63,16 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
+template <int D, int BKV>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                  const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
                  const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (smem + AT_SM_END > smem_raw + AT_SMEM) __trap();      // dynamic smem base less aligned than the 896-B slack allows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_SM_BAR);
+    using Cfg = AttnCfg<D, BKV>;
+    if (smem + Cfg::kSmEnd > smem_raw + AT_SMEM) __trap();      // dynamic smem base less aligned than the 896-B slack allows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmBar);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;      // [2]
     uint64_t* k_empty = bars + 3;     // [2]
@@ -88,59 +100,69 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         prefetch_tmap(&tmQ_hi); prefetch_tmap(&tmQ_lo); prefetch_tmap(&tmK_hi);
         prefetch_tmap(&tmK_lo); prefetch_tmap(&tmV_hi); prefetch_tmap(&tmV_lo);
     }
-    if (warp == 1) {   // TMEM: S0 = columns [0,128), S1 = [128,256), O = [256,320)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512));
+    if (warp == 1) {   // TMEM: S0 = columns [0,BKV), S1 = [BKV,2BKV), O = [2BKV, 2BKV+D)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(Cfg::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_O = tmem_base + 256;
+    const uint32_t tmem_O = tmem_base + Cfg::kTmemO;
 
     if (warp == 0) {
         // ================= TMA producer: K ring and V ring are independent (K_j is free as soon as Q K_j^T retires) =================
         if (lane == 0) {
-            mbar_expect_tx(q_full, 2 * AT_TILE);
-            tma_load_3d(smem + AT_SM_Q, &tmQ_hi, q_full, p.q_off, q0, b);
-            tma_load_3d(smem + AT_SM_Q + AT_TILE, &tmQ_lo, q_full, p.q_off, q0, b);
+            mbar_expect_tx(q_full, 2 * Cfg::kQPlane);
+#pragma unroll
+            for (int a = 0; a < D / 64; ++a) {
+                tma_load_3d(smem + Cfg::kSmQ + a * (AT_BM * 128), &tmQ_hi, q_full, p.q_off + 64 * a, q0, b);
+                tma_load_3d(smem + Cfg::kSmQ + Cfg::kQPlane + a * (AT_BM * 128), &tmQ_lo, q_full, p.q_off + 64 * a, q0, b);
+            }
             for (int j = 0; j < p.nkv; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (uint32_t)(((j >> 1) & 1) ^ 1);
-                uint8_t* st = smem + AT_SM_KV + s * AT_STAGE;
-                const int k0 = j * AT_BKV;
+                uint8_t* st = smem + Cfg::kSmKV + s * Cfg::kStage;
+                const int k0 = j * BKV;
                 mbar_wait(&k_empty[s], ph);
-                mbar_expect_tx(&k_full[s], 2 * AT_TILE);
-                tma_load_3d(st, &tmK_hi, &k_full[s], p.k_off, k0, b);
-                tma_load_3d(st + AT_TILE, &tmK_lo, &k_full[s], p.k_off, k0, b);
+                mbar_expect_tx(&k_full[s], 2 * Cfg::kKPlane);
+#pragma unroll
+                for (int a = 0; a < D / 64; ++a) {
+                    tma_load_3d(st + a * (BKV * 128), &tmK_hi, &k_full[s], p.k_off + 64 * a, k0, b);
+                    tma_load_3d(st + Cfg::kKPlane + a * (BKV * 128), &tmK_lo, &k_full[s], p.k_off + 64 * a, k0, b);
+                }
                 mbar_wait(&v_empty[s], ph);
-                mbar_expect_tx(&v_full[s], 2 * AT_TILE);
-                tma_load_3d(st + 2 * AT_TILE, &tmV_hi, &v_full[s], k0, 0, b);                      // keys k0 .. k0+63
-                tma_load_3d(st + 2 * AT_TILE + AT_TILE / 2, &tmV_hi, &v_full[s], k0 + 64, 0, b);   // keys k0+64 .. k0+127
-                tma_load_3d(st + 3 * AT_TILE, &tmV_lo, &v_full[s], k0, 0, b);
-                tma_load_3d(st + 3 * AT_TILE + AT_TILE / 2, &tmV_lo, &v_full[s], k0 + 64, 0, b);
+                mbar_expect_tx(&v_full[s], 2 * Cfg::kVPlane);
+#pragma unroll
+                for (int a = 0; a < BKV / 64; ++a) {      // 64-key atoms of the V^T block
+                    tma_load_3d(st + 2 * Cfg::kKPlane + a * (D * 128), &tmV_hi, &v_full[s], k0 + 64 * a, 0, b);
+                    tma_load_3d(st + 2 * Cfg::kKPlane + Cfg::kVPlane + a * (D * 128), &tmV_lo, &v_full[s], k0 + 64 * a, 0, b);
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread): Q K^T runs two key blocks ahead of P V =================
         if (lane == 0) {
-            const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BKV >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
-            const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_D >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
-            const uint32_t sQ = smem_u32(smem + AT_SM_Q), sP = smem_u32(smem + AT_SM_P);
-            const uint64_t dq_hi = make_smem_desc(sQ), dq_lo = make_smem_desc(sQ + AT_TILE);
+            const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+            const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+            const uint32_t sQ = smem_u32(smem + Cfg::kSmQ), sP = smem_u32(smem + Cfg::kSmP);
             auto issue_qk = [&](int j) {      // S[j & 1] = Q . K_j^T
                 const int s = j & 1;
                 mbar_wait(&k_full[s], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + AT_SM_KV + s * AT_STAGE);
-                const uint64_t dk_hi = make_smem_desc(st), dk_lo = make_smem_desc(st + AT_TILE);
-                const uint32_t tS = tmem_base + (uint32_t)(s * 128);
+                const uint32_t st = smem_u32(smem + Cfg::kSmKV + s * Cfg::kStage);
+                const uint32_t tS = tmem_base + (uint32_t)(s * BKV);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) {
-                    const uint64_t koff = (uint64_t)(k * 2);
-                    umma_bf16(tS, dq_lo + koff, dk_hi + koff, idesc_qk, k != 0);
-                    umma_bf16(tS, dq_hi + koff, dk_lo + koff, idesc_qk, 1u);
-                    umma_bf16(tS, dq_hi + koff, dk_hi + koff, idesc_qk, 1u);
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t atom = (uint32_t)(k >> 2);
+                    const uint64_t koff = (uint64_t)((k & 3) * 2);
+                    const uint64_t dq_hi = make_smem_desc(sQ + atom * (AT_BM * 128)) + koff;
+                    const uint64_t dq_lo = make_smem_desc(sQ + Cfg::kQPlane + atom * (AT_BM * 128)) + koff;
+                    const uint64_t dk_hi = make_smem_desc(st + atom * (BKV * 128)) + koff;
+                    const uint64_t dk_lo = make_smem_desc(st + Cfg::kKPlane + atom * (BKV * 128)) + koff;
+                    umma_bf16(tS, dq_lo, dk_hi, idesc_qk, k != 0);
+                    umma_bf16(tS, dq_hi, dk_lo, idesc_qk, 1u);
+                    umma_bf16(tS, dq_hi, dk_hi, idesc_qk, 1u);
                 }
                 tc_commit(&s_full[s]);
                 tc_commit(&k_empty[s]);
@@ -153,15 +175,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 mbar_wait(&v_full[s], (uint32_t)((j >> 1) & 1));
                 mbar_wait(p_full, (uint32_t)(j & 1));
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + AT_SM_KV + s * AT_STAGE);
+                const uint32_t st = smem_u32(smem + Cfg::kSmKV + s * Cfg::kStage);
 #pragma unroll
-                for (int k = 0; k < AT_BKV / 16; ++k) {      // O (+)= P_j . V_j
+                for (int k = 0; k < BKV / 16; ++k) {      // O (+)= P_j . V_j
                     const uint32_t atom = (uint32_t)(k >> 2);
                     const uint64_t koff = (uint64_t)((k & 3) * 2);
-                    const uint64_t dp_hi = make_smem_desc(sP + atom * AT_TILE) + koff;
-                    const uint64_t dp_lo = make_smem_desc(sP + 2 * AT_TILE + atom * AT_TILE) + koff;
-                    const uint64_t dv_hi = make_smem_desc(st + 2 * AT_TILE + atom * (AT_TILE / 2)) + koff;
-                    const uint64_t dv_lo = make_smem_desc(st + 3 * AT_TILE + atom * (AT_TILE / 2)) + koff;
+                    const uint64_t dp_hi = make_smem_desc(sP + atom * (AT_BM * 128)) + koff;
+                    const uint64_t dp_lo = make_smem_desc(sP + Cfg::kPPlane + atom * (AT_BM * 128)) + koff;
+                    const uint64_t dv_hi = make_smem_desc(st + 2 * Cfg::kKPlane + atom * (D * 128)) + koff;
+                    const uint64_t dv_lo = make_smem_desc(st + 2 * Cfg::kKPlane + Cfg::kVPlane + atom * (D * 128)) + koff;
                     umma_bf16(tmem_O, dp_lo, dv_hi, idesc_pv, (j | k) != 0);
                     umma_bf16(tmem_O, dp_hi, dv_lo, idesc_pv, 1u);
                     umma_bf16(tmem_O, dp_hi, dv_hi, idesc_pv, 1u);
@@ -173,28 +195,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
     } else {
         // ================= softmax / epilogue warps: thread <-> (query row, column half) =================
+        constexpr int SC = BKV / 2;              // S columns per thread
+        constexpr int NV = SC / 32;              // 32-column TMEM loads per thread and block
+        constexpr int OC = D / 2;                // O columns per thread
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;        // S columns [64*half, +64), O columns [32*half, +32)
+        const int half = (warp - 2) >> 2;        // S columns [SC*half, +SC), O columns [OC*half, +OC)
         const int row = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t row_base = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-        const uint32_t sP_hi = smem_u32(smem + AT_SM_P + half * AT_TILE) + row_base;            // key atom `half` of the P tile
-        const uint32_t sP_lo = smem_u32(smem + AT_SM_P + 2 * AT_TILE + half * AT_TILE) + row_base;
-        const uint32_t xch = smem_u32(smem + AT_SM_X);
+        const uint32_t sP_hi = smem_u32(smem + Cfg::kSmP) + row_base;
+        const uint32_t sP_lo = smem_u32(smem + Cfg::kSmP + Cfg::kPPlane) + row_base;
+        const uint32_t xch = smem_u32(smem + Cfg::kSmX);
         const uint32_t xr = (uint32_t)(row & 7);
         const float kLog2e = 1.4426950408889634f;
         float m_run = -INFINITY, nm_run = 0.f, l_run = 0.f;    // l_run: partial sum over this thread's column half; nm_run = -m_run*log2e
         for (int j = 0; j < p.nkv; ++j) {
             mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            const uint32_t tS = tmem_base + (uint32_t)((j & 1) * 128 + half * 64) + lane_sel;
-            tmem_ld32_nowait(tS, v0);
-            tmem_ld32_nowait(tS + 32, v1);
+            uint32_t v[NV][32];
+            const uint32_t tS = tmem_base + (uint32_t)((j & 1) * BKV + half * SC) + lane_sel;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) tmem_ld32_nowait(tS + (uint32_t)(c * 32), v[c]);
             tmem_ld_wait();
             float mx = m_run;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+            for (int c = 0; c < NV; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
+            }
             // combine the row maximum with the warp that owns the other column half
             const uint32_t slot = xch + (uint32_t)(((j & 1) * 2) * 128 * 4);
             sts_f32(slot + (uint32_t)((half * 128 + row) * 4), mx);
@@ -204,15 +232,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             // P = exp(S - max) = 2^(S*log2e - max*log2e), split into hi/lo bf16 (kept in registers until the P tile is free)
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float p0, p1, p2, p3;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v0[2 * i]), kLog2e, nm)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v0[2 * i + 1]), kLog2e, nm)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p2) : "f"(fmaf(__uint_as_float(v1[2 * i]), kLog2e, nm)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p3) : "f"(fmaf(__uint_as_float(v1[2 * i + 1]), kLog2e, nm)));
-                sum += (p0 + p1) + (p2 + p3);
-                split2(p0, p1, v0[2 * i], v0[2 * i + 1]);       // v0[2i] = hi pair, v0[2i+1] = lo pair of columns (2i, 2i+1)
-                split2(p2, p3, v1[2 * i], v1[2 * i + 1]);
+            for (int c = 0; c < NV; ++c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0, p1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[c][2 * i]), kLog2e, nm)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[c][2 * i + 1]), kLog2e, nm)));
+                    sum += p0 + p1;
+                    split2(p0, p1, v[c][2 * i], v[c][2 * i + 1]);       // v[2i] = hi pair, v[2i+1] = lo pair of columns (2i, 2i+1)
+                }
             }
             if (j > 0) {
                 mbar_wait(pv_done, (uint32_t)((j - 1) & 1));     // O += P_{j-1} V_{j-1} has retired
@@ -220,25 +248,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 const bool grew = mx > m_run;
                 if (__any_sync(0xffffffffu, grew)) {     // exact online softmax: rescale this row of O when its max grows
                     const float alpha = exp2f(nm - nm_run);          // same rounded exponent offsets as the P values already summed
-                    uint32_t o[32];
-                    tmem_ld32(tmem_O + lane_sel + (uint32_t)(half * 32), o);
+#pragma unroll 1
+                    for (int c = 0; c < OC / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_O + lane_sel + (uint32_t)(half * OC + c * 32), o);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(tmem_O + lane_sel + (uint32_t)(half * 32), o);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_O + lane_sel + (uint32_t)(half * OC + c * 32), o);
+                    }
                     l_run *= alpha;
                 }
             }
             m_run = mx;
             nm_run = nm;
             l_run += sum;
-            // 128B-swizzled K-major P tile: 16-byte chunk g of this row's 64 keys goes to chunk (g ^ (row & 7))
+            // 128B-swizzled K-major P tile: key column col of this row lives in atom col/64, 16-byte chunk ((col%64)/8) ^ (row & 7)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint32_t c0 = ((uint32_t)g ^ xr) << 4, c1 = ((uint32_t)(4 + g) ^ xr) << 4;
-                sts_v4(sP_hi + c0, v0[8 * g], v0[8 * g + 2], v0[8 * g + 4], v0[8 * g + 6]);
-                sts_v4(sP_lo + c0, v0[8 * g + 1], v0[8 * g + 3], v0[8 * g + 5], v0[8 * g + 7]);
-                sts_v4(sP_hi + c1, v1[8 * g], v1[8 * g + 2], v1[8 * g + 4], v1[8 * g + 6]);
-                sts_v4(sP_lo + c1, v1[8 * g + 1], v1[8 * g + 3], v1[8 * g + 5], v1[8 * g + 7]);
+            for (int c = 0; c < NV; ++c) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int col = half * SC + c * 32 + g * 8;
+                    const uint32_t off = (uint32_t)((col >> 6) * (AT_BM * 128)) + ((((uint32_t)(col & 63) >> 3) ^ xr) << 4);
+                    sts_v4(sP_hi + off, v[c][8 * g], v[c][8 * g + 2], v[c][8 * g + 4], v[c][8 * g + 6]);
+                    sts_v4(sP_lo + off, v[c][8 * g + 1], v[c][8 * g + 3], v[c][8 * g + 5], v[c][8 * g + 7]);
+                }
             }
             fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
@@ -252,22 +285,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         mbar_wait(pv_done, (uint32_t)((p.nkv - 1) & 1));
         tc_fence_after();
         const size_t pos = (size_t)b * p.s + q0 + row;
-        {
+#pragma unroll 1
+        for (int c = 0; c < OC / 32; ++c) {
             uint32_t v[32];
-            tmem_ld32(tmem_O + lane_sel + (uint32_t)(half * 32), v);
+            tmem_ld32(tmem_O + lane_sel + (uint32_t)(half * OC + c * 32), v);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g * 8 + i]) * inv;
+                const int ch = half * OC + c * 32 + g * 8;
                 if (p.r_hi) {
                     float r[8];
-                    const size_t roff = pos * p.r_ld + p.r_off + half * 32 + g * 8;
+                    const size_t roff = pos * p.r_ld + p.r_off + ch;
                     load8(p.r_hi + roff, p.r_lo ? p.r_lo + roff : nullptr, r);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] += r[i];
                 }
-                const size_t ooff = pos * p.o_ld + p.o_off + half * 32 + g * 8;
+                const size_t ooff = pos * p.o_ld + p.o_off + ch;
                 store8(p.o_hi + ooff, p.o_lo + ooff, o);
             }
         }
@@ -275,7 +310,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols));
     }
 }
 
@@ -292,43 +327,53 @@ static int encode_rows_map(CUtensorMap* map, const void* base, int row_len, int 
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-}  // namespace hupr
-
-extern "C" int hupr_attention_fwd(const hupr_attn_desc* d, void* stream) {
-    using namespace hupr;
-    if (!d || !d->q_hi || !d->q_lo || !d->k_hi || !d->k_lo || !d->vt_hi || !d->vt_lo || !d->o_hi || !d->o_lo) return HUPR_ERR_BAD_ARG;
-    if (d->batch <= 0 || d->batch > 65535 || d->s <= 0 || d->s % AT_BKV || d->c != AT_D) return HUPR_ERR_BAD_ARG;
-    if (d->q_ld % 8 || d->k_ld % 8 || d->q_off % 8 || d->k_off % 8 || d->q_off + AT_D > d->q_ld || d->k_off + AT_D > d->k_ld) return HUPR_ERR_BAD_ARG;
-    if (d->o_ld % 8 || d->o_off % 8 || d->o_off + AT_D > d->o_ld) return HUPR_ERR_BAD_ARG;
-    if (d->r_hi && (d->r_ld % 8 || d->r_off % 8 || d->r_off + AT_D > d->r_ld)) return HUPR_ERR_BAD_ARG;
-    const uintptr_t align_or = (uintptr_t)d->q_hi | (uintptr_t)d->q_lo | (uintptr_t)d->k_hi | (uintptr_t)d->k_lo | (uintptr_t)d->vt_hi |
-                               (uintptr_t)d->vt_lo | (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo;
-    if (align_or & 15) return HUPR_ERR_ALIGNMENT;
+template <int D, int BKV>
+static int launch_attention(const hupr_attn_desc* d, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        if (prop.major != 10) return HUPR_ERR_ARCH;
-        if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return HUPR_ERR_CUDA;
+        if (cudaFuncSetAttribute(attention_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return HUPR_ERR_CUDA;
         configured = true;
     }
     CUtensorMap q_hi, q_lo, k_hi, k_lo, v_hi, v_lo;
     int rc;
     if ((rc = encode_rows_map(&q_hi, d->q_hi, d->q_ld, d->s, d->batch, AT_BM)) != HUPR_OK) return rc;
     if ((rc = encode_rows_map(&q_lo, d->q_lo, d->q_ld, d->s, d->batch, AT_BM)) != HUPR_OK) return rc;
-    if ((rc = encode_rows_map(&k_hi, d->k_hi, d->k_ld, d->s, d->batch, AT_BKV)) != HUPR_OK) return rc;
-    if ((rc = encode_rows_map(&k_lo, d->k_lo, d->k_ld, d->s, d->batch, AT_BKV)) != HUPR_OK) return rc;
-    if ((rc = encode_rows_map(&v_hi, d->vt_hi, d->s, AT_D, d->batch, AT_D)) != HUPR_OK) return rc;
-    if ((rc = encode_rows_map(&v_lo, d->vt_lo, d->s, AT_D, d->batch, AT_D)) != HUPR_OK) return rc;
+    if ((rc = encode_rows_map(&k_hi, d->k_hi, d->k_ld, d->s, d->batch, BKV)) != HUPR_OK) return rc;
+    if ((rc = encode_rows_map(&k_lo, d->k_lo, d->k_ld, d->s, d->batch, BKV)) != HUPR_OK) return rc;
+    if ((rc = encode_rows_map(&v_hi, d->vt_hi, d->s, D, d->batch, D)) != HUPR_OK) return rc;
+    if ((rc = encode_rows_map(&v_lo, d->vt_lo, d->s, D, d->batch, D)) != HUPR_OK) return rc;
     AttnParams p;
-    p.nkv = d->s / AT_BKV;
+    p.nkv = d->s / BKV;
     p.q_off = d->q_off; p.k_off = d->k_off;
     p.r_hi = (const __nv_bfloat16*)d->r_hi; p.r_lo = (const __nv_bfloat16*)d->r_lo; p.r_ld = d->r_ld; p.r_off = d->r_off;
     p.o_hi = (__nv_bfloat16*)d->o_hi; p.o_lo = (__nv_bfloat16*)d->o_lo; p.o_ld = d->o_ld; p.o_off = d->o_off;
     p.s = d->s;
     const dim3 grid(d->s / AT_BM, d->batch);
-    attention_kernel<<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p);
+    attention_kernel<D, BKV><<<grid, AT_THREADS, AT_SMEM, stream>>>(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+}  // namespace hupr
+
+extern "C" int hupr_attention_fwd(const hupr_attn_desc* d, void* stream) {
+    using namespace hupr;
+    if (!d || !d->q_hi || !d->q_lo || !d->k_hi || !d->k_lo || !d->vt_hi || !d->vt_lo || !d->o_hi || !d->o_lo) return HUPR_ERR_BAD_ARG;
+    if (d->batch <= 0 || d->batch > 65535 || d->s <= 0 || d->s % AT_BM || (d->c != 64 && d->c != 128)) return HUPR_ERR_BAD_ARG;
+    const int c = d->c;
+    if (d->q_ld % 8 || d->k_ld % 8 || d->q_off % 8 || d->k_off % 8 || d->q_off + c > d->q_ld || d->k_off + c > d->k_ld) return HUPR_ERR_BAD_ARG;
+    if (d->o_ld % 8 || d->o_off % 8 || d->o_off + c > d->o_ld) return HUPR_ERR_BAD_ARG;
+    if (d->r_hi && (d->r_ld % 8 || d->r_off % 8 || d->r_off + c > d->r_ld)) return HUPR_ERR_BAD_ARG;
+    const uintptr_t align_or = (uintptr_t)d->q_hi | (uintptr_t)d->q_lo | (uintptr_t)d->k_hi | (uintptr_t)d->k_lo | (uintptr_t)d->vt_hi |
+                               (uintptr_t)d->vt_lo | (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo;
+    if (align_or & 15) return HUPR_ERR_ALIGNMENT;
+    static int arch_ok = 0;
+    if (!arch_ok) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
+        if (prop.major != 10) return HUPR_ERR_ARCH;
+        arch_ok = 1;
+    }
+    return c == 64 ? launch_attention<64, 128>(d, (cudaStream_t)stream) : launch_attention<128, 64>(d, (cudaStream_t)stream);
 }

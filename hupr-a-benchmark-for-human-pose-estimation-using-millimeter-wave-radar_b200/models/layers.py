@@ -158,6 +158,9 @@ class DecoderWeights(object):
         self.head = pack_conv([sd[p + "decoderLayer1.2.weight"].unsqueeze(2)], pad64(nf), [pad64(keypoints)], split)
         self.gcn_w = [sd[p + "gcn.L%d.weight" % i].float().contiguous() for i in (1, 2, 3)]
         self.gcn_b = [sd[p + "gcn.L%d.bias" % i].float().contiguous() for i in (1, 2, 3)]
+        # tensor-core PRGCN: W[q, p] is already the K-major B operand of  Yt[(b,j), q] = sum_p St[(b,j), p] W[q, p]
+        self.gcn_w_tc = [SplitTensor.from_float(w.view(1, 1024, 1024), True) for w in self.gcn_w] if split else None
+        self.gcn_relu = torch.zeros(1024, dtype=torch.float32, device=self.gcn_w[0].device)
 
 
 class DecoderBuffers(object):
@@ -170,7 +173,7 @@ class DecoderBuffers(object):
                                     proj_ra=mk(b, 1, 1, s, 4 * c), proj_re=mk(b, 1, 1, s, 4 * c),
                                     vt_ra=mk(b, c, s), vt_re=mk(b, c, s),
                                     cat=mk(b, 1, hw, hw, prev + 4 * c)))
-        smax = 64 * 64 if not split else 32 * 32      # level 1 (S = 4096) runs fused when split; scratch covers the unfused levels
+        smax = 64 * 64 if not split else 16 * 16      # levels 1 and 2 run fused when split; scratch covers the unfused level(s)
         self.logits = torch.empty(b * smax * smax, dtype=torch.float32, device=dev)
         self.probs = mk(b * smax * smax)
         self.t3a, self.o3a = mk(b, 1, 16, 16, 16 * nf), mk(b, 1, 16, 16, 8 * nf)
@@ -181,6 +184,11 @@ class DecoderBuffers(object):
         self.t1b, self.o1b = mk(b, 1, 64, 64, 2 * pad64(nf)), mk(b, 1, 64, 64, pad64(nf))
         self.logits_out = torch.empty((b, 64 * 64, pad64(keypoints)), dtype=torch.float32, device=dev)
         self.gcn_ws = torch.empty(max(ops.prgcn_workspace_bytes(b) // 4, 4), dtype=torch.float32, device=dev)
+        self.gcn_rows = -(-(b * keypoints) // 128) * 128          # rows (b, j) of the transposed GCN activations, padded to the GEMM tile
+        if split:
+            self.gcn_st = [SplitTensor.empty((1, 1, 1, self.gcn_rows, 1024), dev, True, zero=True) for _ in range(2)]
+            self.gcn_y3 = torch.zeros((1, 1, 1, self.gcn_rows, 1024), dtype=torch.float32, device=dev)
+            self.gcn_bias_rows = None
         self.heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
         self.gcn_heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
 
@@ -197,7 +205,7 @@ def run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, out, o_off, residua
     logits[n, m] = <Q[n], K[m]>;  P = softmax over keys m;  out[n] = sum_m P[n, m] V[m]  (+ V[n] for the cross branches)."""
     b = v.hi.shape[0]
     c, s = lv["c"], lv["s"]
-    if c == 64 and v.lo is not None:      # fused flash-style kernel (level 1: S = 4096, 88 % of the attention FLOPs)
+    if c in (64, 128) and v.lo is not None:      # fused flash-style kernel (levels 1 and 2: 99.7 % of the attention FLOPs)
         ops.attention_fwd(q_src, q_off, k_src, k_off, vt, c, out, o_off, residual=v if residual else None)
         return
     logits = bf.logits[:b * s * s].view(b, 1, 1, s, s)
@@ -250,5 +258,22 @@ def run_decoder(w, bf, feats_ra, feats_re, adj):
     run_block(bf.o1a, w.blocks[5], bf.t1b, bf.o1b)
     b = bf.o1b.hi.shape[0]
     ops.conv_gemm(bf.o1b, pad64(nf), w.head, bf.logits_out.shape[-1], out_f32=bf.logits_out.view(b, 1, 64, 64, -1))
-    ops.prgcn_fwd(bf.logits_out, w.gcn_w, w.gcn_b, adj, bf.gcn_ws, bf.heatmap, bf.gcn_heatmap)
+    if w.gcn_w_tc is None:
+        ops.prgcn_fwd(bf.logits_out, w.gcn_w, w.gcn_b, adj, bf.gcn_ws, bf.heatmap, bf.gcn_heatmap)
+        return bf.heatmap, bf.gcn_heatmap
+    if bf.gcn_bias_rows is None:      # bias[q, j] as residual rows [(b, j)][q], built once per plan
+        rows = []
+        for bias in w.gcn_b:
+            t = torch.zeros(bf.gcn_rows, 1024, dtype=torch.float32, device=bias.device)
+            t[:b * bias.shape[1]] = bias.t().repeat(b, 1)
+            rows.append(SplitTensor.from_float(t.view(1, 1, 1, bf.gcn_rows, 1024), True))
+        bf.gcn_bias_rows = rows
+    st_a, st_b = bf.gcn_st
+    ops.gcn_nodes(bf.logits_out, adj, bf.heatmap, st_a)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[0], 1024, residual=bf.gcn_bias_rows[0], slope=w.gcn_relu, out=st_b)
+    ops.gcn_mix(st_b, adj, st_a, b)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[1], 1024, residual=bf.gcn_bias_rows[1], slope=w.gcn_relu, out=st_b)
+    ops.gcn_mix(st_b, adj, st_a, b)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[2], 1024, residual=bf.gcn_bias_rows[2], out_f32=bf.gcn_y3)
+    ops.gcn_heads(bf.gcn_y3.view(bf.gcn_rows, 1024), bf.gcn_heatmap, b)
     return bf.heatmap, bf.gcn_heatmap

@@ -223,6 +223,23 @@ def prgcn_fwd(logits, weights, biases, adj, workspace, heatmap, gcn_heatmap):
     return heatmap, gcn_heatmap
 
 
+def gcn_nodes(logits, adj, heatmap, st):
+    """logits float32 [B, 4096, ld] -> heatmap [B,14,64,64], st SplitTensor rows [(b,j)][1024] (hupr_gcn_nodes)."""
+    batch, ld = logits.shape[0], logits.shape[-1]
+    with torch.cuda.device(logits.device):
+        _call("hupr_gcn_nodes", _p(logits), ld, _p(adj), _p(heatmap), _p(st.hi), _p(st.lo), batch, _C.stream_ptr())
+
+
+def gcn_mix(yt, adj, st, batch):
+    with torch.cuda.device(adj.device):
+        _call("hupr_gcn_mix", _p(yt.hi), _p(yt.lo), _p(adj), _p(st.hi), _p(st.lo), batch, _C.stream_ptr())
+
+
+def gcn_heads(y, gcn_heatmap, batch):
+    with torch.cuda.device(y.device):
+        _call("hupr_gcn_heads", _p(y), y.shape[-1], _p(gcn_heatmap), batch, _C.stream_ptr())
+
+
 def keypoints_argmax(maps, preds=None, maxvals=None):
     """float32 [..., 64, 64] -> float32 [..., 2] (x, y) of the first maximum (hupr_keypoints_argmax)."""
     lead = maps.shape[:-2]

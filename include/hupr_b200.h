@@ -92,7 +92,7 @@ int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
  * q, k : bf16 split, rows [batch][s][q_ld | k_ld], the c contracted channels start at q_off | k_off
  * vt   : bf16 split [batch][c][s]  (V transposed: hupr_transpose_split)
  * r    : optional residual rows [batch][s][r_ld] at r_off;  o: output rows [batch][s][o_ld] at o_off (bf16 split)
- * Supported: c == 64, s a multiple of 128, all four lo planes present (other shapes: HUPR_ERR_BAD_ARG — compose
+ * Supported: c == 64 or 128, s a multiple of 128, all four lo planes present (other shapes: HUPR_ERR_BAD_ARG — compose
  * hupr_conv_gemm(w_batched) + hupr_softmax_rows instead).
  */
 typedef struct hupr_attn_desc {
@@ -162,6 +162,15 @@ int hupr_transpose_split(const void* in_hi, const void* in_lo, int n, int s, int
 size_t hupr_prgcn_workspace_bytes(int batch);
 int hupr_prgcn_fwd(const float* logits, int ld, const float* const* weights, const float* const* biases, const float* adj,
                    void* workspace, size_t ws_bytes, float* heatmap, float* gcn_heatmap, int batch, void* stream);
+
+/* Tensor-core formulation of the same PRGCN (the caller runs the three 1024x1024 contractions with hupr_conv_gemm in the transposed
+ * layout Yt[(b,j), q] = sum_p St[(b,j), p] W[q, p], bias as residual rows, ReLU as slope):
+ *   hupr_gcn_nodes  logits -> heatmap = sigmoid(logits) [batch][14][64][64]  and  St0 = (X.A)^T bf16 split rows [(b,j)][1024]
+ *   hupr_gcn_mix    St_next[(b,j'), q] = sum_j A[j,j'] Yt[(b,j), q]   (bf16 split in and out, rows [(b,j)][1024])
+ *   hupr_gcn_heads  Yt_3 float rows [(b,j)][y_ld] (= [batch][14][32][32] maps) -> bilinear x2 + sigmoid -> [batch][14][64][64] */
+int hupr_gcn_nodes(const float* logits, int ld, const float* adj, float* heatmap, void* s_hi, void* s_lo, int batch, void* stream);
+int hupr_gcn_mix(const void* y_hi, const void* y_lo, const float* adj, void* s_hi, void* s_lo, int batch, void* stream);
+int hupr_gcn_heads(const float* y, int y_ld, float* gcn_heatmap, int batch, void* stream);
 
 /* Keypoint decode.  Replaces get_max_preds (/root/reference/misc/metrics.py:10-38).
  * maps: float [n_maps][64*64] -> preds float [n_maps][2] = (x, y) of the first maximum, zeroed where max <= 0; maxvals may be NULL. */

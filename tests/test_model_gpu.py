@@ -221,15 +221,16 @@ def test_forward_requires_eval_and_cuda():
         net(torch.zeros(1, 8, 8, 2, 64, 64, 8), torch.zeros(1, 8, 8, 2, 64, 64, 8))
 
 
-@pytest.mark.parametrize("batch,s,residual", [(1, 128, False), (2, 512, True), (1, 4096, True)])
-def test_fused_attention_matches_torch(batch, s, residual):
+@pytest.mark.parametrize("batch,s,residual,c", [(1, 128, False, 64), (2, 512, True, 64), (1, 4096, True, 64),
+                                                (1, 128, True, 128), (3, 1024, False, 128)])
+def test_fused_attention_matches_torch(batch, s, residual, c):
     """hupr_attention_fwd vs softmax(QK^T)V in float64; logits are un-scaled and large (|logit| up to ~60) like the network's."""
     from hupr_b200 import ops
     from hupr_b200.ops import SplitTensor
     torch.manual_seed(7)
-    c = 64
-    proj_q = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * 1.5
-    proj_k = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * 1.5
+    scale = 1.5 if c == 64 else 1.25       # logits std ~18 in both cases
+    proj_q = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * scale
+    proj_k = torch.randn(batch, 1, 1, s, 4 * c, device="cuda") * scale
     v = torch.randn(batch, 1, 1, s, c, device="cuda")
     PQ, PK, V = SplitTensor.from_float(proj_q), SplitTensor.from_float(proj_k), SplitTensor.from_float(v)
     VT = SplitTensor.empty((batch, c, s), "cuda")
