@@ -337,3 +337,77 @@ extern "C" int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heat
     note_launches(2);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
+
+// ================================================================================================================================
+// Training building blocks (row a-17 of SURVEY.md §8; the full backward pass is not assembled yet — DESIGN.md §8).
+//   hupr_heatmap_loss_bwd  d(loss1 + loss2)/d(logits) through BCE(mean) and the sigmoids  (reference: autograd of misc/losses.py:23-48)
+//   hupr_adam_step         torch.optim.Adam with coupled L2 weight decay on a flat fp32 buffer (reference: tools/base.py:47)
+// ================================================================================================================================
+namespace hupr {
+
+__device__ __forceinline__ float bce_sigmoid_grad(float p, float t, float inv_n) {
+    // BCE backward: (p - t) / max(p (1 - p), 1e-12) / N ; sigmoid backward: * p (1 - p)
+    const float pq = p * (1.0f - p);
+    return (p - t) / fmaxf(pq, 1e-12f) * pq * inv_n;
+}
+
+// One CTA per (b, k) map.  d_heat_logits: channels-last [B][4096][ld] (the head conv's output layout); d_gcn_pre: [B][14][64][64].
+__global__ void __launch_bounds__(256)
+loss_bwd_kernel(const float* __restrict__ heatmap, const float* __restrict__ gcn, const long long* __restrict__ joints, int ld,
+                float inv_n, float* __restrict__ d_heat_logits, float* __restrict__ d_gcn_pre) {
+    const int bk = blockIdx.x;
+    const int b = bk / kJ, k = bk % kJ;
+    int mx, my;
+    const bool valid = joint_center(joints, bk, mx, my);
+    for (int i = threadIdx.x; i < 4096; i += 256) {
+        const float t = target_value(valid, mx, my, i & 63, i >> 6);
+        d_heat_logits[((size_t)b * 4096 + i) * ld + k] = bce_sigmoid_grad(__ldg(heatmap + (size_t)bk * 4096 + i), t, inv_n);
+        d_gcn_pre[(size_t)bk * 4096 + i] = bce_sigmoid_grad(__ldg(gcn + (size_t)bk * 4096 + i), t, inv_n);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float weight_decay) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float pi = p[i];
+        const float gi = fmaf(weight_decay, pi, g[i]);            // coupled L2: grad += wd * param
+        const float mi = m[i] + (1.0f - beta1) * (gi - m[i]);     // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = fmaf((1.0f - beta2) * gi, gi, v[i] * beta2);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
+}  // namespace hupr
+
+extern "C" int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
+                                     float* d_heat_logits, float* d_gcn_pre, void* stream) {
+    if (batch < 0) return HUPR_ERR_BAD_ARG;
+    if (batch == 0) return HUPR_OK;
+    if (!heatmap || !gcn_heatmap || !joints || !d_heat_logits || !d_gcn_pre || ld < kJ) return HUPR_ERR_BAD_ARG;
+    int rc = heads_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const float inv_n = 1.0f / ((float)batch * kJ * 4096.0f);
+    loss_bwd_kernel<<<batch * kJ, 256, 0, (cudaStream_t)stream>>>(heatmap, gcn_heatmap, joints, ld, inv_n, d_heat_logits, d_gcn_pre);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+extern "C" int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, void* stream) {
+    if (n < 0 || step < 1) return HUPR_ERR_BAD_ARG;
+    if (n == 0) return HUPR_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return HUPR_ERR_BAD_ARG;
+    int rc = heads_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)((double)lr / bc1),
+                                                                    (float)sqrt(bc2), beta1, beta2, eps, weight_decay);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}

@@ -33,6 +33,14 @@ def pack_conv(weights, cin_pad, cout_pads, split=True):
     return SplitTensor.from_float(torch.cat(mats, dim=1), split)
 
 
+def pack_dgrad(weight, cout_pad, cin_pad, split=True):
+    """Data-gradient filter of a stride-1 'same' convolution: ``dX = conv(dY, W')`` with ``W'[tap][ci][co] = W[co][ci][flipped tap]``
+    — the same implicit-GEMM kernel computes dgrad (reference: autograd of nn.Conv3d / nn.Conv2d).  For a depth-valid kernel
+    ``(T, 1, 1)`` call the convolution with ``pad=(T-1, 0, 0)``."""
+    flip_dims = tuple(range(2, weight.dim()))
+    return pack_conv([weight.transpose(0, 1).flip(flip_dims)], cout_pad, [cin_pad], split)
+
+
 def bn_affine(sd, prefix):
     scale = sd[prefix + ".weight"].float() / torch.sqrt(sd[prefix + ".running_var"].float() + BN_EPS)
     shift = sd[prefix + ".bias"].float() - sd[prefix + ".running_mean"].float() * scale

@@ -203,8 +203,21 @@ class HuPRNet(nn.Module):
         plan's output buffers — valid until the next forward)."""
         batch = chirp_ra.hi.shape[0]
         pk, plan = self._plan(batch)
-        feats_ra = L.run_encoder(chirp_ra, pk["RAradarEncoder"], plan["enc_ra"])
-        feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
+        if batch <= 4 and ops._PROFILE is None:
+            # small batches leave most SMs idle inside one encoder (level 2/3 convolutions launch 16-64 CTAs): run the two
+            # independent sensor branches on two streams (fork/join with events, captured into the CUDA graph as parallel branches)
+            main = torch.cuda.current_stream()
+            side = plan.get("side_stream")
+            if side is None:
+                side = plan["side_stream"] = torch.cuda.Stream(device=pk["device"])
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
+            feats_ra = L.run_encoder(chirp_ra, pk["RAradarEncoder"], plan["enc_ra"])
+            main.wait_stream(side)
+        else:
+            feats_ra = L.run_encoder(chirp_ra, pk["RAradarEncoder"], plan["enc_ra"])
+            feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
         return L.run_decoder(pk["decoder"], plan["dec"], feats_ra, feats_re, pk["adj"])
 
     def forward(self, VRDAEmaps_hori, VRDAEmaps_vert):

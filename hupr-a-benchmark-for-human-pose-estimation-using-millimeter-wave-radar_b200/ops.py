@@ -264,3 +264,25 @@ def heatmap_loss_fwd(heatmap, gcn_heatmap, joints, want_targets=False):
         _call("hupr_heatmap_loss_fwd", _p(heatmap), _p(gcn_heatmap), _p(joints), batch, _p(ws), ws.numel() * 8,
               _p(losses), _p(targets), _p(gt2d), _C.stream_ptr())
     return losses, gt2d, targets
+
+
+def heatmap_loss_bwd(heatmap, gcn_heatmap, joints, d_heat_logits, d_gcn_pre):
+    """Gradient of loss1 + loss2 w.r.t. the pre-sigmoid logits (hupr_heatmap_loss_bwd).
+    d_heat_logits float32 [B, 4096, ld] channels-last (14 channels written), d_gcn_pre float32 [B, 14, 64, 64]."""
+    batch = joints.shape[0]
+    joints = joints.to(device=heatmap.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(heatmap.device):
+        _call("hupr_heatmap_loss_bwd", _p(heatmap), _p(gcn_heatmap), _p(joints), batch, d_heat_logits.shape[-1],
+              _p(d_heat_logits), _p(d_gcn_pre), _C.stream_ptr())
+    return d_heat_logits, d_gcn_pre
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+    """One Adam step with coupled L2 on flat float32 CUDA buffers (hupr_adam_step); defaults = reference tools/base.py:47."""
+    n = params.numel()
+    if not (grads.numel() == exp_avg.numel() == exp_avg_sq.numel() == n):
+        raise ValueError("adam_step: buffer sizes differ")
+    with torch.cuda.device(params.device):
+        _call("hupr_adam_step", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), n, lr, betas[0], betas[1], eps, weight_decay, step,
+              _C.stream_ptr())
+    return params

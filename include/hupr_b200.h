@@ -185,6 +185,21 @@ int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds, float* ma
 int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch,
                           void* workspace, size_t ws_bytes, float* losses, float* targets, float* gt2d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training building blocks (the complete backward pass is not assembled yet).
+ *
+ * hupr_heatmap_loss_bwd: gradient of loss = BCE(heatmap, T) + BCE(gcn_heatmap, T) (mean reduction, lossDecay == -1) with respect to the
+ * pre-sigmoid values — what autograd computes for /root/reference/misc/losses.py:23-48 + the sigmoids of models/networks.py:40 and
+ * models/gcn_networks.py:64.  d_heat_logits: float channels-last [batch][4096][ld] (first 14 channels written; the layout of the head
+ * convolution's output), d_gcn_pre: float [batch][14][64][64].
+ *
+ * hupr_adam_step: one torch.optim.Adam step with coupled L2 weight decay (tools/base.py:47: lr 1e-4, betas (0.9, 0.999), eps 1e-8,
+ * weight_decay 1e-4) over a flat fp32 buffer of n elements; `step` is the 1-based step count used for the bias corrections. */
+int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
+                          float* d_heat_logits, float* d_gcn_pre, void* stream);
+int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
