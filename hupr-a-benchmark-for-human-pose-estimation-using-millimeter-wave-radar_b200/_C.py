@@ -27,6 +27,7 @@ class ConvDesc(ctypes.Structure):
         ("o_f32", ctypes.c_void_p), ("o_f32_ld", ctypes.c_int),
         ("w_ld", ctypes.c_int), ("w_ch_off", ctypes.c_int),
         ("a_n_stride", ctypes.c_longlong),
+        ("k_split", ctypes.c_int), ("w_k_off", ctypes.c_int),
     ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "hupr_gcn_mix": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "hupr_gcn_heads": (ctypes.c_int, [_P, _I, _P, _I, _P]),
     "hupr_keypoints_argmax": (ctypes.c_int, [_P, _I, _P, _P, _P]),
+    "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
     "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, _I, _P]),

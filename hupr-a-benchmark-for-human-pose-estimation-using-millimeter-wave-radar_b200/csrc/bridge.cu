@@ -457,3 +457,61 @@ extern "C" int hupr_transpose_split(const void* in_hi, const void* in_lo, int n,
     if (in_lo) transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
     return launch_status(in_lo ? 2 : 1);
 }
+
+// ================================================================================================================================
+// Position-major ("K-major") copies for the weight-gradient GEMMs.
+//   dW[tap][co][ci] = sum_pos dY[pos][co] * X[pos + off(tap)][ci]
+// contracts over POSITIONS, so both operands are re-laid out as [channel][P] with P a zero-padded linear position index
+//   P(n, d, h, w) = ((n*Dp + d + pd)*Hp + h + ph)*Wp + w + pw
+// in which a filter tap is a constant shift `off` (hupr_conv_desc.w_k_off) and the convolution's zero padding is literal zeros.
+// TMA needs 16-byte aligned box starts, so the +-1 shifts along W cannot be coordinates: the X operand is stored once per kw tap,
+// pre-shifted by `shift` = kw - pw elements, and Wp is a multiple of 8 so that the kd / kh parts of `off` stay aligned.
+// ================================================================================================================================
+namespace hupr {
+
+struct KMajorParams {
+    int n, d, h, w, ld, ch_off;
+    int dp, hp, wp, pd, ph, pw, shift;
+    long long ppad;
+};
+
+__global__ void __launch_bounds__(256)
+to_kmajor_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, const KMajorParams p) {
+    __shared__ uint16_t tile[32][34];
+    const long long pos0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) tile[j][tx] = src[(size_t)(pos0 + j) * p.ld + p.ch_off + c0 + tx];
+    __syncthreads();
+    long long pos = pos0 + tx;
+    const int w = (int)(pos % p.w); pos /= p.w;
+    const int h = (int)(pos % p.h); pos /= p.h;
+    const int d = (int)(pos % p.d);
+    const int n = (int)(pos / p.d);
+    const long long P = (((long long)n * p.dp + d + p.pd) * p.hp + h + p.ph) * p.wp + w + p.pw - p.shift;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) dst[(size_t)(c0 + j) * p.ppad + P] = tile[tx][j];
+}
+
+}  // namespace hupr
+
+extern "C" int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c,
+                              void* dst_hi, void* dst_lo, int dp, int hp, int wp, int pd, int ph, int pw, int shift, long long ppad,
+                              void* stream) {
+    if (!src_hi || !dst_hi || n <= 0 || d <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 32 || ch_off < 0 || ch_off + c > ld) return HUPR_ERR_BAD_ARG;
+    if ((src_lo == nullptr) != (dst_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    const long long positions = (long long)n * d * h * w;
+    if (positions % 32 || d + pd > dp || h + ph > hp || w + pw > wp || pd < 0 || ph < 0 || pw < 0) return HUPR_ERR_BAD_ARG;
+    if ((long long)(pd * hp + ph) * wp + pw - shift < 0 || shift < -pw - 1) return HUPR_ERR_BAD_ARG;       // first / last interior cell stay inside dst
+    if (ppad < (long long)n * dp * hp * wp || positions / 32 > 2147483647LL || c / 32 > 65535) return HUPR_ERR_BAD_ARG;
+    int rc = check_sm100();
+    if (rc != HUPR_OK) return rc;
+    KMajorParams p;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.ld = ld; p.ch_off = ch_off;
+    p.dp = dp; p.hp = hp; p.wp = wp; p.pd = pd; p.ph = ph; p.pw = pw; p.shift = shift; p.ppad = ppad;
+    const dim3 grid((unsigned)(positions / 32), c / 32), block(32, 8);
+    to_kmajor_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)src_hi, (uint16_t*)dst_hi, p);
+    if (src_lo) to_kmajor_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)src_lo, (uint16_t*)dst_lo, p);
+    return launch_status(src_lo ? 2 : 1);
+}

@@ -24,6 +24,8 @@ struct ConvParams {
     int o_ld, o_ch_off;
     float* o_f32;
     int o_f32_ld;
+    int w_k_off;                   // added to the B operand's contracted-axis coordinate (shifted correlation; out of range = zero fill)
+    int kb_per_split, k_split, atomic;
 };
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos`.
@@ -65,6 +67,12 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
             const float sl = __ldg(p.slope + ch0 + j);
             v[j] = v[j] > 0.0f ? v[j] : v[j] * sl;
         }
+    }
+    if (p.atomic) {     // split-K partial sum (no scale / shift / residual / activation on this path)
+        float* dst = p.o_f32 + pos * p.o_f32_ld + ch0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+        return;
     }
     if (p.o_f32) {
         float4* dst = reinterpret_cast<float4*>(p.o_f32 + pos * p.o_f32_ld + ch0);

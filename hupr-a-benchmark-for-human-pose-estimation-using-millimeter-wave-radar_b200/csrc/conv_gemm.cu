@@ -61,7 +61,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int n = t / p.d_out;
     const int w0 = tw * p.bw, h0 = th * p.bh;
     const int n0 = blockIdx.y * BN;
-    const int num_kb = p.kd * p.kh * p.kw * p.cin_blocks;
+    const int total_kb = p.kd * p.kh * p.kw * p.cin_blocks;
+    const int kb_begin = blockIdx.z * p.kb_per_split;                      // split-K: this CTA contracts k-blocks [kb_begin, kb_end)
+    const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -91,9 +93,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int it = kb - kb_begin;
+                const int s = it % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
                 const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
@@ -102,10 +105,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const int ac = p.a_ch_off + cb * BK, aw = w0 + tkw - p.pw, ah = h0 + tkh - p.ph, ad = od + tkd - p.pd;
                 const int b2 = p.w_batched ? n : tap;
                 tma_load_5d(st, &tmA_hi, &full[s], ac, aw, ah, ad, n);
-                tma_load_3d(st + Cfg::kPlanes * Cfg::kABytes, &tmB_hi, &full[s], cb * BK, n0, b2);
+                tma_load_3d(st + Cfg::kPlanes * Cfg::kABytes, &tmB_hi, &full[s], cb * BK + p.w_k_off, n0, b2);
                 if (NPROD == 3) {
                     tma_load_5d(st + Cfg::kABytes, &tmA_lo, &full[s], ac, aw, ah, ad, n);
-                    tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK, n0, b2);
+                    tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK + p.w_k_off, n0, b2);
                 }
             }
         }
@@ -114,9 +117,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int it = kb - kb_begin;
+                const int s = it % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
@@ -128,11 +132,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (NPROD == 3) {
                         const uint64_t da_lo = make_smem_desc(st + Cfg::kABytes);
                         const uint64_t db_lo = make_smem_desc(st + 2 * Cfg::kABytes + Cfg::kBBytes);
-                        umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (it | k) != 0);
                         umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
                         umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, 1u);
                     } else {
-                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
                     }
                 }
                 tc_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
@@ -201,7 +205,7 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
             return HUPR_ERR_CUDA;
         configured = true;
     }
-    dim3 grid(m_tiles, p.cout / BN, 1);
+    dim3 grid(m_tiles, p.cout / BN, p.k_split);
     conv_gemm_kernel<BN, NPROD><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
@@ -248,6 +252,16 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     p.r_hi = (const __nv_bfloat16*)d->r_hi; p.r_lo = (const __nv_bfloat16*)d->r_lo; p.r_ld = d->r_ld; p.r_ch_off = d->r_ch_off;
     p.o_hi = (__nv_bfloat16*)d->o_hi; p.o_lo = (__nv_bfloat16*)d->o_lo; p.o_ld = d->o_ld; p.o_ch_off = d->o_ch_off;
     p.o_f32 = d->o_f32; p.o_f32_ld = d->o_f32_ld;
+    p.w_k_off = d->w_k_off;
+    {   // split-K (wgrad-style contractions: few output tiles, very long K): partial sums are added atomically into o_f32
+        const int total_kb = taps * p.cin_blocks;
+        int ks = d->k_split > 1 ? d->k_split : 1;
+        if (ks > total_kb) ks = total_kb;
+        if (ks > 1 && (!d->o_f32 || d->o_hi || d->scale || d->shift || d->slope || d->r_hi)) return HUPR_ERR_BAD_ARG;
+        p.kb_per_split = (total_kb + ks - 1) / ks;
+        p.k_split = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+        p.atomic = p.k_split > 1 ? 1 : 0;
+    }
 
     {   // 3-tap-in-H convolutions with enough tiles go to the halo-reuse kernel (conv_halo.cu)
         const int hr = conv_halo_try(d, p, static_cast<cudaStream_t>(stream));

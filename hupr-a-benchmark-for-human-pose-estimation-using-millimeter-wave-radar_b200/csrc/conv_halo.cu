@@ -211,7 +211,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
 // Returns HUPR_OK after launching, or a positive value (1) if the shape is not handled here (caller falls through to the
 // generic kernel).  Arguments were validated by hupr_conv_gemm.
 int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream) {
-    if (d->a_lo == nullptr || d->w_batched) return 1;
+    if (d->a_lo == nullptr || d->w_batched || d->k_split > 1 || d->w_k_off != 0) return 1;
     if (d->kh != 3 || d->ph != 1 || d->kw != 2 * d->pw + 1) return 1;
     if (d->w != 16 && d->w != 32 && d->w != 64) return 1;
     const int bw = d->w, bh = HM / bw;

@@ -71,7 +71,7 @@ class SplitTensor(object):
 
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -90,6 +90,7 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.pd, desc.ph, desc.pw = pad
     desc.w_batched = 1 if w_batched else 0
     desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
+    desc.k_split, desc.w_k_off = k_split, w_k_off
     if a.hi.stride(0) != d * h * w * ca:        # overlapping sliding-window view over a frame stream
         if tuple(a.hi.stride()[1:]) != (h * w * ca, w * ca, ca, 1) or (a.lo is not None and a.lo.stride() != a.hi.stride()):
             raise ValueError("conv_gemm: only the sample stride of A may be non-dense")
@@ -286,3 +287,51 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.9
         _call("hupr_adam_step", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), n, lr, betas[0], betas[1], eps, weight_decay, step,
               _C.stream_ptr())
     return params
+
+
+class KMajorGeometry(object):
+    """Zero-padded linear position index shared by the two operands of a weight-gradient GEMM (see hupr_to_kmajor).  Wp is rounded
+    up to a multiple of 8 so that the depth/height parts of a tap offset are 16-byte aligned (a TMA requirement); the +-1 shifts
+    along W are realised as separately stored, pre-shifted copies of the X operand (one per kw tap)."""
+
+    def __init__(self, n, d, h, w, pad):
+        self.n, self.d, self.h, self.w = n, d, h, w
+        self.pd, self.ph, self.pw = pad
+        self.dp, self.hp = d + 2 * pad[0], h + 2 * pad[1]
+        self.wp = -(-(w + 2 * pad[2]) // 8) * 8
+        self.ppad = -(-(n * self.dp * self.hp * self.wp) // 64) * 64
+
+    def tap_offset(self, kd, kh):
+        return ((kd - self.pd) * self.hp + (kh - self.ph)) * self.wp
+
+
+def to_kmajor(x, ch_off, c, geom, out, shift=0):
+    """x SplitTensor [n, d, h, w, ld] channels [ch_off, +c) -> out SplitTensor [c, geom.ppad], written at P - shift (interior cells
+    only; out is zero-filled once by its owner).  ``x`` may have depth 1 while geom.d > 1 (a depth-valid convolution's output
+    placed at d = 0)."""
+    n, d, h, w, ld = x.hi.shape
+    with torch.cuda.device(x.hi.device):
+        _call("hupr_to_kmajor", _p(x.hi), _p(x.lo), n, d, h, w, ld, ch_off, c, _p(out.hi), _p(out.lo),
+              geom.dp, geom.hp, geom.wp, geom.pd, geom.ph, geom.pw, shift, geom.ppad, _C.stream_ptr())
+    return out
+
+
+def conv_wgrad(xts, cin, dyt, rows, geom, kernel, out):
+    """Weight gradient of a stride-1 convolution from position-major operands (hupr_conv_gemm with k_split / w_k_off).
+
+    xts : list of kernel[2] SplitTensors [cin, ppad]: input activations, copy kw pre-shifted by kw - pw (to_kmajor(shift=...))
+    dyt : SplitTensor [rows, ppad]: output gradients in the same index space, rows = cout rounded up to a multiple of 128 (zero rows)
+    out : float32 [taps, rows, cin], zero-filled by the caller; tap order (kd, kh, kw) row-major like torch's weight layout."""
+    ppad = geom.ppad
+    a = SplitTensor(dyt.hi.view(1, 1, 1, rows, ppad), None if dyt.lo is None else dyt.lo.view(1, 1, 1, rows, ppad))
+    tiles = max(1, rows // 128) * max(1, cin // (128 if cin % 128 == 0 else 64))
+    k_split = max(1, min(ppad // 64, (296 + tiles - 1) // tiles))
+    tap = 0
+    for kd in range(kernel[0]):
+        for kh in range(kernel[1]):
+            for kw in range(kernel[2]):
+                xt = xts[kw]
+                w = SplitTensor(xt.hi.view(1, cin, ppad), None if xt.lo is None else xt.lo.view(1, cin, ppad))
+                conv_gemm(a, ppad, w, cin, out_f32=out[tap].view(1, 1, 1, rows, cin), k_split=k_split, w_k_off=geom.tap_offset(kd, kh))
+                tap += 1
+    return out

@@ -81,6 +81,12 @@ typedef struct hupr_conv_desc {
     int w_ld, w_ch_off;                                           /* weight row stride / first column in elements (0, 0 = dense [..][cout][cin]) */
     long long a_n_stride;                                         /* elements between samples of A (0 = dense d*h*w*ca); smaller values give
                                                                      overlapping sliding windows over a frame stream */
+    int k_split;                                                  /* > 1: split the contraction over this many CTAs per output tile and ADD the
+                                                                     partial sums atomically into o_f32 (pre-zeroed by the caller; no scale / shift /
+                                                                     slope / residual / bf16 output).  For contractions with few output tiles and a very
+                                                                     long K: the weight-gradient GEMMs (K = positions) */
+    int w_k_off;                                                  /* added to the weight operand's contracted-axis coordinate (may be negative; out of
+                                                                     range reads zero): shifted correlations over position-major operands */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
@@ -195,6 +201,13 @@ int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const 
  *
  * hupr_adam_step: one torch.optim.Adam step with coupled L2 weight decay (tools/base.py:47: lr 1e-4, betas (0.9, 0.999), eps 1e-8,
  * weight_decay 1e-4) over a flat fp32 buffer of n elements; `step` is the 1-based step count used for the bias corrections. */
+/* Position-major copy for the weight-gradient GEMMs: src bf16 split [n][d][h][w][ld] channels ch_off..+c  ->  dst [c][ppad] with
+ * P(n,d,h,w) = ((n*dp + d + pd)*hp + h + ph)*wp + w + pw.  The caller zero-fills dst once (padding cells are never written); a filter
+ * tap is then the constant shift ((kd-pd)*hp + (kh-ph))*wp + (kw-pw) passed as hupr_conv_desc.w_k_off, and
+ *   dW[tap][co][ci] = sum_P dYt[co][P] * Xt[ci][P + off]   is   hupr_conv_gemm(A = dYt, W = Xt, k_split, w_k_off)
+ * (what autograd computes for the weights of nn.Conv3d / nn.Conv2d). */
+int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c,
+                   void* dst_hi, void* dst_lo, int dp, int hp, int wp, int pd, int ph, int pw, int shift, long long ppad, void* stream);
 int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
                           float* d_heat_logits, float* d_gcn_pre, void* stream);
 int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,

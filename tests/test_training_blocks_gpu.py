@@ -75,3 +75,39 @@ def test_conv_dgrad_via_flipped_filters_matches_autograd(shape):
     torch.cuda.synchronize()
     got = out.float().permute(0, 4, 1, 2, 3).double()
     assert float((got - x.grad).abs().max() / x.grad.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 64, 128, 4, 32, 32, (3, 3, 3), (1, 1, 1)),
+    (1, 64, 64, 2, 16, 16, (3, 3, 3), (1, 1, 1)),
+    (2, 128, 64, 1, 32, 32, (1, 3, 3), (0, 1, 1)),
+    (2, 64, 64, 1, 64, 64, (1, 1, 1), (0, 0, 0)),
+    (2, 64, 64, 8, 64, 64, (8, 1, 1), (0, 0, 0)),       # temporal merge: depth-valid, dY lives at d = 0 of the input index space
+])
+def test_conv_wgrad_from_position_major_operands_matches_autograd(shape):
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    n, cin, cout, d, h, w, kernel, pad = shape
+    torch.manual_seed(14)
+    x = torch.randn(n, cin, d, h, w, device="cuda", dtype=torch.float64)
+    wt = torch.randn(cout, cin, *kernel, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(x, wt, padding=pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    X = SplitTensor.from_float(x.float().permute(0, 2, 3, 4, 1).contiguous())
+    DY = SplitTensor.from_float(dy.float().permute(0, 2, 3, 4, 1).contiguous())
+    geom = ops.KMajorGeometry(n, d, h, w, pad)
+    rows = -(-cout // 128) * 128
+    xts = []
+    for kw in range(kernel[2]):
+        xt = SplitTensor.empty((cin, geom.ppad), "cuda", zero=True)
+        ops.to_kmajor(X, 0, cin, geom, xt, shift=kw - pad[2])
+        xts.append(xt)
+    dyt = SplitTensor.empty((rows, geom.ppad), "cuda", zero=True)
+    ops.to_kmajor(DY, 0, cout, geom, dyt)
+    taps = kernel[0] * kernel[1] * kernel[2]
+    out = torch.zeros(taps, rows, cin, device="cuda")
+    ops.conv_wgrad(xts, cin, dyt, rows, geom, kernel, out)
+    torch.cuda.synchronize()
+    got = out[:, :cout].permute(1, 2, 0).reshape(cout, cin, *kernel).double()
+    assert float((got - wt.grad).abs().max() / wt.grad.abs().max()) < 3e-5
