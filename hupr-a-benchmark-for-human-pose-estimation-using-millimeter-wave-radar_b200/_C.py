@@ -43,8 +43,14 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class TensorView(ctypes.Structure):
+    """Mirror of ``hupr_tensor_view``."""
+    _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("ld", ctypes.c_int), ("ch_off", ctypes.c_int)]
+
+
 _P = ctypes.c_void_p
 _I = ctypes.c_int
+_TV = ctypes.POINTER(TensorView)
 
 # name -> (restype, argtypes); must list every symbol of include/hupr_b200.h
 SIGNATURES = {
@@ -68,6 +74,13 @@ SIGNATURES = {
     "hupr_gcn_mix": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "hupr_gcn_heads": (ctypes.c_int, [_P, _I, _P, _I, _P]),
     "hupr_keypoints_argmax": (ctypes.c_int, [_P, _I, _P, _P, _P]),
+    "hupr_channel_sums": (ctypes.c_int, [_I, _TV, _TV, _TV, _P, _P, ctypes.c_longlong, _I, _P, _P, _P]),
+    "hupr_affine_act": (ctypes.c_int, [_TV, _P, _P, _TV, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_bn_bwd_apply": (ctypes.c_int, [_TV, _TV, _TV, _P, _P, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_act_bwd": (ctypes.c_int, [_TV, _TV, _P, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_accumulate": (ctypes.c_int, [_TV, _TV, _P, _I, _I, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_resample_linear_bwd": (ctypes.c_int, [_TV, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "hupr_softmax_bwd_rows": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _P]),
     "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
     "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

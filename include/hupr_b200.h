@@ -201,6 +201,37 @@ int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const 
  *
  * hupr_adam_step: one torch.optim.Adam step with coupled L2 weight decay (tools/base.py:47: lr 1e-4, betas (0.9, 0.999), eps 1e-8,
  * weight_decay 1e-4) over a flat fp32 buffer of n elements; `step` is the 1-based step count used for the bias corrections. */
+/* Channels-last bf16 split view used by the training kernels: element (pos, ch) lives at index pos*ld + ch_off + ch of both planes
+ * (lo may be NULL for single-bf16 tensors). */
+typedef struct hupr_tensor_view { void* hi; void* lo; int ld, ch_off; } hupr_tensor_view;
+
+/* Training-mode element-wise / reduction kernels (what autograd + nn.BatchNorm3d(training) + nn.PReLU + F.interpolate backward do around
+ * the convolutions of /root/reference/models/layers.py:8-70,186-217 and the softmax of :131).  `positions` rows of `c` channels each.
+ *   hupr_channel_sums  s1[ch] += sum f1, s2[ch] += sum f2 (double, caller zero-fills):
+ *        mode 0 STATS   a = z                      f1 = z,  f2 = z^2                      BatchNorm batch statistics
+ *        mode 1 BN_BWD  a = g, b = z, mask = y     f1 = g', f2 = g' * (z - mean) * rstd   g' = g * [y > 0] (mask optional)
+ *        mode 2 PRELU   a = g, b = s (optional)    f1 = g * s * [s <= 0], f2 = g          PReLU slope gradient / bias gradient
+ *   hupr_affine_act    out = act(scale1*z + shift1 (+ scale2*r + shift2)); act(v) = v > 0 ? v : slope[ch]*v  (NULL scale = 1, shift = 0,
+ *                      slope NULL = identity)
+ *   hupr_bn_bwd_apply  out = k1 * (g' - k2 - (z - mean)*rstd * k3)          k1 = gamma*rstd, k2 = mean(g'), k3 = mean(g' zhat)
+ *   hupr_act_bwd       out = g * (s > 0 ? 1 : slope[ch])
+ *   hupr_accumulate    out = a + b + f   (a, b bf16 split views, f float [positions][f_ld] at f_off; each optional)
+ *   hupr_resample_linear_bwd  adjoint of hupr_resample_linear: din float [n][di][hi][wi][in_ld] (+= , caller zero-fills)
+ *   hupr_softmax_bwd_rows     ds = p * (dp - sum_m p*dp) per row (p bf16 split, dp float, ds bf16 split; cols % 4 == 0, <= 4096) */
+int hupr_channel_sums(int mode, const hupr_tensor_view* a, const hupr_tensor_view* b, const hupr_tensor_view* mask, const float* mean,
+                      const float* rstd, long long positions, int c, double* s1, double* s2, void* stream);
+int hupr_affine_act(const hupr_tensor_view* z, const float* scale1, const float* shift1, const hupr_tensor_view* r, const float* scale2,
+                    const float* shift2, const float* slope, const hupr_tensor_view* out, long long positions, int c, void* stream);
+int hupr_bn_bwd_apply(const hupr_tensor_view* g, const hupr_tensor_view* z, const hupr_tensor_view* mask, const float* mean, const float* rstd,
+                      const float* k1, const float* k2, const float* k3, const hupr_tensor_view* out, long long positions, int c, void* stream);
+int hupr_act_bwd(const hupr_tensor_view* g, const hupr_tensor_view* s, const float* slope, const hupr_tensor_view* out, long long positions,
+                 int c, void* stream);
+int hupr_accumulate(const hupr_tensor_view* a, const hupr_tensor_view* b, const float* f, int f_ld, int f_off, const hupr_tensor_view* out,
+                    long long positions, int c, void* stream);
+int hupr_resample_linear_bwd(const hupr_tensor_view* g, int n, int dout, int ho, int wo, int c, float* din, int di, int hi, int wi, int in_ld,
+                             int in_ch_off, void* stream);
+int hupr_softmax_bwd_rows(const void* p_hi, const void* p_lo, const float* dp, void* ds_hi, void* ds_lo, long long rows, int cols, void* stream);
+
 /* Position-major copy for the weight-gradient GEMMs: src bf16 split [n][d][h][w][ld] channels ch_off..+c  ->  dst [c][ppad] with
  * P(n,d,h,w) = ((n*dp + d + pd)*hp + h + ph)*wp + w + pw.  The caller zero-fills dst once (padding cells are never written); a filter
  * tap is then the constant shift ((kd-pd)*hp + (kh-ph))*wp + (kw-pw) passed as hupr_conv_desc.w_k_off, and

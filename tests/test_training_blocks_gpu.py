@@ -111,3 +111,98 @@ def test_conv_wgrad_from_position_major_operands_matches_autograd(shape):
     torch.cuda.synchronize()
     got = out[:, :cout].permute(1, 2, 0).reshape(cout, cin, *kernel).double()
     assert float((got - wt.grad).abs().max() / wt.grad.abs().max()) < 3e-5
+
+
+def _cl(x):
+    """NCDHW float -> SplitTensor channels-last."""
+    from hupr_b200.ops import SplitTensor
+    return SplitTensor.from_float(x.float().permute(0, 2, 3, 4, 1).contiguous().cuda())
+
+
+def _nc(t):
+    return t.float().permute(0, 4, 1, 2, 3).cpu().double()
+
+
+def test_batchnorm_train_forward_backward_match_autograd():
+    """relu(BN(z)) with batch statistics, forward and backward, assembled from hupr_channel_sums / hupr_affine_act /
+    hupr_bn_bwd_apply exactly as the training step does (layers.py:45-53 in training mode)."""
+    from hupr_b200 import train_ops as T
+    from hupr_b200.ops import SplitTensor
+    torch.manual_seed(15)
+    n, c, d, h, w = 2, 64, 4, 16, 16
+    z = (torch.randn(n, c, d, h, w, dtype=torch.float64) * 1.7 + 0.3).requires_grad_()
+    gamma = (torch.rand(c, dtype=torch.float64) + 0.5).requires_grad_()
+    beta = (torch.randn(c, dtype=torch.float64) * 0.2).requires_grad_()
+    y = F.relu(F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5))
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    N = n * d * h * w
+    Z = SplitTensor.empty((n, d, h, w, 2 * c), "cuda", zero=True)         # z lives in channels [c, 2c) of a wider buffer
+    Zsrc = _cl(z.detach())
+    Z.hi[..., c:] = Zsrc.hi; Z.lo[..., c:] = Zsrc.lo
+    s1 = torch.zeros(c, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
+    T.channel_sums(T.SUMS_STATS, (Z, c), c, s1, s2)
+    mean = s1 / N
+    var = s2 / N - mean * mean
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale = (gamma.detach().cuda() * rstd).float(); shift = (beta.detach().cuda() - mean * gamma.detach().cuda() * rstd).float()
+    Y = SplitTensor.empty((n, d, h, w, c), "cuda")
+    T.affine_act((Z, c), c, Y, scale1=scale, shift1=shift, slope=torch.zeros(c, device="cuda"))
+    torch.cuda.synchronize()
+    assert float((_nc(Y) - y.detach()).abs().max()) < 3e-5 * float(y.abs().max())
+    G = _cl(gy)
+    t1 = torch.zeros_like(s1); t2 = torch.zeros_like(s1)
+    meanf, rstdf = mean.float(), rstd.float()
+    T.channel_sums(T.SUMS_BN_BWD, G, c, t1, t2, b=(Z, c), mask=Y, mean=meanf, rstd=rstdf)
+    DZ = SplitTensor.empty((n, d, h, w, c), "cuda")
+    T.bn_bwd_apply(G, (Z, c), c, meanf, rstdf, scale, (t1 / N).float(), (t2 / N).float(), DZ, mask=Y)
+    torch.cuda.synchronize()
+    assert float((t1.cpu() - beta.grad).abs().max()) < 1e-4 * float(beta.grad.abs().max())
+    assert float((t2.cpu() - gamma.grad).abs().max()) < 1e-4 * float(gamma.grad.abs().max())
+    assert float((_nc(DZ) - z.grad).abs().max()) < 5e-5 * float(z.grad.abs().max())
+
+
+def test_prelu_resample_softmax_backward_match_autograd():
+    from hupr_b200 import train_ops as T
+    from hupr_b200.ops import SplitTensor
+    torch.manual_seed(16)
+    # PReLU backward + slope gradient
+    n, c, d, h, w = 2, 64, 1, 16, 16
+    s = torch.randn(n, c, d, h, w, dtype=torch.float64, requires_grad=True)
+    a = torch.tensor([0.3], dtype=torch.float64, requires_grad=True)
+    y = F.prelu(s, a); g = torch.randn_like(y); y.backward(g)
+    S, G = _cl(s.detach()), _cl(g)
+    DS = SplitTensor.empty((n, d, h, w, c), "cuda")
+    T.act_bwd(G, S, c, torch.full((c,), 0.3, device="cuda"), DS)
+    p1 = torch.zeros(c, dtype=torch.float64, device="cuda"); p2 = torch.zeros_like(p1)
+    T.channel_sums(T.SUMS_PRELU, G, c, p1, p2, b=S)
+    torch.cuda.synchronize()
+    assert float((_nc(DS) - s.grad).abs().max()) < 3e-5 * float(s.grad.abs().max())
+    assert abs(float(p1.sum()) - float(a.grad)) < 1e-4 * abs(float(a.grad)) and float((p2.cpu() - g.sum(dim=(0, 2, 3, 4))).abs().max()) < 1e-3
+    # resample backward (trilinear 0.5x and bilinear 2x, align_corners)
+    for shape, out in (((2, 64, 8, 32, 32), (4, 16, 16)), ((1, 64, 1, 16, 16), (1, 32, 32))):
+        x = torch.randn(shape, dtype=torch.float64, requires_grad=True)
+        if shape[2] == 1:
+            yy = F.interpolate(x[:, :, 0], size=out[1:], mode="bilinear", align_corners=True).unsqueeze(2)
+        else:
+            yy = F.interpolate(x, size=out, mode="trilinear", align_corners=True)
+        gg = torch.randn_like(yy); yy.backward(gg)
+        din = torch.zeros((shape[0], shape[2], shape[3], shape[4], shape[1]), device="cuda")
+        T.resample_linear_bwd(_cl(gg), shape[1], din)
+        torch.cuda.synchronize()
+        assert float((din.permute(0, 4, 1, 2, 3).cpu().double() - x.grad).abs().max()) < 3e-5 * float(x.grad.abs().max())
+    # softmax backward
+    logits = (torch.randn(40, 1024, dtype=torch.float64) * 3).requires_grad_()
+    p = torch.softmax(logits, dim=1); gp = torch.randn_like(p); p.backward(gp)
+    P = SplitTensor.from_float(p.detach().float().cuda())
+    DSm = SplitTensor.empty((40, 1024), "cuda")
+    T.softmax_bwd_rows(P, gp.float().cuda(), DSm)
+    torch.cuda.synchronize()
+    assert float((DSm.float().cpu().double() - logits.grad).abs().max()) < 5e-5 * float(logits.grad.abs().max())
+    # accumulate: split + split + float -> split
+    A, B = SplitTensor.from_float(torch.randn(4, 8, 64).cuda()), SplitTensor.from_float(torch.randn(4, 8, 64).cuda())
+    f = torch.randn(4, 8, 128, device="cuda")
+    O = SplitTensor.empty((4, 8, 64), "cuda")
+    T.accumulate(O, 64, a=A, b=B, f=f, f_off=64)
+    torch.cuda.synchronize()
+    assert float((O.float() - (A.float() + B.float() + f[..., 64:])).abs().max()) < 1e-4
