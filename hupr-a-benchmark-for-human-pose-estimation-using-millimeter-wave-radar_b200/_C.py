@@ -81,6 +81,10 @@ SIGNATURES = {
     "hupr_accumulate": (ctypes.c_int, [_TV, _TV, _P, _I, _I, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_resample_linear_bwd": (ctypes.c_int, [_TV, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "hupr_softmax_bwd_rows": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _P]),
+    "hupr_gcn_bias_grad": (ctypes.c_int, [_P, _P, _P, _I, _P]),
+    "hupr_gcn_heads_bwd": (ctypes.c_int, [_P, _P, _I, _P]),
+    "hupr_gcn_nodes_bwd": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "hupr_mnet_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
     "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

@@ -416,3 +416,186 @@ extern "C" int hupr_softmax_bwd_rows(const void* p_hi, const void* p_lo, const f
                                                                             (__nv_bfloat16*)ds_hi, (__nv_bfloat16*)ds_lo, cols);
     return finish(1);
 }
+
+// ================================================================================================================================
+// Backward pieces of the PRGCN head and of MNet (reference: autograd of models/gcn_networks.py:23-64, models/chirp_networks.py:17-21).
+// ================================================================================================================================
+namespace hupr {
+
+constexpr int kTJ = 14;
+
+// dbias[q][j] = sum_b dYt[(b, j)][q]      (dYt: bf16 split rows [(b, j)][1024])
+__global__ void __launch_bounds__(256)
+gcn_bias_grad_kernel(const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo, float* __restrict__ dbias, int batch) {
+    const int gid = blockIdx.x * 256 + threadIdx.x;       // (j, q)
+    if (gid >= kTJ * 1024) return;
+    const int j = gid >> 10, q = gid & 1023;
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) {
+        const size_t o = (size_t)(b * kTJ + j) * 1024 + q;
+        s += __bfloat162float(g_hi[o]) + __bfloat162float(g_lo[o]);
+    }
+    dbias[q * kTJ + j] = s;
+}
+
+// Adjoint of gcn_heads (bilinear x2 of the 32x32 maps): d_pre float [B][14][64][64] -> dYt float rows [(b, j)][1024] (+=, zero-filled).
+__global__ void __launch_bounds__(256)
+gcn_heads_bwd_kernel(const float* __restrict__ d_pre, float* __restrict__ dyt, int batch) {
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    if (gid >= batch * kTJ * 4096) return;
+    const int pos = gid & 4095, bj = gid >> 12;
+    const int oh = pos >> 6, ow = pos & 63;
+    const float scale = 31.0f / 63.0f;
+    const float fh = scale * oh, fw = scale * ow;
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < 31), w1 = w0 + (w0 < 31);
+    const float lh1 = fh - h0, lw1 = fw - w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+    const float g = __ldg(d_pre + gid);
+    float* m = dyt + (size_t)bj * 1024;
+    atomicAdd(m + h0 * 32 + w0, lh0 * lw0 * g);
+    atomicAdd(m + h0 * 32 + w1, lh0 * lw1 * g);
+    atomicAdd(m + h1 * 32 + w0, lh1 * lw0 * g);
+    atomicAdd(m + h1 * 32 + w1, lh1 * lw1 * g);
+}
+
+// Adjoint of gcn_nodes' node path: dSt0 (bf16 split rows [(b, j')][1024]) -> dx[b][node][k] = sum_j' A[k][j'] dSt0[(b, j')][node]
+// -> scattered through the bilinear x0.5 stencil into d_logits float channels-last [B][4096][ld] (+=).
+__global__ void __launch_bounds__(256)
+gcn_nodes_bwd_kernel(const __nv_bfloat16* __restrict__ s_hi, const __nv_bfloat16* __restrict__ s_lo, const float* __restrict__ adj,
+                     float* __restrict__ d_logits, int ld, int batch) {
+    __shared__ float sA[kTJ * kTJ];
+    if (threadIdx.x < kTJ * kTJ) sA[threadIdx.x] = __ldg(adj + threadIdx.x);
+    __syncthreads();
+    const int gid = blockIdx.x * 256 + threadIdx.x;
+    if (gid >= batch * 1024) return;
+    const int b = gid >> 10, node = gid & 1023;
+    float ds[kTJ];
+#pragma unroll
+    for (int j = 0; j < kTJ; ++j) {
+        const size_t o = (size_t)(b * kTJ + j) * 1024 + node;
+        ds[j] = __bfloat162float(s_hi[o]) + __bfloat162float(s_lo[o]);
+    }
+    const int oh = node >> 5, ow = node & 31;
+    const float scale = 63.0f / 31.0f;
+    const float fh = scale * oh, fw = scale * ow;
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < 63), w1 = w0 + (w0 < 63);
+    const float lh1 = fh - h0, lw1 = fw - w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+    float* base = d_logits + (size_t)b * 4096 * ld;
+#pragma unroll
+    for (int k = 0; k < kTJ; ++k) {
+        float dx = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTJ; ++j) dx = fmaf(sA[k * kTJ + j], ds[j], dx);
+        atomicAdd(base + (size_t)(h0 * 64 + w0) * ld + k, lh0 * lw0 * dx);
+        atomicAdd(base + (size_t)(h0 * 64 + w1) * ld + k, lh0 * lw1 * dx);
+        atomicAdd(base + (size_t)(h1 * 64 + w0) * ld + k, lh1 * lw0 * dx);
+        atomicAdd(base + (size_t)(h1 * 64 + w1) * ld + k, lh1 * lw1 * dx);
+    }
+}
+
+// MNet backward: the max over the 4 chirp pairs routes each output gradient to one pair; weights [32][2][2] and bias [32] gradients
+// are reduced over all positions (double atomics, 160 per CTA).
+__global__ void __launch_bounds__(256)
+mnet_bwd_kernel(const float* __restrict__ vrdae, const float* __restrict__ weight, const float* __restrict__ bias,
+                const __nv_bfloat16* __restrict__ g_hi, const __nv_bfloat16* __restrict__ g_lo, double* __restrict__ dw /* [32][4] */,
+                double* __restrict__ db /* [32] */, int n_slots) {
+    __shared__ float sW[32 * 4 + 32];
+    __shared__ float sRed[8][160];
+    if (threadIdx.x < 160) sW[threadIdx.x] = threadIdx.x < 128 ? __ldg(weight + threadIdx.x) : __ldg(bias + threadIdx.x - 128);
+    __syncthreads();
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const bool live = gid < (size_t)n_slots * 4096;
+    float m[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m[j] = 0.f;
+    if (live) {
+        const size_t slot = gid / 4096;
+        const int pos = (int)(gid % 4096);
+        const float4* base = reinterpret_cast<const float4*>(vrdae + slot * (16 * 4096 * 8) + (size_t)pos * 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 a = __ldg(base + (size_t)j * (4096 * 2));
+            const float4 b = __ldg(base + (size_t)j * (4096 * 2) + 1);
+            m[j] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * 0.125f;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int o = 0; o < 32; ++o) {
+        float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            const float w00 = sW[o * 4], w01 = sW[o * 4 + 1], w10 = sW[o * 4 + 2], w11 = sW[o * 4 + 3], bb = sW[128 + o];
+            float best = -INFINITY;
+            int bt = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float y = fmaf(w11, m[9 + 2 * t], fmaf(w10, m[8 + 2 * t], fmaf(w01, m[2 * t + 1], w00 * m[2 * t]))) + bb;
+                if (y > best) { best = y; bt = t; }       // first maximum wins (torch max_pool3d backward)
+            }
+            const float g = __bfloat162float(g_hi[gid * 32 + o]) + (g_lo ? __bfloat162float(g_lo[gid * 32 + o]) : 0.f);
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (t == bt) { m0 = m[2 * t]; m1 = m[2 * t + 1]; m2 = m[8 + 2 * t]; m3 = m[9 + 2 * t]; }
+            }
+            c[0] = g * m0; c[1] = g * m1; c[2] = g * m2; c[3] = g * m3; c[4] = g;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], s);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sRed[warp][o * 5 + k] = c[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 160) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sRed[w][threadIdx.x];
+        const int o = threadIdx.x / 5, k = threadIdx.x % 5;
+        if (k < 4) atomicAdd(dw + o * 4 + k, (double)s);
+        else atomicAdd(db + o, (double)s);
+    }
+}
+
+}  // namespace hupr
+
+extern "C" int hupr_gcn_bias_grad(const void* g_hi, const void* g_lo, float* dbias, int batch, void* stream) {
+    if (batch <= 0 || !g_hi || !g_lo || !dbias) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    gcn_bias_grad_kernel<<<(kTJ * 1024 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g_hi, (const __nv_bfloat16*)g_lo, dbias, batch);
+    return finish(1);
+}
+
+extern "C" int hupr_gcn_heads_bwd(const float* d_pre, float* dyt, int batch, void* stream) {
+    if (batch <= 0 || !d_pre || !dyt) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    gcn_heads_bwd_kernel<<<(batch * kTJ * 4096 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_pre, dyt, batch);
+    return finish(1);
+}
+
+extern "C" int hupr_gcn_nodes_bwd(const void* s_hi, const void* s_lo, const float* adj, float* d_logits, int ld, int batch, void* stream) {
+    if (batch <= 0 || !s_hi || !s_lo || !adj || !d_logits || ld < kTJ) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    gcn_nodes_bwd_kernel<<<(batch * 1024 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)s_hi, (const __nv_bfloat16*)s_lo, adj,
+                                                                                      d_logits, ld, batch);
+    return finish(1);
+}
+
+extern "C" int hupr_mnet_bwd(const float* vrdae, const float* weight, const float* bias, const void* g_hi, const void* g_lo, double* dweight,
+                             double* dbias, int n_slots, void* stream) {
+    if (n_slots <= 0 || !vrdae || !weight || !bias || !g_hi || !dweight || !dbias) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const size_t total = (size_t)n_slots * 4096;
+    mnet_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vrdae, weight, bias, (const __nv_bfloat16*)g_hi,
+                                                                                       (const __nv_bfloat16*)g_lo, dweight, dbias, n_slots);
+    return finish(1);
+}

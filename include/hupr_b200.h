@@ -232,6 +232,17 @@ int hupr_resample_linear_bwd(const hupr_tensor_view* g, int n, int dout, int ho,
                              int in_ch_off, void* stream);
 int hupr_softmax_bwd_rows(const void* p_hi, const void* p_lo, const float* dp, void* ds_hi, void* ds_lo, long long rows, int cols, void* stream);
 
+/* Backward pieces of the PRGCN head and of MNet (autograd of /root/reference/models/gcn_networks.py:23-64, chirp_networks.py:17-21):
+ *   hupr_gcn_bias_grad  dbias[q][j] = sum_b dYt[(b,j)][q]                      (dYt bf16 split rows [(b,j)][1024]; dbias float [1024][14])
+ *   hupr_gcn_heads_bwd  adjoint of hupr_gcn_heads' bilinear x2: d_pre float [batch][14][64][64] -> dyt float rows [(b,j)][1024] (+=)
+ *   hupr_gcn_nodes_bwd  adjoint of hupr_gcn_nodes' node path: dSt0 rows -> d_logits float channels-last [batch][4096][ld] (+=)
+ *   hupr_mnet_bwd       weight [32][2][2] / bias [32] gradients of MNet (double, +=) from the chirp-feature gradient [n_slots][4096][32] */
+int hupr_gcn_bias_grad(const void* g_hi, const void* g_lo, float* dbias, int batch, void* stream);
+int hupr_gcn_heads_bwd(const float* d_pre, float* dyt, int batch, void* stream);
+int hupr_gcn_nodes_bwd(const void* s_hi, const void* s_lo, const float* adj, float* d_logits, int ld, int batch, void* stream);
+int hupr_mnet_bwd(const float* vrdae, const float* weight, const float* bias, const void* g_hi, const void* g_lo, double* dweight, double* dbias,
+                  int n_slots, void* stream);
+
 /* Position-major copy for the weight-gradient GEMMs: src bf16 split [n][d][h][w][ld] channels ch_off..+c  ->  dst [c][ppad] with
  * P(n,d,h,w) = ((n*dp + d + pd)*hp + h + ph)*wp + w + pw.  The caller zero-fills dst once (padding cells are never written); a filter
  * tap is then the constant shift ((kd-pd)*hp + (kh-ph))*wp + (kw-pw) passed as hupr_conv_desc.w_k_off, and

@@ -141,7 +141,13 @@ def make_vrdae(batch, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------ forward
+TRAINING = False      # set by huprnet_forward(training=True): BatchNorm uses batch statistics (model.train(), tools/run.py:66)
+
+
 def _bn(x, sd, prefix):
+    if TRAINING:
+        return F.batch_norm(x, sd[prefix + ".running_mean"].clone(), sd[prefix + ".running_var"].clone(), sd[prefix + ".weight"],
+                            sd[prefix + ".bias"], True, 0.1, 1e-5)
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
                         sd[prefix + ".bias"], False, 0.1, 1e-5)
 
@@ -227,8 +233,33 @@ def decoder(feats_ra, feats_re, sd):
     return logits, prgcn(logits, sd)
 
 
-def huprnet_forward(sd, vrdae_hori, vrdae_vert, return_intermediates=False):
+def huprnet_forward(sd, vrdae_hori, vrdae_vert, return_intermediates=False, training=False):
     """HuPRNet.forward (networks.py:35-41): returns (heatmap [B,14,1,64,64], gcn_heatmap [B,1,14,64,64])."""
+    global TRAINING
+    TRAINING = training
+    try:
+        return _huprnet_forward(sd, vrdae_hori, vrdae_vert, return_intermediates)
+    finally:
+        TRAINING = False
+
+
+def training_gradients(sd, vrdae_hori, vrdae_vert, joints):
+    """Reference training step semantics (tools/run.py:74-78): model.train() forward, loss = BCE + BCE, loss.backward().
+    Returns (loss, loss2, {parameter name: gradient}) computed by torch autograd on the CPU."""
+    from . import loss as oloss
+    import numpy as np
+    names = [k for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k]
+    leaf = {k: (sd[k].clone().requires_grad_() if k in names else sd[k]) for k in sd}
+    heat, gcn = huprnet_forward(leaf, vrdae_hori, vrdae_vert, training=True)
+    b = vrdae_hori.shape[0]
+    targets = torch.from_numpy(np.stack([oloss.generate_target(np.asarray(joints[i]))[0] for i in range(b)]))
+    loss1 = F.binary_cross_entropy(heat.reshape(b, NUM_KEYPOINTS, 64, 64), targets)
+    loss2 = F.binary_cross_entropy(gcn.reshape(b, NUM_KEYPOINTS, 64, 64), targets)
+    (loss1 + loss2).backward()
+    return float((loss1 + loss2).detach()), float(loss2.detach()), {k: leaf[k].grad for k in names}
+
+
+def _huprnet_forward(sd, vrdae_hori, vrdae_vert, return_intermediates=False):
     ra = chirp_net(vrdae_hori, sd, "RAchirpNet")
     re = chirp_net(vrdae_vert, sd, "REchirpNet")
     feats_ra = encoder3d(ra, sd, "RAradarEncoder")

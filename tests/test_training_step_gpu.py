@@ -1,0 +1,209 @@
+"""GPU parity tests of the assembled training step: train-mode forward, hand-written backward of the whole
+MSCSA-PRGCN and Adam, against torch autograd / torch.optim.
+
+A note on the metric.  ReLU / PReLU / max-pool make the gradient a discontinuous function of the pre-activations: an element whose
+pre-activation is within the forward error (~1e-5) of zero gets a different mask in two implementations that round differently,
+and ONE such flip changes a weight gradient by ~1/sqrt(#positions) in relative L2 (measured below: 2e-3 for one flip in 131 072
+elements; 7e-6 with no flip).  The per-block tests therefore search for a seed without flips (checked against a float64
+reference) and assert tight agreement there; the whole-network test asserts loss parity and direction/L2 agreement of every
+gradient tensor with flip-sized tolerances."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cl(x):
+    from hupr_b200.ops import SplitTensor
+    return SplitTensor.from_float(x.float().permute(0, 2, 3, 4, 1).contiguous())
+
+
+def nc(t, c=None):
+    v = t.float().permute(0, 4, 1, 2, 3).double()
+    return v if c is None else v[:, :c]
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def flips(ours, ref):
+    return int(((ours > 0) != (ref > 0)).sum())
+
+
+def test_block2d_backward_matches_autograd_when_no_mask_flips():
+    from hupr_b200 import training as TR
+    from oracle import model as om
+    cin, cout, hw, b = 128, 64, 32, 2
+    prefix = "blk"
+    for seed in range(8):
+        torch.manual_seed(seed)
+        sd = {prefix + ".main.0.weight": torch.randn(cout, cin, 3, 3, device=DEV, dtype=torch.float64) * 0.05,
+              prefix + ".main.1.weight": torch.tensor([0.3], device=DEV, dtype=torch.float64),
+              prefix + ".main.2.weight": torch.randn(cout, cout, 3, 3, device=DEV, dtype=torch.float64) * 0.05,
+              prefix + ".downsample.0.weight": torch.randn(cout, cin, 3, 3, device=DEV, dtype=torch.float64) * 0.05,
+              prefix + ".relu.weight": torch.tensor([0.2], device=DEV, dtype=torch.float64)}
+        for v in sd.values():
+            v.requires_grad_()
+        x = torch.randn(b, cin, hw, hw, device=DEV, dtype=torch.float64, requires_grad=True)
+        y = om.block2d(x, sd, prefix)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        blk = TR.Block2D(prefix, cin, cout)
+        blk.pack({k: v.detach().float() for k, v in sd.items()})
+        out = blk.forward(cl(x.detach().unsqueeze(2)))
+        grads = {}
+        dx = blk.backward(cl(gy.unsqueeze(2)), 0, grads)
+        torch.cuda.synchronize()
+        zc_ref = F.conv2d(x.detach(), sd[prefix + ".main.0.weight"].detach(), padding=1)
+        s_ref = (F.conv2d(F.prelu(zc_ref, sd[prefix + ".main.1.weight"].detach()), sd[prefix + ".main.2.weight"].detach(), padding=1)
+                 + F.conv2d(x.detach(), sd[prefix + ".downsample.0.weight"].detach(), padding=1))
+        if flips(nc(blk.zc)[:, :cout, 0], zc_ref) + flips(nc(blk.s)[:, :cout, 0], s_ref):
+            continue
+        assert rel(nc(out, cout)[:, :, 0], y.detach()) < 3e-5 and rel(nc(dx, cin)[:, :, 0], x.grad) < 5e-5
+        for k in sd:
+            assert rel(grads[k].double().reshape(sd[k].shape), sd[k].grad) < 1e-4, k
+        return
+    pytest.fail("no seed without activation-mask flips found")
+
+
+def test_block3d_train_backward_matches_autograd_when_no_mask_flips():
+    from hupr_b200 import training as TR
+    from oracle import model as om
+    cin, cout, d, hw, b = 64, 64, 2, 16, 1
+    prefix = "b3"
+    for seed in range(12):
+        torch.manual_seed(seed)
+        sd = {}
+        for n, shp in ((".main.0.weight", (cout, cin, 3, 3, 3)), (".main.3.weight", (cout, cout, 3, 3, 3)), (".downsample.0.weight", (cout, cin, 3, 3, 3))):
+            sd[prefix + n] = torch.randn(shp, device=DEV, dtype=torch.float64) * 0.03
+        for bn in (".main.1", ".main.4", ".downsample.1"):
+            sd[prefix + bn + ".weight"] = torch.rand(cout, device=DEV, dtype=torch.float64) + 0.5
+            sd[prefix + bn + ".bias"] = torch.randn(cout, device=DEV, dtype=torch.float64) * 0.1
+            sd[prefix + bn + ".running_mean"] = torch.zeros(cout, device=DEV, dtype=torch.float64)
+            sd[prefix + bn + ".running_var"] = torch.ones(cout, device=DEV, dtype=torch.float64)
+        for k, v in sd.items():
+            if "running" not in k:
+                v.requires_grad_()
+        x = torch.randn(b, cin, d, hw, hw, device=DEV, dtype=torch.float64, requires_grad=True)
+        om.TRAINING = True
+        try:
+            y = om.block3d(x, sd, prefix)
+        finally:
+            om.TRAINING = False
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        blk = TR.Block3D(prefix, cin, cout)
+        params = {k: v.detach().float() for k, v in sd.items() if "running" not in k}
+        buffers = {k: v.detach().float().clone() for k, v in sd.items() if "running" in k}
+        for bn in (".main.1", ".main.4", ".downsample.1"):
+            buffers[prefix + bn + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long, device=DEV)
+        blk.pack(params)
+        out = blk.forward(cl(x.detach()), params, buffers)
+        grads = {}
+        dx = blk.backward(cl(gy), grads)
+        torch.cuda.synchronize()
+        t_ref = F.relu(F.batch_norm(F.conv3d(x.detach(), sd[prefix + ".main.0.weight"].detach(), padding=1), None, None,
+                                    sd[prefix + ".main.1.weight"].detach(), sd[prefix + ".main.1.bias"].detach(), True, 0.1, 1e-5))
+        if flips(nc(blk.t), t_ref) + flips(nc(out), y.detach()):
+            continue
+        assert rel(nc(out), y.detach()) < 3e-5 and rel(nc(dx, cin), x.grad) < 1e-4
+        for k in params:
+            assert rel(grads[k].double().reshape(sd[k].shape), sd[k].grad) < 2e-4, k
+        # running statistics follow nn.BatchNorm3d(momentum=0.1)
+        z1 = F.conv3d(x.detach(), sd[prefix + ".main.0.weight"].detach(), padding=1)
+        assert float((buffers[prefix + ".main.1.running_mean"].double() - 0.1 * z1.mean(dim=(0, 2, 3, 4))).abs().max()) < 1e-5
+        assert float((buffers[prefix + ".main.1.running_var"].double() - (0.9 + 0.1 * z1.var(dim=(0, 2, 3, 4), unbiased=True))).abs().max()) < 1e-4
+        return
+    pytest.fail("no seed without activation-mask flips found")
+
+
+@pytest.mark.parametrize("c,hw", [(64, 16), (256, 16), (128, 32)])
+def test_attention_level_backward_matches_autograd(c, hw):
+    """No kinks in attention: forward (fused for c = 64 / 128) and the recompute-based backward agree to hi/lo precision."""
+    from hupr_b200 import training as TR
+    from hupr_b200.ops import SplitTensor
+    from oracle import model as om
+    torch.manual_seed(0)
+    b, prev = 2, 64
+    lvl = TR.AttentionLevel(0, c, hw, prev)
+    sd = {}
+    for n in TR.L.PROJ_HORI + TR.L.PROJ_VERT:
+        sd["radarDecoder.%s.0.weight" % n] = (torch.randn(c, c, 1, 1, device=DEV, dtype=torch.float64) / c ** 0.5 * 0.7).requires_grad_()
+    ra = torch.randn(b, c, hw, hw, device=DEV, dtype=torch.float64, requires_grad=True)
+    re = torch.randn(b, c, hw, hw, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = torch.cat(om.attention_level(ra, re, sd, 0), 1)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    lvl.pack({k: v.detach().float() for k, v in sd.items()})
+    cat = SplitTensor.empty((b, 1, hw, hw, prev + 4 * c), DEV, zero=True)
+    lvl.forward(cl(ra.detach().unsqueeze(2)), cl(re.detach().unsqueeze(2)), cat)
+    dcat = torch.zeros(b, prev + 4 * c, 1, hw, hw, device=DEV, dtype=torch.float64)
+    dcat[:, prev:] = gy.unsqueeze(2)
+    grads = {}
+    dra, dre = lvl.backward(cl(dcat), grads)
+    torch.cuda.synchronize()
+    assert rel(nc(cat)[:, prev:, 0], y.detach()) < 1e-4
+    assert rel(nc(dra)[:, :, 0], ra.grad) < 1e-4 and rel(nc(dre)[:, :, 0], re.grad) < 1e-4
+    for k in sd:
+        assert rel(grads[k].double().reshape(sd[k].shape), sd[k].grad) < 1e-4, k
+
+
+def test_training_step_matches_autograd_oracle_and_adam():
+    from hupr_b200.models import HuPRNet
+    from hupr_b200.training import TrainStep
+    from oracle import model as om
+    from tests.test_model_gpu import make_cfg
+    seed, batch = 1, 1
+    sd = om.make_state_dict(seed)
+    hori, vert = om.make_vrdae(batch, seed)
+    joints = torch.randint(0, 256, (batch, 14, 2), generator=torch.Generator().manual_seed(3))
+    ref_loss, ref_loss2, ref_grads = om.training_gradients(sd, hori, vert, joints.numpy())
+
+    net = HuPRNet(make_cfg())
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    step = TrainStep(net)
+    loss, loss2 = step.forward_backward(hori.cuda(), vert.cuda(), joints)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) and abs(float(loss2) - ref_loss2) < 1e-4 * abs(ref_loss2)
+    errs = []
+    for name, q in net.named_parameters():
+        ref, got = ref_grads[name].double(), q.grad.cpu().double()
+        l2 = float((got - ref).norm() / ref.norm())
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()))
+        errs.append((l2, cos, name))
+    errs.sort(reverse=True)
+    print("largest relative-L2 gradient differences:", [(round(e, 5), n) for e, _, n in errs[:6]])
+    assert len(errs) == len(ref_grads) == 165
+    scalars = ("main.1.weight", "relu.weight")          # 1-element PReLU slopes: sums with heavy cancellation, compared in absolute terms
+    for l2, cos, name in errs:
+        if name.startswith("radarDecoder.decoderLayer") and name.endswith(scalars):
+            got, ref = float(dict(net.named_parameters())[name].grad), float(ref_grads[name])
+            assert abs(got - ref) < 5e-5 + 2e-2 * abs(ref), (name, got, ref)
+        else:
+            assert l2 < 0.06 and cos > 0.998, (name, l2, cos)           # a handful of mask flips at most (see module docstring)
+    med = sorted(e for e, _, _ in errs)[len(errs) // 2]
+    assert med < 5e-3, med
+    tail = [e for e, _, n in errs if "gcn" in n or "decoderLayer1.2" in n]       # downstream of every kink: hi/lo precision
+    assert max(tail) < 2e-4, tail
+    # BatchNorm running statistics were updated
+    rm = dict(net.named_buffers())["RAradarEncoder.layer1.1.main.1.running_mean"]
+    assert float((rm.cpu() - sd["RAradarEncoder.layer1.1.main.1.running_mean"]).abs().max()) > 0
+
+    # Adam (coupled L2) against torch.optim.Adam fed with the SAME gradients
+    names = [n for n, _ in net.named_parameters()]
+    params = {k: sd[k].clone().requires_grad_() for k in names}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    for k, p in params.items():
+        p.grad = dict(net.named_parameters())[k].grad.detach().cpu().clone()
+    opt.step()
+    step.optimizer_step()
+    torch.cuda.synchronize()
+    for name, q in net.named_parameters():
+        assert float((q.detach().cpu() - params[name].detach()).abs().max()) < 1e-6, name
+    # the next forward uses the updated weights (packs are rebuilt)
+    loss_b, _ = step.forward_backward(hori.cuda(), vert.cuda(), joints)
+    assert float(loss_b) < float(loss)
