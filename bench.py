@@ -13,6 +13,7 @@ Workloads:
               window/standardise -> MSCSA-PRGCN forward (batch 32) -> argmax keypoints [32,14,2]
   forward-b1  configs[1]: forward-only inference, batch 1 (CUDA-graph replay latency)
   cascade     configs[4]: FFT-cascade throughput on 2048 frame-sensors per step
+  train       configs[3] (per-GPU shard): training step, batch --batch per GPU, one NCCL gradient all-reduce when N > 1
 A "step" is one pass of the workload over one batch of synthetic input resident in HBM.  Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -38,6 +39,8 @@ WORKLOADS = {
            "FFT cascade -> window/standardise -> MSCSA-PRGCN forward -> argmax keypoints [32,14,2]",
     "forward-b1": "MSCSA-PRGCN forward-only inference, batch 1 (BASELINE.json configs[1]), mscsa_prgcn.yaml, CUDA-graph replay",
     "cascade": "fft-cascade sweep (BASELINE.json configs[4]): int16 DCA1000 words -> complex64 [16,64,64,8] cubes",
+    "train": "MSCSA-PRGCN training step (BASELINE.json configs[3] per-GPU shard): train-mode forward + backward + gradient all-reduce + Adam, "
+             "fp32-equivalent hi/lo bf16 tensor-core arithmetic, synthetic VRDAE inputs and joints",
 }
 MODEL_FWD_FLOPS = 137.09e9      # per sample, SURVEY.md §8 d (2 x MACs of the reference forward)
 
@@ -179,6 +182,19 @@ def cpu_baseline_for(workload, cores):
         r = cpu_cascade_sample(n_fs, cores)
         return r["fs_per_s"] / 2.0, ("%d frame-sensors, oracle.cascade.generate_heatmap_looped (numpy port, reference call pattern), "
                                      "%d-process pool, %.1f s wall, %.2f s per call" % (n_fs, cores, r["wall_s"], r["per_call_s"]))
+    if workload == "train":
+        import numpy as np
+        import torch
+        from oracle import model as om
+        torch.set_num_threads(cores)
+        sd = om.make_state_dict(0)
+        hori, vert = om.make_vrdae(2, 0)
+        joints = np.random.default_rng(0).integers(0, 256, (2, 14, 2))
+        t0 = time.perf_counter()
+        om.training_gradients(sd, hori, vert, joints)
+        dt = time.perf_counter() - t0
+        return 2.0 / dt, ("forward + backward of the torch-CPU fp32 oracle (autograd), batch 2, %d threads: %.2f s (optimizer step not "
+                          "included)" % (cores, dt))
     r = cpu_e2e_sample(cores)
     if workload == "forward-b1":
         return 1.0 / r["stage_s"]["forward"], "HuPRNet forward B=1, oracle.model (torch-CPU fp32 restatement), %d threads" % cores
@@ -229,11 +245,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="e2e", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=32, help="e2e: poses (windows) per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="e2e: poses (windows) per GPU per step (default 32); train: samples per GPU (default 8)")
     ap.add_argument("--frames-per-step", type=int, default=1024, help="cascade: radar frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-bf16", action="store_true", help="one bf16 product per k-step instead of the fp32-equivalent 3-product split")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 8 if args.workload == "train" else 32
     args.steps_ref = max(1, min(args.steps, 2))
     args.warmup_ref = 0
 
@@ -288,6 +306,38 @@ def main():
         e2e_units, h2d, d2h = n_e2e, 2 * n_e2e * FS_IN_BYTES, 2 * n_e2e * FS_OUT_BYTES
         l2_note = "inputs+outputs (%.1f GB) exceed the 126 MB L2" % (n_fs * (FS_IN_BYTES + FS_OUT_BYTES) / 1e9)
         dtype = "f32"
+    elif args.workload == "train":
+        from hupr_b200.training import TrainStep
+        torch.manual_seed(0)
+        model = HuPRNet(make_cfg()).to(dev).train()
+        trainer = TrainStep(model)
+        units = args.batch
+        hori = torch.randn((units, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
+        vert = torch.randn((units, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
+        joints = torch.randint(0, 256, (units, 14, 2), generator=gen, device=dev)
+        h_h, h_v = hori.cpu().pin_memory(), vert.cpu().pin_memory()
+        h_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+
+        def step():
+            trainer.forward_backward(hori, vert, joints)
+            trainer.all_reduce_gradients()
+            trainer.optimizer_step()
+
+        def e2e_step():
+            hori.copy_(h_h, non_blocking=True)
+            vert.copy_(h_v, non_blocking=True)
+            l, l2 = trainer.forward_backward(hori, vert, joints)
+            trainer.all_reduce_gradients()
+            trainer.optimizer_step()
+            h_loss[0:1].copy_(l.reshape(1), non_blocking=True)
+            h_loss[1:2].copy_(l2.reshape(1), non_blocking=True)
+        before = ops.launch_count()
+        step()
+        launches_per_step = ops.launch_count() - before
+        e2e_units, h2d, d2h = units, 2 * h_h.numel() * 4, 8
+        profile_step = lambda: trainer.forward_backward(hori, vert, joints)
+        l2_note = "per-step working set (saved activations + gradients, tens of GB at batch 8) exceeds the 126 MB L2"
+        dtype = "bf16 tensor-core products, fp32 accumulate (3-product hi/lo split: fp32-equivalent), fp32 master weights / Adam"
     else:
         torch.manual_seed(0)
         model = HuPRNet(make_cfg(), split=not args.single_bf16).to(dev).eval()      # random-init weights of the reference architecture
@@ -417,7 +467,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic (seeded random int16 ADC words; random-init weights of the reference architecture)",
             "config": {"workload": WORKLOADS[args.workload], "units_per_gpu_per_step": units, "l2": l2_note,
-                       "parallelism": "frames sharded across ranks, no collective"},
+                       "parallelism": ("data parallel: samples sharded across ranks, one NCCL sum all-reduce over the flat fp32 gradient buffer per step"
+                                       if args.workload == "train" else "frames sharded across ranks, no collective")},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "units_per_gpu_per_step": e2e_units},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

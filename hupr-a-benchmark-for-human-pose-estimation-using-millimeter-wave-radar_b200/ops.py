@@ -316,22 +316,22 @@ def to_kmajor(x, ch_off, c, geom, out, shift=0):
     return out
 
 
-def conv_wgrad(xts, cin, dyt, rows, geom, kernel, out):
+def conv_wgrad(xt, cin, dyt, rows, geom, kernel, out):
     """Weight gradient of a stride-1 convolution from position-major operands (hupr_conv_gemm with k_split / w_k_off).
 
-    xts : list of kernel[2] SplitTensors [cin, ppad]: input activations, copy kw pre-shifted by kw - pw (to_kmajor(shift=...))
+    xt  : SplitTensor [kernel[2] * cin, ppad]: input activations, row block kw pre-shifted by kw - pw (to_kmajor(shift=...)); the
+          kw taps are one GEMM (N = kernel[2] * cin), so the output-gradient operand is read once per (kd, kh) instead of once per tap
     dyt : SplitTensor [rows, ppad]: output gradients in the same index space, rows = cout rounded up to a multiple of 128 (zero rows)
-    out : float32 [taps, rows, cin], zero-filled by the caller; tap order (kd, kh, kw) row-major like torch's weight layout."""
+    out : float32 [kernel[0] * kernel[1], rows, kernel[2] * cin], zero-filled by the caller."""
     ppad = geom.ppad
+    n = kernel[2] * cin
     a = SplitTensor(dyt.hi.view(1, 1, 1, rows, ppad), None if dyt.lo is None else dyt.lo.view(1, 1, 1, rows, ppad))
-    tiles = max(1, rows // 128) * max(1, cin // (128 if cin % 128 == 0 else 64))
+    w = SplitTensor(xt.hi.view(1, n, ppad), None if xt.lo is None else xt.lo.view(1, n, ppad))
+    tiles = max(1, rows // 128) * max(1, n // (128 if n % 128 == 0 else 64))
     k_split = max(1, min(ppad // 64, (296 + tiles - 1) // tiles))
-    tap = 0
+    g = 0
     for kd in range(kernel[0]):
         for kh in range(kernel[1]):
-            for kw in range(kernel[2]):
-                xt = xts[kw]
-                w = SplitTensor(xt.hi.view(1, cin, ppad), None if xt.lo is None else xt.lo.view(1, cin, ppad))
-                conv_gemm(a, ppad, w, cin, out_f32=out[tap].view(1, 1, 1, rows, cin), k_split=k_split, w_k_off=geom.tap_offset(kd, kh))
-                tap += 1
+            conv_gemm(a, ppad, w, n, out_f32=out[g].view(1, 1, 1, rows, n), k_split=k_split, w_k_off=geom.tap_offset(kd, kh))
+            g += 1
     return out

@@ -74,16 +74,17 @@ class ConvOp(object):
         geom = ops.KMajorGeometry(n, d, h, w, self.pad)
         cin_rows = self.cin_pad
         c_in = min(self.cin_pad, x.hi.shape[-1] - x_off)
-        xts = []
-        for kw in range(self.kernel[2]):
-            xt = _S((cin_rows, geom.ppad), dev, zero=True)
-            ops.to_kmajor(x, x_off, c_in, geom, xt, shift=kw - self.pad[2])
-            xts.append(xt)
+        kw_n = self.kernel[2]
+        xt = _S((kw_n * cin_rows, geom.ppad), dev, zero=True)
+        for kw in range(kw_n):
+            blk = SplitTensor(xt.hi[kw * cin_rows:(kw + 1) * cin_rows], xt.lo[kw * cin_rows:(kw + 1) * cin_rows])
+            ops.to_kmajor(x, x_off, c_in, geom, blk, shift=kw - self.pad[2])
         rows = -(-self.cout // 128) * 128
         dyt = _S((rows, geom.ppad), dev, zero=True)
         ops.to_kmajor(dy, dy_off, self.cout, geom, dyt)
-        acc = torch.zeros((self.taps, rows, cin_rows), dtype=torch.float32, device=dev)
-        ops.conv_wgrad(xts, cin_rows, dyt, rows, geom, self.kernel, acc)
+        acc = torch.zeros((self.kernel[0] * self.kernel[1], rows, kw_n * cin_rows), dtype=torch.float32, device=dev)
+        ops.conv_wgrad(xt, cin_rows, dyt, rows, geom, self.kernel, acc)
+        acc = acc.view(self.kernel[0] * self.kernel[1], rows, kw_n, cin_rows).permute(0, 2, 1, 3).reshape(self.taps, rows, cin_rows)
         o = 0
         for name, c, cp in zip(self.names, self.couts, self.cout_pads):
             g = acc[:, o:o + c, :self.cin].permute(1, 2, 0).reshape((c, self.cin) + self.kernel)

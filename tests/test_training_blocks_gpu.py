@@ -98,17 +98,16 @@ def test_conv_wgrad_from_position_major_operands_matches_autograd(shape):
     DY = SplitTensor.from_float(dy.float().permute(0, 2, 3, 4, 1).contiguous())
     geom = ops.KMajorGeometry(n, d, h, w, pad)
     rows = -(-cout // 128) * 128
-    xts = []
+    xt = SplitTensor.empty((kernel[2] * cin, geom.ppad), "cuda", zero=True)
     for kw in range(kernel[2]):
-        xt = SplitTensor.empty((cin, geom.ppad), "cuda", zero=True)
-        ops.to_kmajor(X, 0, cin, geom, xt, shift=kw - pad[2])
-        xts.append(xt)
+        ops.to_kmajor(X, 0, cin, geom, SplitTensor(xt.hi[kw * cin:(kw + 1) * cin], xt.lo[kw * cin:(kw + 1) * cin]), shift=kw - pad[2])
     dyt = SplitTensor.empty((rows, geom.ppad), "cuda", zero=True)
     ops.to_kmajor(DY, 0, cout, geom, dyt)
     taps = kernel[0] * kernel[1] * kernel[2]
-    out = torch.zeros(taps, rows, cin, device="cuda")
-    ops.conv_wgrad(xts, cin, dyt, rows, geom, kernel, out)
+    out = torch.zeros(kernel[0] * kernel[1], rows, kernel[2] * cin, device="cuda")
+    ops.conv_wgrad(xt, cin, dyt, rows, geom, kernel, out)
     torch.cuda.synchronize()
+    out = out.view(kernel[0] * kernel[1], rows, kernel[2], cin).permute(0, 2, 1, 3).reshape(taps, rows, cin)
     got = out[:, :cout].permute(1, 2, 0).reshape(cout, cin, *kernel).double()
     assert float((got - wt.grad).abs().max() / wt.grad.abs().max()) < 3e-5
 
