@@ -88,7 +88,7 @@ SIGNATURES = {
     "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
     "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                      ctypes.c_float, _I, _P]),
+                                      ctypes.c_float, _I, _P, _P]),
     "hupr_heatmap_loss_fwd": (ctypes.c_int, [_P, _P, _P, _I, _P, ctypes.c_size_t, _P, _P, _P, _P]),
 }
 

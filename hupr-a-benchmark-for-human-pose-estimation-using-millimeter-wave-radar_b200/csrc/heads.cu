@@ -368,7 +368,13 @@ loss_bwd_kernel(const float* __restrict__ heatmap, const float* __restrict__ gcn
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-            float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float weight_decay) {
+            float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float weight_decay, float lr,
+            const int* __restrict__ step_dev) {
+    if (step_dev) {      // step count lives on the device (CUDA-graph replays): derive the bias corrections here
+        const double t = (double)__ldg(step_dev);
+        step_size = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const float pi = p[i];
         const float gi = fmaf(weight_decay, pi, g[i]);            // coupled L2: grad += wd * param
@@ -397,8 +403,9 @@ extern "C" int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heat
 }
 
 extern "C" int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int step, void* stream) {
-    if (n < 0 || step < 1) return HUPR_ERR_BAD_ARG;
+                              float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream) {
+    if (n < 0 || (step < 1 && !step_dev)) return HUPR_ERR_BAD_ARG;
+    if (step < 1) step = 1;
     if (n == 0) return HUPR_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq) return HUPR_ERR_BAD_ARG;
     int rc = heads_check_sm100();
@@ -407,7 +414,7 @@ extern "C" int hupr_adam_step(float* params, const float* grads, float* exp_avg,
     long long blocks = (n + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)((double)lr / bc1),
-                                                                    (float)sqrt(bc2), beta1, beta2, eps, weight_decay);
+                                                                    (float)sqrt(bc2), beta1, beta2, eps, weight_decay, lr, step_dev);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

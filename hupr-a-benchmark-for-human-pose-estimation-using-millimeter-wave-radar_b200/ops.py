@@ -278,14 +278,15 @@ def heatmap_loss_bwd(heatmap, gcn_heatmap, joints, d_heat_logits, d_gcn_pre):
     return d_heat_logits, d_gcn_pre
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
-    """One Adam step with coupled L2 on flat float32 CUDA buffers (hupr_adam_step); defaults = reference tools/base.py:47."""
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, step_dev=None):
+    """One Adam step with coupled L2 on flat float32 CUDA buffers (hupr_adam_step); defaults = reference tools/base.py:47.
+    ``step_dev``: optional int32 device scalar holding the 1-based step count (used instead of ``step``; CUDA-graph friendly)."""
     n = params.numel()
     if not (grads.numel() == exp_avg.numel() == exp_avg_sq.numel() == n):
         raise ValueError("adam_step: buffer sizes differ")
     with torch.cuda.device(params.device):
         _call("hupr_adam_step", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), n, lr, betas[0], betas[1], eps, weight_decay, step,
-              _C.stream_ptr())
+              _p(step_dev), _C.stream_ptr())
     return params
 
 

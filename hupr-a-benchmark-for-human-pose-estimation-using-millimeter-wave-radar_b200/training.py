@@ -393,6 +393,7 @@ class TrainStep(object):
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.adj = torch.tensor(ADJACENCY, dtype=torch.float32, device=dev)
         self.adj_t = self.adj.t().contiguous()
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._dirty = True
 
     # ---------------------------------------------------------------------------------------------------------------- packing
@@ -528,10 +529,38 @@ class TrainStep(object):
     def optimizer_step(self):
         self.step_count += 1
         h = self.hyper
+        self.step_dev.add_(1)          # device-side step counter: the bias corrections stay right under CUDA-graph replay
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, lr=h["lr"], betas=h["betas"], eps=h["eps"],
-                      weight_decay=h["weight_decay"])
+                      weight_decay=h["weight_decay"], step_dev=self.step_dev)
         self._dirty = True
         self.model.invalidate()
+
+    def capture(self, hori, vert, joints, with_optimizer=True):
+        """Capture forward_backward (+ the Adam launch) into one CUDA graph over the caller's STATIC input tensors; returns a
+        ``replay()`` callable whose result is the device tensor pair (loss, loss2).  The step launches ~1 150 kernels, so at small
+        batches the Python/ctypes launch path is the bottleneck; the graph removes it.  (With several ranks capture only
+        ``with_optimizer=False`` and run all_reduce_gradients() + optimizer_step() eagerly after each replay.)"""
+        joints = joints.to(device=hori.device, dtype=torch.int64).contiguous()
+        for _ in range(2):                       # warm-up: lazy function attributes, allocator high-water mark
+            self.forward_backward(hori, vert, joints)
+            if with_optimizer:
+                self.optimizer_step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward_backward(hori, vert, joints)
+            if with_optimizer:
+                self.optimizer_step()
+        self._graph = graph
+        if with_optimizer:
+            self.step_count -= 1                 # the captured optimizer_step() call was recorded, not executed
+
+        def replay():
+            if with_optimizer:
+                self.step_count += 1             # the device-side counter (step_dev) is advanced by the captured graph itself
+            graph.replay()
+            return out
+        return replay
 
     def all_reduce_gradients(self):
         """Data-parallel training (SURVEY.md §8 e): ONE sum all-reduce over the flat gradient buffer, then divide by the world size."""

@@ -253,7 +253,9 @@ int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, 
 int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
                           float* d_heat_logits, float* d_gcn_pre, void* stream);
 int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, void* stream);
+                   float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream);
+/* step_dev: optional DEVICE int holding the step count; when given it replaces `step`, so a CUDA-graph replay of the launch keeps
+ * the bias corrections advancing. */
 
 #ifdef __cplusplus
 }

@@ -207,3 +207,46 @@ def test_training_step_matches_autograd_oracle_and_adam():
     # the next forward uses the updated weights (packs are rebuilt)
     loss_b, _ = step.forward_backward(hori.cuda(), vert.cuda(), joints)
     assert float(loss_b) < float(loss)
+
+
+def test_graph_replayed_training_equals_eager_training():
+    """TrainStep.capture(): three CUDA-graph replays (forward + backward + Adam with the device-side step counter) leave the same
+    parameters as three eager steps on the same batch."""
+    from hupr_b200.models import HuPRNet
+    from hupr_b200.training import TrainStep
+    from oracle import model as om
+    from tests.test_model_gpu import make_cfg
+    sd = om.make_state_dict(4)
+    hori, vert = (t.cuda() for t in om.make_vrdae(1, 4))
+    joints = torch.randint(0, 256, (1, 14, 2), generator=torch.Generator().manual_seed(5)).cuda()
+    results = []
+    for mode in ("eager", "graph"):
+        net = HuPRNet(make_cfg())
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        step = TrainStep(net)
+        losses = []
+        if mode == "eager":
+            for _ in range(5):
+                loss, _ = step.forward_backward(hori, vert, joints)
+                step.optimizer_step()
+                losses.append(float(loss))
+        else:
+            replay = step.capture(hori, vert, joints)          # two warm-up steps happen inside capture()
+            for _ in range(3):
+                loss, _ = replay()
+                losses.append(float(loss))
+            losses = [None, None] + losses
+        torch.cuda.synchronize()
+        results.append((losses, {k: v.detach().clone() for k, v in net.named_parameters()}, step.step_count))
+    (l_e, p_e, n_e), (l_g, p_g, n_g) = results
+    assert n_e == n_g == 5
+    assert l_e[4] < l_e[0]                                    # the loss goes down on a repeated batch
+    for a, b in zip(l_e[2:], l_g[2:]):
+        assert abs(a - b) < 1e-3 * abs(a)
+    # Early Adam steps move every weight by ~lr * sign(g): an element whose gradient is at round-off level (atomics order, mask flips)
+    # may step the other way in the two runs, so single elements differ by up to 2 * lr per step while the bulk agrees tightly.
+    for k in p_e:
+        diff = (p_e[k] - p_g[k]).abs()
+        assert float(diff.max()) < 5 * 2e-4 + 1e-5, k
+        assert float(diff.mean()) < 2e-5, (k, float(diff.mean()))
