@@ -102,6 +102,30 @@ class RadarPoseStream(object):
             self._step_eager()
         return self.keypoints
 
+    # ---- pipelined ingest: the H2D copy of the NEXT frames runs on a copy stream while the current step computes ----------------
+    def prefetch(self, adc_hori, adc_vert):
+        """Start the asynchronous upload of the next step's DCA1000 words (pinned host tensors) into a staging buffer."""
+        if not hasattr(self, "_staging"):
+            self._staging = torch.empty_like(self.adc)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._uploaded = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(self.device))
+        n = self.n_frames
+        self._copy_stream.wait_event(self._consumed)            # the previous staging contents have been moved into self.adc
+        with torch.cuda.stream(self._copy_stream):
+            self._staging[:n].copy_(adc_hori.view(n, FRAME_WORDS), non_blocking=True)
+            self._staging[n:].copy_(adc_vert.view(n, FRAME_WORDS), non_blocking=True)
+            self._uploaded.record(self._copy_stream)
+
+    def step_prefetched(self):
+        """Run one step on the frames uploaded by the last ``prefetch`` call; returns the device keypoints ``[n_windows, 14, 2]``."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._uploaded)
+        self.adc.copy_(self._staging, non_blocking=True)         # device-to-device, ~20 us
+        self._consumed.record(main)
+        return self.step()
+
     def __call__(self, adc_hori, adc_vert):
         """adc_hori / adc_vert: int16 ``[n_frames, FRAME_WORDS]`` (host pinned or device) -> keypoints ``[n_windows, 14, 2]`` (device)."""
         n = self.n_frames

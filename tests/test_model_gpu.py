@@ -265,3 +265,32 @@ def test_loss_computer_mirror_matches_reference_golden(golden_dir):
     assert pred2d.dtype == np.float32 and np.array_equal(pred2d, g["pred2d"]) and np.array_equal(gt2d, g["gt2d"])
     preds, maxvals = get_max_preds(gcn.view(b, 14, 64, 64))
     assert np.array_equal(preds, g["pred2d"]) and maxvals.shape == (b, 14, 1)
+
+
+def test_c_abi_edge_cases_zero_sizes_alignment_and_bad_shapes():
+    """Empty inputs are no-ops, misaligned pointers and unsupported shapes are rejected with the documented codes (no launch)."""
+    import ctypes
+    from hupr_b200 import _C, ops
+    from hupr_b200.ops import SplitTensor
+    lib = _C.lib()
+    s = _C.stream_ptr()
+    buf = torch.zeros(1 << 16, dtype=torch.float32, device="cuda")
+    p = buf.data_ptr()
+    assert lib.hupr_fft_cascade_i16(p, p, 0, s) == 0
+    assert lib.hupr_window_normalize(p, p, 0, p, s) == 0 and lib.hupr_mnet_fwd(p, p, p, p, p, 0, s) == 0
+    assert lib.hupr_softmax_rows(p, p, p, 0, 256, s) == 0 and lib.hupr_keypoints_argmax(p, 0, p, None, s) == 0
+    assert lib.hupr_prgcn_workspace_bytes(0) == 0 and lib.hupr_frame_features_workspace_bytes(3) == 3 * 256 * 4
+    assert lib.hupr_fft_cascade_i16(p + 2, p, 1, s) == -2                                   # HUPR_ERR_ALIGNMENT
+    assert lib.hupr_softmax_rows(p, p, p, 4, 4100, s) == -1 and lib.hupr_softmax_rows(p, p, p, 4, 6, s) == -1      # cols > 4096 / not % 4
+    assert lib.hupr_heatmap_loss_fwd(p, p, p, 2, p, 8, p, None, None, s) == -5             # HUPR_ERR_WORKSPACE
+    assert lib.hupr_adam_step(p, p, p, p, 16, 1e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None, s) == -1      # step < 1 without a device counter
+    d = _C.AttnDesc()
+    x = SplitTensor.empty((1, 1, 1, 128, 96), "cuda", zero=True)
+    d.q_hi = d.k_hi = d.vt_hi = d.o_hi = x.hi.data_ptr()
+    d.q_lo = d.k_lo = d.vt_lo = d.o_lo = x.lo.data_ptr()
+    d.q_ld = d.k_ld = d.o_ld = 96
+    d.batch, d.s, d.c = 1, 128, 96
+    assert lib.hupr_attention_fwd(ctypes.byref(d), s) == -1                                 # head dim 96 is not supported
+    with pytest.raises(RuntimeError, match="bad argument"):
+        ops.resample_linear(x, 96, SplitTensor.empty((1, 1, 1, 64, 100), "cuda"))          # ld not a multiple of 8
+    torch.cuda.synchronize()

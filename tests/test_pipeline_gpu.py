@@ -71,3 +71,20 @@ def test_frame_features_equal_window_path_per_frame():
     ops.frame_features(cubes, stats, 1, 2, w.contiguous(), b, got)
     torch.cuda.synchronize()
     assert float((got.float() - ref.float()[1:]).abs().max()) < 2e-5
+
+
+def test_prefetched_ingest_equals_direct_call():
+    s, _, hori, vert = build(2, per_frame=True, use_graph=True)
+    direct = s(hori.pin_memory(), vert.pin_memory()).clone()
+    torch.cuda.synchronize()
+    s.adc.zero_()
+    hp, vp = hori.pin_memory(), vert.pin_memory()
+    s.prefetch(hp, vp)
+    first = s.step_prefetched().clone()
+    s.prefetch(vp, hp)                      # swapped sensors: a different result must come out of the second step
+    second = s.step_prefetched().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(first, direct)
+    swapped = s(vert.pin_memory(), hori.pin_memory()).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(second, swapped)
