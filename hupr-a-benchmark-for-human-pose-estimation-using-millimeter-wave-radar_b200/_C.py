@@ -86,6 +86,8 @@ SIGNATURES = {
     "hupr_gcn_nodes_bwd": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "hupr_mnet_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
+    "hupr_to_kmajor_multi": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong,
+                                            ctypes.c_longlong, _P]),
     "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, _I, _P, _P]),

@@ -345,6 +345,12 @@ static int check_sm100() {
     return cached;
 }
 
+int fast_transpose_dense(const void* in_hi, const void* in_lo, int n, int s, int c, int in_ld, int in_ch_off, void* out_hi, void* out_lo,
+                         cudaStream_t stream);
+int fast_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c, void* dst_hi, void* dst_lo,
+                   int dp, int hp, int wp, int pd, int ph, int pw, int shift0, int n_copies, long long copy_stride, long long ppad,
+                   cudaStream_t stream);
+
 static inline int launch_status(int n = 1) {
     note_launches(n);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
@@ -452,6 +458,9 @@ extern "C" int hupr_transpose_split(const void* in_hi, const void* in_lo, int n,
     if (n > 65535 || c / 32 > 65535) return HUPR_ERR_BAD_ARG;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
+    if (s % 64 == 0 && c % 64 == 0 && in_ld % 8 == 0 && in_ch_off % 8 == 0 &&
+        !(((uintptr_t)in_hi | (uintptr_t)in_lo) & 15) && !(((uintptr_t)out_hi | (uintptr_t)out_lo) & 3))
+        return fast_transpose_dense(in_hi, in_lo, n, s, c, in_ld, in_ch_off, out_hi, out_lo, (cudaStream_t)stream);      // transpose.cu
     const dim3 grid(s / 32, c / 32, n), block(32, 8);
     transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_hi, (uint16_t*)out_hi, s, c, in_ld, in_ch_off);
     if (in_lo) transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
@@ -507,6 +516,10 @@ extern "C" int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int
     if (ppad < (long long)n * dp * hp * wp || positions / 32 > 2147483647LL || c / 32 > 65535) return HUPR_ERR_BAD_ARG;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
+    if (positions % 64 == 0 && c % 64 == 0 && w % 2 == 0 && ld % 8 == 0 && ch_off % 8 == 0 && ppad % 2 == 0 &&
+        !(((uintptr_t)src_hi | (uintptr_t)src_lo) & 15) && !(((uintptr_t)dst_hi | (uintptr_t)dst_lo) & 3))
+        return fast_to_kmajor(src_hi, src_lo, n, d, h, w, ld, ch_off, c, dst_hi, dst_lo, dp, hp, wp, pd, ph, pw, shift, 1, 0, ppad,
+                              (cudaStream_t)stream);                                                                     // transpose.cu
     KMajorParams p;
     p.n = n; p.d = d; p.h = h; p.w = w; p.ld = ld; p.ch_off = ch_off;
     p.dp = dp; p.hp = hp; p.wp = wp; p.pd = pd; p.ph = ph; p.pw = pw; p.shift = shift; p.ppad = ppad;

@@ -317,6 +317,16 @@ def to_kmajor(x, ch_off, c, geom, out, shift=0):
     return out
 
 
+def to_kmajor_multi(x, ch_off, c, geom, out, first_shift, n_copies, rows_per_copy):
+    """One read of x, ``n_copies`` position-major copies: copy k goes to rows [k*rows_per_copy, +c) of ``out`` shifted by
+    first_shift + k (hupr_to_kmajor_multi).  Needs c % 64 == 0 and an even W; callers fall back to to_kmajor otherwise."""
+    n, d, h, w, ld = x.hi.shape
+    with torch.cuda.device(x.hi.device):
+        _call("hupr_to_kmajor_multi", _p(x.hi), _p(x.lo), n, d, h, w, ld, ch_off, c, _p(out.hi), _p(out.lo),
+              geom.dp, geom.hp, geom.wp, geom.pd, geom.ph, geom.pw, first_shift, n_copies, rows_per_copy, geom.ppad, _C.stream_ptr())
+    return out
+
+
 def conv_wgrad(xt, cin, dyt, rows, geom, kernel, out):
     """Weight gradient of a stride-1 convolution from position-major operands (hupr_conv_gemm with k_split / w_k_off).
 

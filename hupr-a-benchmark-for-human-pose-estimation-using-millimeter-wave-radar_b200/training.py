@@ -76,9 +76,12 @@ class ConvOp(object):
         c_in = min(self.cin_pad, x.hi.shape[-1] - x_off)
         kw_n = self.kernel[2]
         xt = _S((kw_n * cin_rows, geom.ppad), dev, zero=True)
-        for kw in range(kw_n):
-            blk = SplitTensor(xt.hi[kw * cin_rows:(kw + 1) * cin_rows], xt.lo[kw * cin_rows:(kw + 1) * cin_rows])
-            ops.to_kmajor(x, x_off, c_in, geom, blk, shift=kw - self.pad[2])
+        if c_in % 64 == 0:
+            ops.to_kmajor_multi(x, x_off, c_in, geom, xt, -self.pad[2], kw_n, cin_rows)          # all kw copies from one read
+        else:
+            for kw in range(kw_n):
+                blk = SplitTensor(xt.hi[kw * cin_rows:(kw + 1) * cin_rows], xt.lo[kw * cin_rows:(kw + 1) * cin_rows])
+                ops.to_kmajor(x, x_off, c_in, geom, blk, shift=kw - self.pad[2])
         rows = -(-self.cout // 128) * 128
         dyt = _S((rows, geom.ppad), dev, zero=True)
         ops.to_kmajor(dy, dy_off, self.cout, geom, dyt)

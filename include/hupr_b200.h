@@ -250,6 +250,11 @@ int hupr_mnet_bwd(const float* vrdae, const float* weight, const float* bias, co
  * (what autograd computes for the weights of nn.Conv3d / nn.Conv2d). */
 int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c,
                    void* dst_hi, void* dst_lo, int dp, int hp, int wp, int pd, int ph, int pw, int shift, long long ppad, void* stream);
+/* Same re-layout, n_copies copies from ONE read of src: copy k is written at rows [k*rows_per_copy, +c) of dst with shift
+ * first_shift + k (the kw = 0..2 operands of a 3-wide filter: first_shift = -pw, n_copies = 3).  Needs c % 64 == 0 and an even w. */
+int hupr_to_kmajor_multi(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c, void* dst_hi,
+                         void* dst_lo, int dp, int hp, int wp, int pd, int ph, int pw, int first_shift, int n_copies,
+                         long long rows_per_copy, long long ppad, void* stream);
 int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
                           float* d_heat_logits, float* d_gcn_pre, void* stream);
 int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
