@@ -443,8 +443,11 @@ def main():
     if args.workload == "cascade":
         launch_bytes = 2 * units * (FS_IN_BYTES + FS_OUT_BYTES)
         achieved = launch_bytes / (ms_per_step * 1e-3) / 1e9
+        # DRAM traffic per frame-sensor from the committed ncu --set full capture (profiles/r01_cascade_metrics.csv: 465.6 MB read +
+        # 2 423.5 MB written for a 592-frame-sensor launch = 4 880 262 B each, vs 4 980 736 B algorithmic), scaled to this launch
+        traffic = 2 * units * (465608960 + 2423526000) / 592.0
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                    "traffic": None, "kernel": "hupr::cascade_kernel", "peak_source": peaks["source"],
+                    "traffic": traffic, "kernel": "hupr::cascade_kernel", "peak_source": peaks["source"],
                     "algorithmic_bytes_per_launch": launch_bytes}
     else:
         profile_step()
