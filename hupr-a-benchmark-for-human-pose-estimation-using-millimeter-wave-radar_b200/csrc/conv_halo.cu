@@ -9,7 +9,9 @@
 //     accumulators are sub-views of it (start address + kh*bw rows — legal because bw*64 B is a multiple of the swizzle
 //     atom), i.e. 6 tile-taps per load instead of 1;
 //   * k-blocks are 32 channels (64-byte rows, SWIZZLE_64B) so that a stage (halo box + 3 weight tiles, hi and lo planes)
-//     stays under 96 KiB and two to three stages fit.
+//     stays under 96 KiB and two to three stages fit;
+//   * the kernel is persistent (one CTA per SM walks the tiles) with two accumulator sets in TMEM, so the epilogue of one tile
+//     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
 #include "tc.cuh"
 #include "conv_common.cuh"
@@ -28,6 +30,7 @@ struct HaloGeom {
     int stages;
     int tap_stride_bytes;          // bw * 64: one h-row of the halo
     int acc_stride_bytes;          // (bh / 2) * bw * 64: first row of accumulator 1
+    int m_tiles, n_tiles;          // 256-position tiles x BN-column tiles, walked persistently
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
@@ -45,36 +48,36 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p,
                  const HaloGeom g) {
+    // Persistent: CTA b walks tiles b, b + gridDim.x, ...; the TMA->MMA smem ring runs continuously across tiles and the two
+    // accumulator SETS in TMEM (2 x [2 x BN] columns) let the epilogue of tile i overlap the main loop of tile i + 1.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + 4;
-    uint64_t* accum_full = bars + 8;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* accum_full = bars + 8;     // [2]
+    uint64_t* accum_empty = bars + 10;   // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    int t = blockIdx.x;
-    const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int od = t % p.d_out;
-    const int n = t / p.d_out;
-    const int h0 = th * p.bh;
-    const int n0 = blockIdx.y * BN;
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
+    const int total_tiles = g.m_tiles * g.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&accum_full[s], 1);
+            mbar_init(&accum_empty[s], 128);
+        }
         fence_mbar_init();
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(4 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -82,26 +85,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
+    // tile -> (weight column tile, sample, depth slice, h block); tiles that run concurrently share the weight tile
+    auto decode = [&](int tile, int& n0, int& n, int& od, int& h0) {
+        n0 = (tile / g.m_tiles) * BN;
+        int t = tile % g.m_tiles;
+        h0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+        od = t % p.d_out;
+        n = t / p.d_out;
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (int gi = 0; gi < groups; ++gi) {
-                const int s = gi % g.stages;
-                const uint32_t ph = (uint32_t)(gi / g.stages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                const int cb = gi % p.cin_blocks;
-                const int tkw = (gi / p.cin_blocks) % p.kw, tkd = gi / (p.cin_blocks * p.kw);
-                uint8_t* st = smem + s * g.stage_bytes;
-                mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
-                const int ac = p.a_ch_off + cb * HK;
-                tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                uint8_t* sb = st + 2 * g.a_plane_bytes;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int n0, n, od, h0;
+                decode(tile, n0, n, od, h0);
+                for (int gi = 0; gi < groups; ++gi, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    const int cb = gi % p.cin_blocks;
+                    const int tkw = (gi / p.cin_blocks) % p.kw, tkd = gi / (p.cin_blocks * p.kw);
+                    uint8_t* st = smem + s * g.stage_bytes;
+                    mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
+                    const int ac = p.a_ch_off + cb * HK;
+                    tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                    tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                    uint8_t* sb = st + 2 * g.a_plane_bytes;
 #pragma unroll
-                for (int tkh = 0; tkh < 3; ++tkh) {
-                    const int tap = (tkd * 3 + tkh) * p.kw + tkw;
-                    tma_load_3d(sb + tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
-                    tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                    for (int tkh = 0; tkh < 3; ++tkh) {
+                        const int tap = (tkd * 3 + tkh) * p.kw + tkw;
+                        tma_load_3d(sb + tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
+                        tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                    }
                 }
             }
         }
@@ -109,58 +126,76 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int gi = 0; gi < groups; ++gi) {
-                const int s = gi % g.stages;
-                const uint32_t ph = (uint32_t)(gi / g.stages) & 1u;
-                mbar_wait(&full[s], ph);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const int as = lt & 1;
+                mbar_wait(&accum_empty[as], (uint32_t)(((lt >> 1) & 1) ^ 1));     // the epilogue drained this accumulator set
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * g.stage_bytes);
-                const uint32_t sb = st + 2 * g.a_plane_bytes;
+                const uint32_t tset = tmem_base + (uint32_t)(as * 2 * BN);
+                for (int gi = 0; gi < groups; ++gi, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * g.stage_bytes);
+                    const uint32_t sb = st + 2 * g.a_plane_bytes;
 #pragma unroll
-                for (int tkh = 0; tkh < 3; ++tkh) {
-                    const uint64_t db_hi = make_smem_desc_sw64(sb + tkh * g.b_tile_bytes);
-                    const uint64_t db_lo = make_smem_desc_sw64(sb + (3 + tkh) * g.b_tile_bytes);
+                    for (int tkh = 0; tkh < 3; ++tkh) {
+                        const uint64_t db_hi = make_smem_desc_sw64(sb + tkh * g.b_tile_bytes);
+                        const uint64_t db_lo = make_smem_desc_sw64(sb + (3 + tkh) * g.b_tile_bytes);
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
-                        const uint64_t da_hi = make_smem_desc_sw64(st + aoff);
-                        const uint64_t da_lo = make_smem_desc_sw64(st + g.a_plane_bytes + aoff);
-                        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+                        for (int a = 0; a < 2; ++a) {
+                            const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
+                            const uint64_t da_hi = make_smem_desc_sw64(st + aoff);
+                            const uint64_t da_lo = make_smem_desc_sw64(st + g.a_plane_bytes + aoff);
+                            const uint32_t tacc = tset + (uint32_t)(a * BN);
 #pragma unroll
-                        for (int k = 0; k < HK / 16; ++k) {
-                            const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
-                            umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, (gi | tkh | k) != 0);
-                            umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
-                            umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                            for (int k = 0; k < HK / 16; ++k) {
+                                const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
+                                umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, (gi | tkh | k) != 0);
+                                umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                                umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                            }
                         }
                     }
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);
+                tc_commit(&accum_full[as]);
             }
-            tc_commit(accum_full);
         }
     } else {
         // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31, accumulator 0 then 1 =================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            int n0, n, od, h0;
+            decode(tile, n0, n, od, h0);
+            const int as = lt & 1;
+            mbar_wait(&accum_full[as], (uint32_t)((lt >> 1) & 1));
+            tc_fence_after();
+            const uint32_t tset = tmem_base + (uint32_t)(as * 2 * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int a = 0; a < 2; ++a) {
-            const int ow = row % p.bw, oh = h0 + a * (p.bh / 2) + row / p.bw;
-            const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
+            for (int a = 0; a < 2; ++a) {
+                const int ow = row % p.bw, oh = h0 + a * (p.bh / 2) + row / p.bw;
+                const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), acc);
-                conv_epilogue32(p, acc, pos, n0 + c * 32);
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(tset + (uint32_t)(a * BN + c * 32), acc);
+                    if (a == 1 && c == BN / 32 - 1) {      // last TMEM read of this set: hand it back before the stores
+                        tc_fence_before();
+                        mbar_arrive(&accum_empty[as]);
+                    }
+                    conv_epilogue32(p, acc, pos, n0 + c * 32);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
     }
 }
 
@@ -202,8 +237,17 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     }
     const int smem = g.stages * g.stage_bytes + 1024 + 256;
     if (smem > smem_max) return HUPR_ERR_BAD_ARG;
-    dim3 grid(m_tiles, p.cout / BN, 1);
-    conv_halo_kernel<BN><<<grid, kHaloThreads, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p, g);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HUPR_ERR_CUDA;
+    }
+    HaloGeom gg = g;
+    gg.m_tiles = m_tiles;
+    gg.n_tiles = p.cout / BN;
+    const int total = gg.m_tiles * gg.n_tiles;
+    dim3 grid(total < num_sms ? total : num_sms, 1, 1);
+    conv_halo_kernel<BN><<<grid, kHaloThreads, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p, gg);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
