@@ -26,6 +26,7 @@ struct ConvParams {
     int o_f32_ld;
     int w_k_off;                   // added to the B operand's contracted-axis coordinate (shifted correlation; out of range = zero fill)
     int kb_per_split, k_split, atomic;
+    int m_tiles, n_tiles;          // 128-position tiles x BN-column tiles (x k_split slices), walked persistently
 };
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos`.

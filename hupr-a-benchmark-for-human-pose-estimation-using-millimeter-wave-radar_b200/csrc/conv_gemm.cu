@@ -41,36 +41,32 @@ template <int BN, int NPROD>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p) {
+    // Persistent: CTA b walks work items b, b + gridDim.x, ... (item = (split-K slice, column tile, 128-position tile)); the smem ring
+    // runs continuously across items and two TMEM accumulators let the epilogue of one item overlap the main loop of the next.
     using Cfg = ConvCfg<BN, NPROD>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::kStages;
-    uint64_t* accum_full = bars + 2 * Cfg::kStages;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+    uint64_t* accum_full = bars + 2 * Cfg::kStages;          // [2]
+    uint64_t* accum_empty = bars + 2 * Cfg::kStages + 2;     // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int od = t % p.d_out;
-    const int n = t / p.d_out;
-    const int w0 = tw * p.bw, h0 = th * p.bh;
-    const int n0 = blockIdx.y * BN;
     const int total_kb = p.kd * p.kh * p.kw * p.cin_blocks;
-    const int kb_begin = blockIdx.z * p.kb_per_split;                      // split-K: this CTA contracts k-blocks [kb_begin, kb_end)
-    const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+    const int total_items = p.m_tiles * p.n_tiles * p.k_split;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&accum_full[s], 1);
+            mbar_init(&accum_empty[s], 128);
+        }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -81,8 +77,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             prefetch_tmap(&tmB_lo);
         }
     }
-    if (warp == 1) {   // TMEM allocation (whole warp), BN fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(BN));
+    if (warp == 1) {   // TMEM allocation (whole warp): two accumulators of BN fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -90,25 +86,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
+    // item -> (k slice, column tile, sample, depth slice, h block, w block); consecutive items share the weight tile
+    auto decode = [&](int item, int& kb_begin, int& kb_end, int& n0, int& n, int& od, int& h0, int& w0) {
+        int t = item % p.m_tiles;
+        int r = item / p.m_tiles;
+        n0 = (r % p.n_tiles) * BN;
+        const int z = r / p.n_tiles;
+        kb_begin = z * p.kb_per_split;
+        kb_end = min(total_kb, kb_begin + p.kb_per_split);
+        w0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
+        h0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
+        od = t % p.d_out;
+        n = t / p.d_out;
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                const int it = kb - kb_begin;
-                const int s = it % Cfg::kStages;
-                const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-                const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
-                uint8_t* st = smem + s * Cfg::kStageBytes;
-                mbar_expect_tx(&full[s], Cfg::kStageBytes);
-                const int ac = p.a_ch_off + cb * BK, aw = w0 + tkw - p.pw, ah = h0 + tkh - p.ph, ad = od + tkd - p.pd;
-                const int b2 = p.w_batched ? n : tap;
-                tma_load_5d(st, &tmA_hi, &full[s], ac, aw, ah, ad, n);
-                tma_load_3d(st + Cfg::kPlanes * Cfg::kABytes, &tmB_hi, &full[s], cb * BK + p.w_k_off, n0, b2);
-                if (NPROD == 3) {
-                    tma_load_5d(st + Cfg::kABytes, &tmA_lo, &full[s], ac, aw, ah, ad, n);
-                    tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK + p.w_k_off, n0, b2);
+            int it = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                int kb_begin, kb_end, n0, n, od, h0, w0;
+                decode(item, kb_begin, kb_end, n0, n, od, h0, w0);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+                    const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+                    uint8_t* st = smem + s * Cfg::kStageBytes;
+                    mbar_expect_tx(&full[s], Cfg::kStageBytes);
+                    const int ac = p.a_ch_off + cb * BK, aw = w0 + tkw - p.pw, ah = h0 + tkh - p.ph, ad = od + tkd - p.pd;
+                    const int b2 = p.w_batched ? n : tap;
+                    tma_load_5d(st, &tmA_hi, &full[s], ac, aw, ah, ad, n);
+                    tma_load_3d(st + Cfg::kPlanes * Cfg::kABytes, &tmB_hi, &full[s], cb * BK + p.w_k_off, n0, b2);
+                    if (NPROD == 3) {
+                        tma_load_5d(st + Cfg::kABytes, &tmA_lo, &full[s], ac, aw, ah, ad, n);
+                        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK + p.w_k_off, n0, b2);
+                    }
                 }
             }
         }
@@ -117,52 +131,71 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                const int it = kb - kb_begin;
-                const int s = it % Cfg::kStages;
-                const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
-                mbar_wait(&full[s], ph);
+            int it = 0, li = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+                int kb_begin, kb_end, n0, n, od, h0, w0;
+                decode(item, kb_begin, kb_end, n0, n, od, h0, w0);
+                const int as = li & 1;
+                mbar_wait(&accum_empty[as], (uint32_t)(((li >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-                const uint64_t da_hi = make_smem_desc(st);
-                const uint64_t db_hi = make_smem_desc(st + Cfg::kPlanes * Cfg::kABytes);
+                const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int first = (kb == kb_begin);
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint64_t da_hi = make_smem_desc(st);
+                    const uint64_t db_hi = make_smem_desc(st + Cfg::kPlanes * Cfg::kABytes);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
-                    if (NPROD == 3) {
-                        const uint64_t da_lo = make_smem_desc(st + Cfg::kABytes);
-                        const uint64_t db_lo = make_smem_desc(st + 2 * Cfg::kABytes + Cfg::kBBytes);
-                        umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (it | k) != 0);
-                        umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
-                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, 1u);
-                    } else {
-                        umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
+                        const uint32_t acc_flag = (first && k == 0) ? 0u : 1u;
+                        if (NPROD == 3) {
+                            const uint64_t da_lo = make_smem_desc(st + Cfg::kABytes);
+                            const uint64_t db_lo = make_smem_desc(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+                            umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
+                            umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                            umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                        } else {
+                            umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, acc_flag);
+                        }
                     }
+                    tc_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
                 }
-                tc_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
+                tc_commit(&accum_full[as]);      // accumulator complete
             }
-            tc_commit(accum_full);      // accumulator complete
         }
     } else {
         // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int ow = w0 + row % p.bw, oh = h0 + row / p.bw;
-        const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
+        int li = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+            int kb_begin, kb_end, n0, n, od, h0, w0;
+            decode(item, kb_begin, kb_end, n0, n, od, h0, w0);
+            const int as = li & 1;
+            const int ow = w0 + row % p.bw, oh = h0 + row / p.bw;
+            const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
+            mbar_wait(&accum_full[as], (uint32_t)((li >> 1) & 1));
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
-            const int ch0 = n0 + c * 32;
-            conv_epilogue32(p, acc, pos, ch0);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
+                if (c == BN / 32 - 1) {          // last TMEM read of this accumulator: hand it back before the stores
+                    tc_fence_before();
+                    mbar_arrive(&accum_empty[as]);
+                }
+                conv_epilogue32(p, acc, pos, n0 + c * 32);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
 
@@ -205,8 +238,18 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
             return HUPR_ERR_CUDA;
         configured = true;
     }
-    dim3 grid(m_tiles, p.cout / BN, p.k_split);
-    conv_gemm_kernel<BN, NPROD><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HUPR_ERR_CUDA;
+    }
+    ConvParams pp = p;
+    pp.m_tiles = m_tiles;
+    pp.n_tiles = p.cout / BN;
+    const long long items = (long long)pp.m_tiles * pp.n_tiles * pp.k_split;
+    if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
+    dim3 grid((unsigned)(items < num_sms ? items : num_sms), 1, 1);
+    conv_gemm_kernel<BN, NPROD><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
