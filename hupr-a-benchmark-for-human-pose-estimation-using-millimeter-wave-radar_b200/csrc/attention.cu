@@ -19,6 +19,10 @@
 #include "tc.cuh"
 #include "split.cuh"
 
+#ifndef HUPR_ATTN_P_IN_TMEM
+#define HUPR_ATTN_P_IN_TMEM 1      // 1: softmax probabilities stay in TMEM (tcgen05.st, A-from-TMEM MMA); 0: 128B-swizzled smem tile
+#endif
+
 namespace hupr {
 
 constexpr int AT_BM = 128;       // queries per CTA
@@ -41,7 +45,8 @@ struct AttnCfg {
     static constexpr int kSmX = kSmBar + 128;                     // float [2 parity][2 halves][128 rows] row-max exchange
     static constexpr int kSmEnd = kSmX + 2048;
     static constexpr int kTmemO = 2 * BKV;                        // S0 = [0, BKV), S1 = [BKV, 2 BKV), O = [2 BKV, 2 BKV + D)
-    static constexpr int kTmemCols = (2 * BKV + D) <= 256 ? 256 : 512;
+    static constexpr int kTmemP = 2 * BKV + D;                    // P_hi = [kTmemP, + BKV/2), P_lo = [.. + BKV/2, + BKV): bf16 pairs per column
+    static constexpr int kTmemCols = (2 * BKV + D + BKV) <= 256 ? 256 : 512;
     static_assert(kSmEnd + 896 <= AT_SMEM, "attention shared-memory plan does not fit");
 };
 
@@ -180,13 +185,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 for (int k = 0; k < BKV / 16; ++k) {      // O (+)= P_j . V_j
                     const uint32_t atom = (uint32_t)(k >> 2);
                     const uint64_t koff = (uint64_t)((k & 3) * 2);
-                    const uint64_t dp_hi = make_smem_desc(sP + atom * (AT_BM * 128)) + koff;
-                    const uint64_t dp_lo = make_smem_desc(sP + Cfg::kPPlane + atom * (AT_BM * 128)) + koff;
                     const uint64_t dv_hi = make_smem_desc(st + 2 * Cfg::kKPlane + atom * (D * 128)) + koff;
                     const uint64_t dv_lo = make_smem_desc(st + 2 * Cfg::kKPlane + Cfg::kVPlane + atom * (D * 128)) + koff;
+#if HUPR_ATTN_P_IN_TMEM
+                    // P is the A operand straight from tensor memory: 16 keys = 8 packed columns per k-step
+                    const uint32_t ap_hi = tmem_base + (uint32_t)(Cfg::kTmemP + k * 8);
+                    const uint32_t ap_lo = ap_hi + (uint32_t)(BKV / 2);
+                    umma_bf16_ts(tmem_O, ap_lo, dv_hi, idesc_pv, (j | k) != 0);
+                    umma_bf16_ts(tmem_O, ap_hi, dv_lo, idesc_pv, 1u);
+                    umma_bf16_ts(tmem_O, ap_hi, dv_hi, idesc_pv, 1u);
+#else
+                    const uint64_t dp_hi = make_smem_desc(sP + atom * (AT_BM * 128)) + koff;
+                    const uint64_t dp_lo = make_smem_desc(sP + Cfg::kPPlane + atom * (AT_BM * 128)) + koff;
                     umma_bf16(tmem_O, dp_lo, dv_hi, idesc_pv, (j | k) != 0);
                     umma_bf16(tmem_O, dp_hi, dv_lo, idesc_pv, 1u);
                     umma_bf16(tmem_O, dp_hi, dv_hi, idesc_pv, 1u);
+#endif
                 }
                 tc_commit(&v_empty[s]);
                 tc_commit(pv_done);
@@ -262,6 +276,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             m_run = mx;
             nm_run = nm;
             l_run += sum;
+#if HUPR_ATTN_P_IN_TMEM
+            {   // P stays in tensor memory (A operand of the P.V MMAs): this thread's SC keys are SC/2 packed columns of each plane
+                uint32_t ph[NV * 16], pl[NV * 16];
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { ph[c * 16 + i] = v[c][2 * i]; pl[c * 16 + i] = v[c][2 * i + 1]; }
+                }
+                const uint32_t tp = tmem_base + (uint32_t)(Cfg::kTmemP + half * (SC / 2)) + lane_sel;
+                if constexpr (NV == 2) {
+                    tmem_st32(tp, ph);
+                    tmem_st32(tp + (uint32_t)(BKV / 2), pl);
+                } else {
+                    tmem_st16(tp, ph);
+                    tmem_st16(tp + (uint32_t)(BKV / 2), pl);
+                }
+            }
+#else
             // 128B-swizzled K-major P tile: key column col of this row lives in atom col/64, 16-byte chunk ((col%64)/8) ^ (row & 7)
 #pragma unroll
             for (int c = 0; c < NV; ++c) {
@@ -274,6 +306,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 }
             }
             fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+#endif
             tc_fence_before();
             mbar_arrive(p_full);
         }
