@@ -42,7 +42,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("HUPR_NVCC_EXTRA", "").split()      # e.g. -DHUPR_ATTN_P_IN_TMEM=0 for A/B measurements
+    cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
