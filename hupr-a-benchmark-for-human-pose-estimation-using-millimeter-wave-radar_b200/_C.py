@@ -43,6 +43,19 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class WgradDesc(ctypes.Structure):
+    """Mirror of ``hupr_wgrad_desc``."""
+    _fields_ = [
+        ("x_hi", ctypes.c_void_p), ("x_lo", ctypes.c_void_p),
+        ("n", ctypes.c_int), ("d", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int), ("cx", ctypes.c_int),
+        ("x_ch_off", ctypes.c_int), ("cin", ctypes.c_int),
+        ("dy_hi", ctypes.c_void_p), ("dy_lo", ctypes.c_void_p), ("cy", ctypes.c_int), ("y_ch_off", ctypes.c_int), ("cout", ctypes.c_int),
+        ("kd", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
+        ("pd", ctypes.c_int), ("ph", ctypes.c_int), ("pw", ctypes.c_int),
+        ("dw", ctypes.c_void_p), ("dw_ld", ctypes.c_int),
+    ]
+
+
 class TensorView(ctypes.Structure):
     """Mirror of ``hupr_tensor_view``."""
     _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("ld", ctypes.c_int), ("ch_off", ctypes.c_int)]
@@ -59,6 +72,7 @@ SIGNATURES = {
     "hupr_launch_count": (ctypes.c_longlong, []),
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
+    "hupr_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), ctypes.c_void_p]),
     "hupr_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttnDesc), ctypes.c_void_p]),
     "hupr_window_normalize": (ctypes.c_int, [_P, _P, _I, _P, _P]),
     "hupr_frame_features_workspace_bytes": (ctypes.c_size_t, [_I]),

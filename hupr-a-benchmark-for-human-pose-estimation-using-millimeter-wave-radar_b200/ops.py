@@ -290,6 +290,29 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.9
     return params
 
 
+def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=None):
+    """dW[tap, ci, co] of a stride-1 convolution straight from the channels-last tensors (hupr_conv_wgrad): x SplitTensor
+    [n, d, h, w, cx], dy SplitTensor [n, d_out, h, w, cy] -> float32 [taps, cin, cout] (ACCUMULATED into ``out`` when given)."""
+    n, d, h, w, cx = x.hi.shape
+    taps = kernel[0] * kernel[1] * kernel[2]
+    if out is None:
+        out = torch.zeros((taps, cin, cout), dtype=torch.float32, device=x.hi.device)
+    desc = _C.WgradDesc()
+    desc.x_hi, desc.x_lo = x.hi.data_ptr(), _C.optr(x.lo)
+    desc.n, desc.d, desc.h, desc.w, desc.cx = n, d, h, w, cx
+    desc.x_ch_off, desc.cin = x_ch_off, cin
+    desc.dy_hi, desc.dy_lo, desc.cy = dy.hi.data_ptr(), _C.optr(dy.lo), dy.hi.shape[-1]
+    desc.y_ch_off, desc.cout = y_ch_off, cout
+    desc.kd, desc.kh, desc.kw = kernel
+    desc.pd, desc.ph, desc.pw = pad
+    desc.dw, desc.dw_ld = out.data_ptr(), out.shape[-1]
+    d_out = d + 2 * pad[0] - kernel[0] + 1
+    flops = 2.0 * n * d_out * h * w * cout * cin * taps
+    with torch.cuda.device(x.hi.device), _timed("conv_wgrad", flops):
+        _C.check(_C.lib().hupr_conv_wgrad(desc, _C.stream_ptr()), "hupr_conv_wgrad")
+    return out
+
+
 class KMajorGeometry(object):
     """Zero-padded linear position index shared by the two operands of a weight-gradient GEMM (see hupr_to_kmajor).  Wp is rounded
     up to a multiple of 8 so that the depth/height parts of a tap offset are 16-byte aligned (a TMA requirement); the +-1 shifts

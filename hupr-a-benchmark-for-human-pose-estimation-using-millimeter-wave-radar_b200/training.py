@@ -68,30 +68,13 @@ class ConvOp(object):
         return ops.conv_gemm(dy, self.cout, self.wd, self.cin_pad, kernel=self.kernel, pad=dpad, out=out, **kw)
 
     def wgrad(self, x, x_off, dy, dy_off, grads):
-        """x: saved input [n, d, h, w, ld]; dy: output gradient [n, d_out, h, w, ld'] -> grads[name] (+ bias gradient)."""
-        n, d, h, w, _ = x.hi.shape
+        """x: saved input [n, d, h, w, ld]; dy: output gradient [n, d_out, h, w, ld'] -> grads[name] (+ bias gradient).
+        One hupr_conv_wgrad launch: positions are contracted on the tensor cores straight from the channels-last tensors."""
         dev = x.hi.device
-        geom = ops.KMajorGeometry(n, d, h, w, self.pad)
-        cin_rows = self.cin_pad
-        c_in = min(self.cin_pad, x.hi.shape[-1] - x_off)
-        kw_n = self.kernel[2]
-        xt = _S((kw_n * cin_rows, geom.ppad), dev, zero=True)
-        if c_in % 64 == 0:
-            ops.to_kmajor_multi(x, x_off, c_in, geom, xt, -self.pad[2], kw_n, cin_rows)          # all kw copies from one read
-        else:
-            for kw in range(kw_n):
-                blk = SplitTensor(xt.hi[kw * cin_rows:(kw + 1) * cin_rows], xt.lo[kw * cin_rows:(kw + 1) * cin_rows])
-                ops.to_kmajor(x, x_off, c_in, geom, blk, shift=kw - self.pad[2])
-        rows = -(-self.cout // 128) * 128
-        dyt = _S((rows, geom.ppad), dev, zero=True)
-        ops.to_kmajor(dy, dy_off, self.cout, geom, dyt)
-        acc = torch.zeros((self.kernel[0] * self.kernel[1], rows, kw_n * cin_rows), dtype=torch.float32, device=dev)
-        ops.conv_wgrad(xt, cin_rows, dyt, rows, geom, self.kernel, acc)
-        acc = acc.view(self.kernel[0] * self.kernel[1], rows, kw_n, cin_rows).permute(0, 2, 1, 3).reshape(self.taps, rows, cin_rows)
+        acc = ops.conv_wgrad_direct(x, x_off, self.cin_pad, dy, dy_off, self.cout, self.kernel, self.pad)      # [taps, cin_pad, cout]
         o = 0
         for name, c, cp in zip(self.names, self.couts, self.cout_pads):
-            g = acc[:, o:o + c, :self.cin].permute(1, 2, 0).reshape((c, self.cin) + self.kernel)
-            grads[name] = g
+            grads[name] = acc[:, :self.cin, o:o + c].permute(2, 1, 0).reshape((c, self.cin) + self.kernel)
             o += cp
         if self.bias_name:
             s1 = torch.zeros(self.cout, dtype=torch.float64, device=dev)

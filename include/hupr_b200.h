@@ -255,6 +255,23 @@ int hupr_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, 
 int hupr_to_kmajor_multi(const void* src_hi, const void* src_lo, int n, int d, int h, int w, int ld, int ch_off, int c, void* dst_hi,
                          void* dst_lo, int dp, int hp, int wp, int pd, int ph, int pw, int first_shift, int n_copies,
                          long long rows_per_copy, long long ppad, void* stream);
+/* Weight gradient of a stride-1 convolution read straight from the channels-last tensors (no position-major copies):
+ *   dW[tap][ci][co] += sum_{n,d,h,w} X[n, d+kd-pd, h+kh-ph, w+kw-pw, x_ch_off+ci] * dY[n, d, h, w, y_ch_off+co]      tap = (kd*KH + kh)*KW + kw
+ * — what autograd derives for nn.Conv3d / nn.Conv2d weights in loss.backward() (/root/reference/tools/run.py:78; the convolutions of
+ * /root/reference/models/layers.py:24-32,45-63,116-123,195-210).  The contraction runs over POSITIONS on the tensor cores with both
+ * operands MN-major (channels contiguous), a filter tap being a TMA coordinate offset with out-of-bounds zero fill.
+ * x  : bf16 split [n][d][h][w][cx];  dy : bf16 split [n][d_out][h][w][cy], d_out = d + 2*pd - kd + 1 (H, W are 'same': k = 2p+1)
+ * dw : float [taps*cin][dw_ld], row = tap*cin + ci, column = co; ACCUMULATED with atomic adds (split-K) — zero it first.
+ * cin, cout multiples of 64 (channel slices may run past cx / cy up to the next multiple of 64: those read as zero);
+ * w must divide 64 or be a multiple of 64, h a multiple of 64 / min(w, 64). */
+typedef struct hupr_wgrad_desc {
+    const void* x_hi; const void* x_lo; int n, d, h, w, cx, x_ch_off, cin;
+    const void* dy_hi; const void* dy_lo; int cy, y_ch_off, cout;
+    int kd, kh, kw, pd, ph, pw;
+    float* dw; int dw_ld;
+} hupr_wgrad_desc;
+int hupr_conv_wgrad(const hupr_wgrad_desc* desc, void* stream);
+
 int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
                           float* d_heat_logits, float* d_gcn_pre, void* stream);
 int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,

@@ -210,8 +210,11 @@ def test_training_step_matches_autograd_oracle_and_adam():
 
 
 def test_graph_replayed_training_equals_eager_training():
-    """TrainStep.capture(): three CUDA-graph replays (forward + backward + Adam with the device-side step counter) leave the same
-    parameters as three eager steps on the same batch."""
+    """TrainStep.capture(): a CUDA-graph replay produces the same gradients as an eager pass (round-off level: the split-K partial
+    sums are added atomically, so two identical eager passes already differ by ~3e-6 in relative L2 — measured), and three replays
+    with the captured Adam launch (device-side step counter) follow the eager trajectory.  Five early Adam steps on a batch of one are
+    chaotic (each step is ~lr * sign(g), so round-off-level gradients flip single weights): two EAGER runs measured 5e-4 apart in the
+    loss after five steps and eager vs graph 2e-3, hence the 5e-3 bound on the trajectory and the tight bound on the gradients."""
     from hupr_b200.models import HuPRNet
     from hupr_b200.training import TrainStep
     from oracle import model as om
@@ -219,12 +222,32 @@ def test_graph_replayed_training_equals_eager_training():
     sd = om.make_state_dict(4)
     hori, vert = (t.cuda() for t in om.make_vrdae(1, 4))
     joints = torch.randint(0, 256, (1, 14, 2), generator=torch.Generator().manual_seed(5)).cuda()
-    results = []
-    for mode in ("eager", "graph"):
+
+    def fresh():
         net = HuPRNet(make_cfg())
         net.load_state_dict(sd)
         net = net.cuda().train()
-        step = TrainStep(net)
+        return net, TrainStep(net)
+
+    # ---- gradients: eager pass vs graph replay on identical weights (no optimizer in the graph)
+    net, step = fresh()
+    loss_e, _ = step.forward_backward(hori, vert, joints)
+    g_eager = step.flat_g.clone()
+    loss_e = float(loss_e)
+    replay = step.capture(hori, vert, joints, with_optimizer=False)
+    step.flat_g.zero_()
+    loss_g, _ = replay()
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - loss_e) < 1e-6 * abs(loss_e)
+    assert float((step.flat_g - g_eager).norm() / g_eager.norm()) < 5e-5
+    loss_g2, _ = replay()                                       # a second replay starts from zeroed accumulators again
+    torch.cuda.synchronize()
+    assert float((step.flat_g - g_eager).norm() / g_eager.norm()) < 5e-5
+
+    # ---- trajectories: 5 eager steps vs 2 warm-up steps + 3 replays
+    results = []
+    for mode in ("eager", "graph"):
+        net, step = fresh()
         losses = []
         if mode == "eager":
             for _ in range(5):
@@ -243,7 +266,7 @@ def test_graph_replayed_training_equals_eager_training():
     assert n_e == n_g == 5
     assert l_e[4] < l_e[0]                                    # the loss goes down on a repeated batch
     for a, b in zip(l_e[2:], l_g[2:]):
-        assert abs(a - b) < 1e-3 * abs(a)
+        assert abs(a - b) < 5e-3 * abs(a)
     # Early Adam steps move every weight by ~lr * sign(g): an element whose gradient is at round-off level (atomics order, mask flips)
     # may step the other way in the two runs, so single elements differ by up to 2 * lr per step while the bulk agrees tightly.
     for k in p_e:
