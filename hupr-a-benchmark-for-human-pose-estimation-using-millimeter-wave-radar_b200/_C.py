@@ -53,6 +53,7 @@ class WgradDesc(ctypes.Structure):
         ("kd", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
         ("pd", ctypes.c_int), ("ph", ctypes.c_int), ("pw", ctypes.c_int),
         ("dw", ctypes.c_void_p), ("dw_ld", ctypes.c_int),
+        ("batched", ctypes.c_int), ("dw_batch_stride", ctypes.c_longlong),
     ]
 
 

@@ -49,9 +49,10 @@ struct WgParams {
     int cin_blocks, x_ch_off, y_ch_off;
     int bw, bh, tiles_w, tiles_h;
     int atoms, slots, groups, n_tiles;
-    int kblocks, kb_per_split, k_split;
+    int kblocks, kb_per_split, k_split;   // kblocks: K blocks of the whole tensor, or of ONE sample in batched mode
     float* out;
     int out_ld;
+    long long out_batch_stride;            // batched mode: the samples are independent problems, dw[sample] = out + sample * stride
 };
 
 // MN-major, SWIZZLE_128B operand: rows (K) of 128 B = 64 channels; 8-row groups SBO = 1024 B apart; 64-channel atoms LBO apart.
@@ -91,8 +92,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
     // work item: (split-K slice, column tile of cout, group of accumulator slots)
     int item = blockIdx.x;
     const int group = item % p.groups; item /= p.groups;
-    const int n0 = (item % p.n_tiles) * BN;
-    const int z = item / p.n_tiles;
+    const int n0 = (item % p.n_tiles) * BN; item /= p.n_tiles;
+    const int z = item % p.k_split;
+    const int sample = item / p.k_split;               // 0 unless batched
     const int kb_begin = z * p.kb_per_split;
     const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
     const int slot0 = group * Cfg::kSlots;
@@ -123,7 +125,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
                 const int w0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
                 const int h0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
                 const int od = t % p.d_out;
-                const int n = t / p.d_out;
+                const int n = sample + t / p.d_out;
                 const int i = kb - kb_begin, yb = i & 1;
                 mbar_wait(&y_empty[yb], (uint32_t)(((i >> 1) & 1) ^ 1));
                 mbar_expect_tx(&y_full[yb], Cfg::kYBytes);
@@ -194,7 +196,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
         for (int sl = 0; sl < nslots; ++sl) {
             const int atom = (slot0 + sl) * 2 + (row >> 6);
             const bool valid = atom < p.atoms;
-            float* dst = p.out + ((size_t)atom * 64 + (row & 63)) * p.out_ld + n0;
+            float* dst = p.out + (size_t)sample * p.out_batch_stride + ((size_t)atom * 64 + (row & 63)) * p.out_ld + n0;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
@@ -231,7 +233,7 @@ static int encode_pos_map(CUtensorMap* map, const void* base, int c, int w, int 
 
 template <int BN>
 static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi, const CUtensorMap& y_lo, WgParams p,
-                        int cout, int num_sms, cudaStream_t stream) {
+                        int cout, int problems, int num_sms, cudaStream_t stream) {
     using Cfg = WgCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -240,13 +242,13 @@ static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const 
     }
     p.groups = (p.slots + Cfg::kSlots - 1) / Cfg::kSlots;
     p.n_tiles = cout / BN;
-    const int tiles = p.groups * p.n_tiles;
-    int ks = num_sms / tiles;                       // one wave of CTAs when the tile count allows it
+    const long long tiles = (long long)p.groups * p.n_tiles * problems;
+    int ks = (int)(num_sms / tiles);                       // one wave of CTAs when the tile count allows it
     if (ks < 1) ks = 1;
     if (ks > p.kblocks) ks = p.kblocks;
     p.kb_per_split = (p.kblocks + ks - 1) / ks;
     p.k_split = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
-    const long long items = (long long)tiles * p.k_split;
+    const long long items = tiles * p.k_split;
     if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
     wgrad_kernel<BN><<<(unsigned)items, WG_THREADS, Cfg::kSmemBytes, stream>>>(x_hi, x_lo, y_hi, y_lo, p);
     note_launches(1);
@@ -281,7 +283,9 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
         if (prop.major != 10) return HUPR_ERR_ARCH;
         num_sms = prop.multiProcessorCount;
     }
-    const long long kblocks = (long long)d->n * d_out * (d->h / bh) * (d->w / bw);
+    const int problems = d->batched ? d->n : 1;
+    if (d->batched && (d->dw_batch_stride < 0 || d->dw_batch_stride % 4)) return HUPR_ERR_BAD_ARG;
+    const long long kblocks = (long long)(d->batched ? 1 : d->n) * d_out * (d->h / bh) * (d->w / bw);
     if (kblocks > 2147483647LL) return HUPR_ERR_BAD_ARG;
 
     WgParams p;
@@ -293,7 +297,7 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     p.slots = (p.atoms + 1) / 2;
     p.groups = 0; p.n_tiles = 0;
     p.kblocks = (int)kblocks; p.kb_per_split = 0; p.k_split = 0;
-    p.out = d->dw; p.out_ld = d->dw_ld;
+    p.out = d->dw; p.out_ld = d->dw_ld; p.out_batch_stride = d->batched ? d->dw_batch_stride : 0;
 
     CUtensorMap x_hi, x_lo, y_hi, y_lo;
     int rc;
@@ -302,7 +306,7 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     if ((rc = encode_pos_map(&y_hi, d->dy_hi, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
     if ((rc = encode_pos_map(&y_lo, d->dy_lo, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (d->cout % 256 == 0) return launch_wgrad<256>(x_hi, x_lo, y_hi, y_lo, p, d->cout, num_sms, s);
-    if (d->cout % 128 == 0) return launch_wgrad<128>(x_hi, x_lo, y_hi, y_lo, p, d->cout, num_sms, s);
-    return launch_wgrad<64>(x_hi, x_lo, y_hi, y_lo, p, d->cout, num_sms, s);
+    if (d->cout % 256 == 0) return launch_wgrad<256>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    if (d->cout % 128 == 0) return launch_wgrad<128>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    return launch_wgrad<64>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
 }

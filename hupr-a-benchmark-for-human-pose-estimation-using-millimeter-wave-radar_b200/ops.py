@@ -290,13 +290,14 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.9
     return params
 
 
-def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=None):
+def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=None, batched=False, tag="conv_wgrad"):
     """dW[tap, ci, co] of a stride-1 convolution straight from the channels-last tensors (hupr_conv_wgrad): x SplitTensor
-    [n, d, h, w, cx], dy SplitTensor [n, d_out, h, w, cy] -> float32 [taps, cin, cout] (ACCUMULATED into ``out`` when given)."""
+    [n, d, h, w, cx], dy SplitTensor [n, d_out, h, w, cy] -> float32 [taps, cin, cout] (ACCUMULATED into ``out`` when given).
+    ``batched``: no sum over the samples, out is [n, taps, cin, cout]."""
     n, d, h, w, cx = x.hi.shape
     taps = kernel[0] * kernel[1] * kernel[2]
     if out is None:
-        out = torch.zeros((taps, cin, cout), dtype=torch.float32, device=x.hi.device)
+        out = torch.zeros(((n,) if batched else ()) + (taps, cin, cout), dtype=torch.float32, device=x.hi.device)
     desc = _C.WgradDesc()
     desc.x_hi, desc.x_lo = x.hi.data_ptr(), _C.optr(x.lo)
     desc.n, desc.d, desc.h, desc.w, desc.cx = n, d, h, w, cx
@@ -306,11 +307,23 @@ def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=Non
     desc.kd, desc.kh, desc.kw = kernel
     desc.pd, desc.ph, desc.pw = pad
     desc.dw, desc.dw_ld = out.data_ptr(), out.shape[-1]
+    if batched:
+        desc.batched, desc.dw_batch_stride = 1, out.stride(0)
     d_out = d + 2 * pad[0] - kernel[0] + 1
     flops = 2.0 * n * d_out * h * w * cout * cin * taps
-    with torch.cuda.device(x.hi.device), _timed("conv_wgrad", flops):
+    with torch.cuda.device(x.hi.device), _timed(tag, flops):
         _C.check(_C.lib().hupr_conv_wgrad(desc, _C.stream_ptr()), "hupr_conv_wgrad")
     return out
+
+
+def matmul_tn(a, b, b_ch_off, c, out):
+    """out[s, m, :c] += sum_n a[s, n, m] * b[s, n, b_ch_off : b_ch_off + c] per sample s (hupr_conv_wgrad, batched): a SplitTensor
+    [B, rows, cols] row-major, b SplitTensor [B, rows, ld]; out float32 [B, cols, c].  The attention backward's dK = dS^T Q and
+    dV = P^T dO without transposed copies of the [S, S] matrices."""
+    bsz, rows, cols = a.hi.shape
+    av = SplitTensor(a.hi.view(bsz, 1, 1, rows, cols), a.lo.view(bsz, 1, 1, rows, cols))
+    bv = SplitTensor(b.hi.view(bsz, 1, 1, rows, b.hi.shape[-1]), b.lo.view(bsz, 1, 1, rows, b.hi.shape[-1]))
+    return conv_wgrad_direct(av, 0, cols, bv, b_ch_off, c, (1, 1, 1), (0, 0, 0), out=out.view(bsz, 1, cols, c), batched=True, tag="matmul_tn")
 
 
 class KMajorGeometry(object):

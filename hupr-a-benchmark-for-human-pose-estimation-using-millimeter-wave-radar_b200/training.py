@@ -4,10 +4,11 @@ backward pass and Adam, every arithmetic step a launch into libhupr_b200.so.
 Replaces ``loss.backward(); optimizer.step()`` of /root/reference/tools/run.py:76-79 with ``optim.Adam(lr 1e-4, betas (.9,.999),
 weight_decay 1e-4)`` of tools/base.py:47.  There is no autograd graph: the backward of each stage is written out against the
 tensors the forward saved —
-  convolutions : dgrad = the implicit-GEMM kernel with flipped filters; wgrad = the same kernel contracting over positions
-                 (position-major padded copies, split-K, shifted operand) — ops.conv_wgrad
+  convolutions : dgrad = the implicit-GEMM kernel with flipped filters; wgrad = hupr_conv_wgrad: positions contracted on the tensor
+                 cores with MN-major operands read straight from the channels-last tensors — ops.conv_wgrad_direct
   BatchNorm    : batch statistics (double sums), affine + ReLU, standard three-term backward — train_ops
   attention    : P is recomputed (QK^T GEMM + row softmax), then dV = P^T dO, dP = dO V^T, dS = P*(dP - rowsum), dQ = dS K, dK = dS^T Q
+                 (the two A^T B products contract over queries with MN-major operands — ops.matmul_tn, no transposed [S,S] copies)
   PRGCN        : the transposed-layout GEMMs of the forward with W^T, adjacency mixes with A^T, adjoint resampling
 This first version favours exactness over speed (fp32-equivalent hi/lo arithmetic everywhere, unfused backward attention).
 """
@@ -261,7 +262,10 @@ class AttentionLevel(object):
         dcat_s = _rows(dcat)
         v = {"ra": self.ra, "re": self.re}
         dpr = {"ra": _S((b, 1, 1, s, 4 * c), dev), "re": _S((b, 1, 1, s, 4 * c), dev)}
-        dv = {"ra": None, "re": None}
+        # dV of both attentions that read a map as V accumulate in one fp32 buffer; the A^T B products (dK = dS^T Q, dV = P^T dO)
+        # contract over the query axis with MN-major tensor-core operands (ops.matmul_tn): no transposed [S, S] copies
+        dvf = {"ra": torch.zeros((b, s, c), dtype=torch.float32, device=dev), "re": torch.zeros((b, s, c), dtype=torch.float32, device=dev)}
+        dv_res = {}
         for qs, qo, ks, ko, vs, oo, res in self._plan():
             scratch = torch.empty((b, 1, 1, s, s), dtype=torch.float32, device=dev)
             kview = SplitTensor(self.pr[ks].hi.view(b, s, 4 * c), self.pr[ks].lo.view(b, s, 4 * c))
@@ -273,16 +277,18 @@ class AttentionLevel(object):
             T.softmax_bwd_rows(probs, scratch, dsm)
             kt = ops.transpose_split(self.pr[ks], c, _S((b, c, s), dev), in_ch_off=ko)
             ops.conv_gemm(dsm, s, kt, c, w_batched=True, out=dpr[qs], o_ch_off=qo)                                 # dQ = dS K
-            dst = ops.transpose_split(SplitTensor(dsm.hi.view(b, s, s), dsm.lo.view(b, s, s)), s, _S((b, s, s), dev))
-            qt = ops.transpose_split(self.pr[qs], c, _S((b, c, s), dev), in_ch_off=qo)
-            ops.conv_gemm(SplitTensor(dst.hi.view(b, 1, 1, s, s), dst.lo.view(b, 1, 1, s, s)), s, qt, c, w_batched=True, out=dpr[ks], o_ch_off=ko)   # dK = dS^T Q
-            pt = ops.transpose_split(SplitTensor(probs.hi.view(b, s, s), probs.lo.view(b, s, s)), s, _S((b, s, s), dev))
-            dot = ops.transpose_split(dcat_s, c, _S((b, c, s), dev), in_ch_off=oo)
-            new = _S((b, 1, 1, s, c), dev)
-            ops.conv_gemm(SplitTensor(pt.hi.view(b, 1, 1, s, s), pt.lo.view(b, 1, 1, s, s)), s, dot, c, w_batched=True, residual=dv[vs], out=new)   # dV += P^T dO
+            dkf = torch.zeros((b, s, c), dtype=torch.float32, device=dev)
+            ops.matmul_tn(SplitTensor(dsm.hi.view(b, s, s), dsm.lo.view(b, s, s)), SplitTensor(self.pr[qs].hi.view(b, s, 4 * c), self.pr[qs].lo.view(b, s, 4 * c)),
+                          qo, c, dkf)                                                                              # dK = dS^T Q
+            T.accumulate((dpr[ks], ko), c, f=dkf.view(b * s, c))
+            ops.matmul_tn(SplitTensor(probs.hi.view(b, s, s), probs.lo.view(b, s, s)),
+                          SplitTensor(dcat_s.hi.view(b, s, -1), dcat_s.lo.view(b, s, -1)), oo, c, dvf[vs])         # dV += P^T dO
             if res:
-                T.accumulate(new, c, a=new, b=(dcat_s, oo))
-            dv[vs] = new
+                dv_res[vs] = oo
+        dv = {}
+        for key in ("ra", "re"):
+            dv[key] = _S((b, 1, 1, s, c), dev)
+            T.accumulate(dv[key], c, b=(dcat_s, dv_res[key]) if key in dv_res else None, f=dvf[key].view(b * s, c))
         out = {}
         for key, proj in (("ra", self.proj_h), ("re", self.proj_v)):
             proj.wgrad(v[key], 0, dpr[key], 0, grads)

@@ -263,12 +263,16 @@ int hupr_to_kmajor_multi(const void* src_hi, const void* src_lo, int n, int d, i
  * x  : bf16 split [n][d][h][w][cx];  dy : bf16 split [n][d_out][h][w][cy], d_out = d + 2*pd - kd + 1 (H, W are 'same': k = 2p+1)
  * dw : float [taps*cin][dw_ld], row = tap*cin + ci, column = co; ACCUMULATED with atomic adds (split-K) — zero it first.
  * cin, cout multiples of 64 (channel slices may run past cx / cy up to the next multiple of 64: those read as zero);
- * w must divide 64 or be a multiple of 64, h a multiple of 64 / min(w, 64). */
+ * w must divide 64 or be a multiple of 64, h a multiple of 64 / min(w, 64).
+ * batched != 0: the n samples are independent problems (no sum over n), dw[sample] = dw + sample * dw_batch_stride floats — the
+ * "A^T B" products of the attention backward (/root/reference/models/layers.py:126-133 under autograd): dK = dS^T Q and dV = P^T dO are
+ * contractions over the QUERY axis of row-major [queries][keys] matrices, i.e. x = the matrix with cx = keys "channels". */
 typedef struct hupr_wgrad_desc {
     const void* x_hi; const void* x_lo; int n, d, h, w, cx, x_ch_off, cin;
     const void* dy_hi; const void* dy_lo; int cy, y_ch_off, cout;
     int kd, kh, kw, pd, ph, pw;
     float* dw; int dw_ld;
+    int batched; long long dw_batch_stride;
 } hupr_wgrad_desc;
 int hupr_conv_wgrad(const hupr_wgrad_desc* desc, void* stream);
 

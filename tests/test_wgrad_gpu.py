@@ -77,3 +77,20 @@ def test_wgrad_direct_rejects_bad_arguments():
     X24 = SplitTensor.empty((1, 1, 24, 24, 64), "cuda")
     with pytest.raises(RuntimeError):
         ops.conv_wgrad_direct(X24, 0, 64, X24, 0, 64, (1, 1, 1), (0, 0, 0))       # W = 24 does not tile 64-position K blocks
+
+
+@pytest.mark.parametrize("shape", [(3, 256, 256, 256, 1024, 512), (2, 1024, 1024, 128, 512, 0), (2, 4096, 4096, 64, 320, 64)])
+def test_matmul_tn_batched_matches_float64(shape):
+    """out[s] += a[s]^T b[s][:, off:off+c] (the attention backward's dK = dS^T Q, dV = P^T dO): batched mode of hupr_conv_wgrad."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    bsz, rows, cols, c, ld, off = shape
+    torch.manual_seed(23)
+    a = torch.randn(bsz, rows, cols, device="cuda")
+    bm = torch.randn(bsz, rows, ld, device="cuda")
+    out = torch.full((bsz, cols, c), 0.25, device="cuda")
+    ops.matmul_tn(SplitTensor.from_float(a), SplitTensor.from_float(bm), off, c, out)
+    torch.cuda.synchronize()
+    ref = torch.matmul(a.double().transpose(1, 2), bm.double()[:, :, off:off + c])
+    err = float(((out.double() - 0.25) - ref).abs().max() / ref.abs().max())
+    assert err < 3e-5, err
