@@ -89,6 +89,7 @@ SIGNATURES = {
     "hupr_gcn_mix": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "hupr_gcn_heads": (ctypes.c_int, [_P, _I, _P, _I, _P]),
     "hupr_keypoints_argmax": (ctypes.c_int, [_P, _I, _P, _P, _P]),
+    "hupr_keypoint_oks": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_channel_sums": (ctypes.c_int, [_I, _TV, _TV, _TV, _P, _P, ctypes.c_longlong, _I, _P, _P, _P]),
     "hupr_affine_act": (ctypes.c_int, [_TV, _P, _P, _TV, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_bn_bwd_apply": (ctypes.c_int, [_TV, _TV, _TV, _P, _P, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),

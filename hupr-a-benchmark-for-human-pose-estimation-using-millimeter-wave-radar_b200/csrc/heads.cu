@@ -321,6 +321,38 @@ extern "C" int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
+// Object keypoint similarity of one detection against one ground-truth pose per image (the reference's vendored COCOeval.computeOks,
+// /root/reference/misc/cocoeval.py:192-236, for the HuPR case: every joint labelled visible).  float64 like the numpy original.
+__global__ void oks_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const double* __restrict__ area,
+                           const double* __restrict__ sigmas, int n, int k, double* __restrict__ oks, double* __restrict__ per_joint) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double denom = area[i] + 2.220446049250313e-16;      // np.spacing(1)
+    double acc = 0.0;
+    for (int j = 0; j < k; ++j) {
+        const double dx = (double)pred[(i * k + j) * 2] - (double)gt[(i * k + j) * 2];
+        const double dy = (double)pred[(i * k + j) * 2 + 1] - (double)gt[(i * k + j) * 2 + 1];
+        const double var = (sigmas[j] * 2.0) * (sigmas[j] * 2.0);
+        const double e = (dx * dx + dy * dy) / var / denom / 2.0;
+        const double sim = exp(-e);
+        if (per_joint) per_joint[i * k + j] = sim;
+        acc += sim;
+    }
+    oks[i] = acc / (double)k;
+}
+
+extern "C" int hupr_keypoint_oks(const float* pred, const float* gt, const double* area, const double* sigmas, int n, int k, double* oks,
+                                 double* per_joint, void* stream) {
+    if (n < 0 || k <= 0) return HUPR_ERR_BAD_ARG;
+    if (n == 0) return HUPR_OK;
+    if (!pred || !gt || !area || !sigmas || !oks) return HUPR_ERR_BAD_ARG;
+    int rc = heads_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    oks_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pred, gt, area, sigmas, n, k, oks, per_joint);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
 extern "C" int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch,
                                      void* workspace, size_t ws_bytes, float* losses, float* targets, float* gt2d, void* stream) {
     if (batch < 0) return HUPR_ERR_BAD_ARG;

@@ -7,7 +7,8 @@ generated ``<dataDir>/<phase>_gt.json`` in COCO keypoint format).  What changes 
 normalises 256 planes per sample on the CPU (dataset.py:139-150, base.py:13-24; 1.25 s/sample); here the cube slices are uploaded
 once per frame and ``hupr_window_normalize`` standardises them on the GPU, with a small per-frame cache because consecutive windows
 share 7 of their 8 frames.  Items therefore carry CUDA tensors and the DataLoader must run with ``num_workers=0``.
-COCO evaluation (``evaluate`` / ``evaluateEach``) is delegated to pycocotools exactly like the reference; it is not on the hot path.
+COCO evaluation (``evaluate`` / ``evaluateEach``) uses ``hupr_b200.misc.keypoint_eval``, a mirror of the reference's vendored evaluator
+(misc/cocoeval.py) pinned to it by golden statistics; ``evaluatePoses`` evaluates device-resident poses without the results file.
 """
 import collections
 import json
@@ -107,10 +108,14 @@ class HuPR3D_horivert(data.Dataset):
             self._cache.move_to_end(path)
             return hit
         cube = np.load(path)
-        if cube.shape != (16, 64, 64, 8):
-            raise ValueError("%s: expected a [16,64,64,8] cube, got %s" % (path, (cube.shape,)))
-        dev_cube = torch.from_numpy(np.ascontiguousarray(cube.astype(np.complex64))).to(self.device).unsqueeze(0)
-        planes = ops.window_normalize(dev_cube, torch.zeros(1, dtype=torch.int32, device=self.device))[0]
+        if cube.shape == (8, 2, 64, 64, 8) and cube.dtype == np.float32:
+            # compact cache (RadarObject(cacheFormat='planes') / datasets.cubecache.convert): already standardised
+            planes = torch.from_numpy(cube).to(self.device)
+        else:
+            if cube.shape != (16, 64, 64, 8):
+                raise ValueError("%s: expected a [16,64,64,8] cube or a float32 [8,2,64,64,8] plane cache, got %s %s" % (path, cube.dtype, (cube.shape,)))
+            dev_cube = torch.from_numpy(np.ascontiguousarray(cube.astype(np.complex64))).to(self.device).unsqueeze(0)
+            planes = ops.window_normalize(dev_cube, torch.zeros(1, dtype=torch.int32, device=self.device))[0]
         self._cache[path] = planes
         if len(self._cache) > self._cache_frames:
             self._cache.popitem(last=False)
@@ -131,39 +136,50 @@ class HuPR3D_horivert(data.Dataset):
     def __len__(self):
         return len(self.VRDAEPaths_hori) // self.sampling_ratio
 
-    # ------------------------------------------------------------------------------------------------ COCO evaluation (off the hot path)
-    def _coco_tools(self):
-        try:
-            from pycocotools.coco import COCO
-            from pycocotools.cocoeval import COCOeval
-        except ImportError as exc:
-            raise RuntimeError("COCO keypoint evaluation needs pycocotools patched with the reference's misc/coco.py and misc/cocoeval.py "
-                               "(README of the reference, 'Evaluation'); it is not part of hupr_b200") from exc
+    # ------------------------------------------------------------------------------------------------ COCO keypoint evaluation
+    # The reference patches pycocotools with its own misc/coco.py + misc/cocoeval.py (README 'Evaluation'); hupr_b200.misc.keypoint_eval
+    # mirrors that evaluator for HuPR's one-pose-per-image files (pinned to it by tests/golden/cocoeval_reference.npz), so no
+    # pycocotools install is needed and the similarities can be computed on the GPU.
+    def _keval(self):
+        from ..misc.keypoint_eval import KeypointEval
         if self._coco is None:
-            self._coco = COCO(self.gtFile)
-        return self._coco, COCOeval
+            self._coco = KeypointEval(self.gtFile)
+        return self._coco
+
+    @staticmethod
+    def _print_stats(stats):
+        labels = ["AP", "AP .5", "AP .75", "AP (M)", "AP (L)", "AR", "AR .5", "AR .75", "AR (M)", "AR (L)"]
+        print(" | ".join("%s %.3f" % (l, v) for l, v in zip(labels, stats)))
 
     def evaluate(self, loadDir):
-        coco, COCOeval = self._coco_tools()
-        res_file = os.path.join(loadDir, "%s_results.json" % self.phase)
-        coco_eval = COCOeval(coco, coco.loadRes(res_file), "keypoints")
-        coco_eval.params.useSegm = None
-        coco_eval.evaluate()
-        coco_eval.accumulate()
-        coco_eval.summarize()
-        return coco_eval.stats[0]
+        """dataset.py:48-66: AP of ``<loadDir>/<phase>_results.json`` against the generated ground-truth file."""
+        stats = self._keval().evaluate(os.path.join(loadDir, "%s_results.json" % self.phase))
+        self._print_stats(stats)
+        return stats[0]
 
     def evaluateEach(self, loadDir):
-        coco, COCOeval = self._coco_tools()
+        """dataset.py:68-88: the same with the similarity restricted to one joint at a time; returns the last joint's AP like the
+        reference does."""
         res_file = os.path.join(loadDir, "%s_results.json" % self.phase)
-        coco_eval = COCOeval(coco, coco.loadRes(res_file), "keypoints")
-        coco_eval.params.useSegm = None
-        per_joint = []
-        for i in range(self.numKeypoints):
-            coco_eval.evaluate(i)
-            coco_eval.accumulate()
-            coco_eval.summarize()
-            per_joint.append(coco_eval.stats[0])
+        per_joint = [self._keval().evaluate(res_file, idx_keypoint=i)[0] for i in range(self.numKeypoints)]
         for name, ap in zip(self.idxToJoints, per_joint):
             print("%s: %.3f" % (name, ap))
         return per_joint[-1]
+
+    def evaluatePoses(self, imageIds, pred_xy, idx_keypoint=-1):
+        """Evaluation tail without the results file: ``pred_xy`` ``[n, 14, 2]`` image-pixel poses (a CUDA tensor
+        stays on the device: hupr_keypoint_oks) for the images ``imageIds``; images of the split without a pose count as missed."""
+        ev = self._keval()
+        order = [ev.index[int(i)] for i in imageIds]
+        if len(set(order)) != len(order):
+            raise ValueError("evaluatePoses: one pose per image")
+        n = len(ev.image_ids)
+        has = np.zeros(n, dtype=bool)
+        has[order] = True
+        if isinstance(pred_xy, torch.Tensor):
+            full = torch.zeros((n,) + tuple(pred_xy.shape[1:]), dtype=torch.float32, device=pred_xy.device)
+            full[torch.as_tensor(order, device=pred_xy.device)] = pred_xy.float()
+        else:
+            full = np.zeros((n,) + tuple(np.shape(pred_xy)[1:]))
+            full[order] = np.asarray(pred_xy)
+        return ev.evaluate_arrays(full, has, idx_keypoint)

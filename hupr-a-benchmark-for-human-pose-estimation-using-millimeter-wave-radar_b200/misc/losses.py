@@ -52,7 +52,8 @@ class LossComputer(object):
         if (self.numKeypoints, self.heatmapSize, self.imgSize) != (14, 64, 256):
             raise ValueError("hupr_b200 loss kernels are specialised for 14 keypoints, 64x64 heatmaps, 256-px frames")
 
-    def computeLoss(self, preds, gt):
+    def computeLoss(self, preds, gt, host=True):
+        """losses.py:23-45.  ``host=False`` returns pred2d / gt2d as CUDA tensors (no synchronising read-back; the evaluation loop uses it)."""
         heat, gcn = preds
         b = gt.size(0)
         heat = heat.reshape(b, self.numKeypoints, self.height, self.width).contiguous()
@@ -66,4 +67,6 @@ class LossComputer(object):
             loss = self.alpha * losses[2] + self.beta * losses[1]
         else:
             loss = losses[0]
+        if not host:
+            return loss, losses[1], pred2d, gt2d
         return loss, losses[1], pred2d.cpu().numpy(), gt2d.cpu().numpy()

@@ -11,8 +11,16 @@ Differences that matter to a user switching over:
     dtype, values are the complex64 results widened);
   * the GPU path consumes the DCA1000 int16 words directly (``cascade_i16``): 4x fewer bytes over PCIe
     than a complex64 frame, and the de-interleave is fused into the kernel's load stage;
-  * there is no CPU fallback — a missing ``libhupr_b200.so`` or a non-B200 device raises RuntimeError.
+  * there is no CPU fallback — a missing ``libhupr_b200.so`` or a non-B200 device raises RuntimeError;
+  * ``processRadarDataHoriVert`` is a three-stage pipeline: the capture file is read through a memory map into
+    PINNED staging buffers, uploaded on a copy stream while the previous chunk is in the cascade, and the results return through pinned
+    buffers on a third stream while a writer thread saves the files of the chunk before;
+  * ``cacheFormat='planes'`` stores what the loader actually consumes — the 8 kept Doppler rows, real and imaginary
+    parts standardised per (row, part, elevation) plane, float32 ``[8,2,64,64,8]`` = 2 MiB per frame instead of the 8 MiB complex128
+    cube — computed by the same kernel the loader would run (``hupr_window_normalize``), so a loader item built from either cache is
+    bit-identical; ``hupr_b200.datasets.cubecache.convert`` converts an existing cube cache.
 """
+import concurrent.futures
 import os
 
 import numpy as np
@@ -63,7 +71,10 @@ def frames_to_dca1000(frames):
 
 class RadarObject(object):
     def __init__(self, numGroup=276, root='HuPR', saveRoot='HuPR', device='cuda', cubeDtype=np.complex128,
-                 framesPerLaunch=64):
+                 framesPerLaunch=64, cacheFormat='cube'):
+        if cacheFormat not in ('cube', 'planes'):
+            raise ValueError("cacheFormat must be 'cube' (reference .npy cubes) or 'planes' (compact standardised planes)")
+        self.cacheFormat = cacheFormat
         self.root = root
         self.saveRoot = saveRoot
         self.sensorType = 'iwr1843'
@@ -115,18 +126,77 @@ class RadarObject(object):
     def saveRadarData(self, matrix, dirName, idxFrame):
         np.save(dirName + ('/%09d' % idxFrame) + '.npy', matrix)
 
+    # ---- f-3: pipelined ingest of one capture file ----------------------------------------------
+    def _stage_buffers(self):
+        L, dev = self.framesPerLaunch, self.device
+        planes = self.cacheFormat == 'planes'
+        out_shape = (L, 8, 2, 64, 64, 8) if planes else (L,) + CUBE_SHAPE
+        out_dtype = torch.float32 if planes else torch.complex64
+        return {"h_in": torch.empty((L, FRAME_WORDS), dtype=torch.int16).pin_memory(),
+                "d_in": torch.empty((L, FRAME_WORDS), dtype=torch.int16, device=dev),
+                "d_cube": torch.empty((L,) + CUBE_SHAPE, dtype=torch.complex64, device=dev),
+                "d_out": torch.empty(out_shape, dtype=out_dtype, device=dev) if planes else None,
+                "h_out": torch.empty(out_shape, dtype=out_dtype).pin_memory(),
+                "slots": torch.arange(L, dtype=torch.int32, device=dev),
+                "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "returned": torch.cuda.Event(), "pending": None}
+
+    def _save_chunk(self, stage, n, saveDir, f0):
+        stage["returned"].synchronize()
+        host = stage["h_out"][:n].numpy()
+        for k in range(n):
+            frame = host[k] if self.cacheFormat == 'planes' else host[k].astype(self.cubeDtype, copy=False)
+            self.saveRadarData(frame, saveDir, f0 + k)
+
+    def processCapture(self, words, saveDir, nFrames=None):
+        """int16 words of one capture (ndarray or np.memmap, ``nFrames * FRAME_WORDS`` long) -> ``<saveDir>/%09d.npy`` per frame.
+        Upload (copy stream), cascade (+ standardisation for the planes cache), read-back (third stream) and file writing (thread) of
+        consecutive chunks overlap; two stages of pinned / device buffers are re-used for the whole capture."""
+        from .. import ops
+        words = np.asarray(words) if not isinstance(words, np.memmap) else words
+        total = words.size // FRAME_WORDS if nFrames is None else nFrames
+        words = words[:total * FRAME_WORDS].reshape(total, FRAME_WORDS)
+        if not hasattr(self, "_stages"):
+            with torch.cuda.device(self.device):
+                self._stages = [self._stage_buffers(), self._stage_buffers()]
+                self._copy_in, self._copy_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+                self._writer = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        L = self.framesPerLaunch
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            for c, f0 in enumerate(range(0, total, L)):
+                st = self._stages[c & 1]
+                n = min(L, total - f0)
+                if st["pending"] is not None:
+                    st["pending"].result()                       # the files of this stage's previous chunk are on disk: buffers are free
+                np.copyto(st["h_in"][:n].numpy(), words[f0:f0 + n])
+                with torch.cuda.stream(self._copy_in):
+                    st["d_in"][:n].copy_(st["h_in"][:n], non_blocking=True)
+                    st["uploaded"].record(self._copy_in)
+                main.wait_event(st["uploaded"])
+                cascade_i16(st["d_in"][:n], st["d_cube"][:n])
+                if self.cacheFormat == 'planes':
+                    ops.window_normalize(st["d_cube"], st["slots"][:n], st["d_out"][:n])
+                st["computed"].record(main)
+                with torch.cuda.stream(self._copy_out):
+                    self._copy_out.wait_event(st["computed"])
+                    src = st["d_out"] if self.cacheFormat == 'planes' else st["d_cube"]
+                    st["h_out"][:n].copy_(src[:n], non_blocking=True)
+                    st["returned"].record(self._copy_out)
+                st["pending"] = self._writer.submit(self._save_chunk, st, n, saveDir, f0)
+            for st in self._stages:
+                if st["pending"] is not None:
+                    st["pending"].result()
+                    st["pending"] = None
+        return total
+
     def processRadarDataHoriVert(self):
         """Process every capture directory; file naming identical to the reference (:184-196)."""
         for names, saveDir in zip(self.radarDataFileNameGroup, self.saveDirNameGroup):
             for sensorDir, sub in zip(names, ('hori', 'vert')):
-                words = self.readDCA1000Words(sensorDir)
+                words = np.memmap(os.path.join(sensorDir, 'adc_data.bin'), dtype=np.int16, mode='r')
                 nFrames = min(self.numFrame, words.size // FRAME_WORDS)
-                words = words[:nFrames * FRAME_WORDS].reshape(nFrames, FRAME_WORDS)
-                for f0 in range(0, nFrames, self.framesPerLaunch):
-                    cubes = self.generateHeatmapBatch(words[f0:f0 + self.framesPerLaunch]).cpu().numpy()
-                    for k in range(cubes.shape[0]):
-                        self.saveRadarData(cubes[k].astype(self.cubeDtype, copy=False),
-                                           saveDir + '/' + sub, f0 + k)
+                os.makedirs(saveDir + '/' + sub, exist_ok=True)
+                self.processCapture(words, saveDir + '/' + sub, nFrames)
                 print('%s, finished %d frames' % (sensorDir, nFrames), end='\r')
 
 

@@ -153,24 +153,33 @@ class Runner(object):
 
     # ---------------------------------------------------------------------------------------------- loops
     def eval(self, visualization=False, epoch=-1):
+        """run.py:35-63.  The per-batch keypoints stay on the device (no synchronising read-back inside the loop); the results file
+        the reference writes is produced from ONE transfer after the loop, and AP comes from the device-resident poses
+        (``evaluatePoses`` -> hupr_keypoint_oks) — identical to evaluating the file (tests/test_runner_gpu.py)."""
         self.model.eval()
-        savePreds, losses = [], []
+        poses, boxes, ids, losses = [], [], [], []
         for batch in self.testLoader:
             hori = batch["VRDAEmap_hori"].float().to(self.device)
             vert = batch["VRDAEmap_vert"].float().to(self.device)
             preds = self.model(hori, vert)
-            loss, loss2, pred2d, _ = self.lossComputer.computeLoss(preds, batch["jointsGroup"])
-            self.saveKeypoints(savePreds, pred2d * self.imgHeatmapRatio, batch["bbox"], batch["imageId"])
-            losses.append(float(loss))
+            loss, loss2, pred2d, _ = self.lossComputer.computeLoss(preds, batch["jointsGroup"], host=False)
+            poses.append(pred2d.float() * self.imgHeatmapRatio)
+            boxes.append(torch.as_tensor(batch["bbox"]).float())
+            ids.extend(int(i) for i in batch["imageId"])
+            losses.append(loss.detach().reshape(1) if isinstance(loss, torch.Tensor) else torch.tensor([float(loss)]))
+        savePreds = []
+        if poses:
+            poses_dev = torch.cat(poses)
+            self.saveKeypoints(savePreds, poses_dev.cpu().numpy(), torch.cat(boxes).numpy(), ids)
         self.writeKeypoints(savePreds)
-        self.last_eval_loss = float(np.mean(losses)) if losses else float("nan")
-        try:
-            if getattr(self.args, "keypoints", False):
-                self.testSet.evaluateEach(self.dir)
-            return self.testSet.evaluate(self.dir)
-        except RuntimeError as exc:
-            print("==========>%s" % exc)
+        self.last_eval_loss = float(torch.cat([l.float().cpu() for l in losses]).mean()) if losses else float("nan")
+        if not poses:
             return float("nan")
+        if getattr(self.args, "keypoints", False):
+            self.testSet.evaluateEach(self.dir)
+        stats = self.testSet.evaluatePoses(ids, poses_dev)
+        self.testSet._print_stats(stats)
+        return float(stats[0])
 
     def train(self):
         for epoch in range(self.start_epoch, self.cfg.TRAINING.epochs):

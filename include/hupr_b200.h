@@ -182,6 +182,15 @@ int hupr_gcn_heads(const float* y, int y_ld, float* gcn_heatmap, int batch, void
  * maps: float [n_maps][64*64] -> preds float [n_maps][2] = (x, y) of the first maximum, zeroed where max <= 0; maxvals may be NULL. */
 int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds, float* maxvals, void* stream);
 
+/* Evaluation tail on the device.  Object keypoint similarity of one predicted pose against the one ground-truth
+ * pose of its image — COCOeval.computeOks of the reference's vendored evaluator (/root/reference/misc/cocoeval.py:192-236) with all k
+ * joints labelled visible, as /root/reference/datasets/base.py:60 writes them:
+ *   oks[i] = mean_j exp(-((dx^2 + dy^2) / (2 sigma_j)^2 / (area[i] + eps) / 2)),  eps = np.spacing(1); float64 like the original.
+ * pred, gt: float [n][k][2] image-pixel (x, y); area, sigmas: double; per_joint (optional): double [n][k] = the k exponentials
+ * (per-joint evaluation, cocoeval.py:232-233). */
+int hupr_keypoint_oks(const float* pred, const float* gt, const double* area, const double* sigmas, int n, int k, double* oks,
+                      double* per_joint, void* stream);
+
 /* Heatmap loss.  Replaces LossComputer.computeLoss + generateTarget
  *   /root/reference/misc/losses.py:23-48, /root/reference/misc/utils.py:6-65
  * heatmap, gcn_heatmap: float [batch][14][64][64] (post-sigmoid); joints: int64 [batch][14][2] image pixels (256-px frame)

@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the UNMODIFIED reference (build container only).
 
-    python -m oracle.make_golden [cascade|dca|loader|model|loss|all]
+    python -m oracle.make_golden [cascade|dca|loader|model|loss|cocoeval|all]
 
 The fixtures pin the oracle restatements (oracle/*.py) to the reference's own code; they are small
 (strided samples + float64 checksums) so they can live in git.  /root/reference is needed to run this
@@ -131,7 +131,75 @@ def make_loader():
     print("loader", out.shape, np.isfinite(out).all())
 
 
-TARGETS = {"cascade": make_cascade, "dca": make_dca, "model": make_model, "loss": make_loss, "loader": make_loader}
+
+def synth_keypoint_eval_case(seed, n_images=60, k=14):
+    """Seeded COCO-format ground truth + results in the shape HuPR writes them (datasets/base.py:26-92, tools/base.py:124-147): one
+    pose per image, integer joints in a 256x256 frame, all joints visible, area = bbox area / 2; results = the ground truth displaced by
+    noise whose scale varies per image (so the similarities straddle every IoU threshold), boxes spanning all three area ranges, a few
+    images without a prediction."""
+    rng = np.random.default_rng(seed)
+    gt = {"images": [], "annotations": [], "categories": [{"supercategory": "person", "id": 1, "name": "person",
+                                                           "keypoints": ["j%d" % j for j in range(k)], "skeleton": []}]}
+    results = []
+    for i in range(n_images):
+        image_id = 100000 * (1 + i // 25) + (i % 25)
+        size = float(rng.choice([20, 40, 70, 110, 160]))                    # bbox side: areas/2 of 200 .. 12 800 px^2
+        x0, y0 = rng.uniform(0, 256 - size, 2)
+        joints = np.rint(np.stack([rng.uniform(x0, x0 + size, k), rng.uniform(y0, y0 + size, k)], axis=1))
+        kp = np.concatenate([joints, np.full((k, 1), 2.0)], axis=1).reshape(-1).tolist()
+        gt["images"].append({"id": image_id, "height": 256, "width": 256, "file_name": "%09d.jpg" % image_id})
+        gt["annotations"].append({"num_keypoints": k, "area": size * size / 2, "iscrowd": 0, "keypoints": kp, "image_id": image_id,
+                                  "bbox": [float(x0), float(y0), size, size], "category_id": 1, "id": image_id})
+        if rng.uniform() < 0.08:
+            continue                                                          # no prediction for this image
+        noise = rng.choice([0.0, 1.0, 3.0, 6.0, 12.0]) * size / 64.0
+        pred = np.float32(joints + rng.normal(0, 1, (k, 2)) * noise)          # float32 like pred2d * imgHeatmapRatio
+        res_kp = np.concatenate([pred.astype(np.float64), np.ones((k, 1))], axis=1).reshape(-1).tolist()
+        results.append({"category_id": 1, "image_id": image_id, "score": 1.0, "keypoints": res_kp})
+    return gt, results
+
+
+def make_cocoeval():
+    """Reference vendored COCOeval (misc/coco.py, misc/cocoeval.py) on seeded HuPR-shaped files: the 10 summary statistics, overall
+    and for every single joint (``evaluate(idx_keypoint)``, as datasets/dataset.py:68-88 drives it)."""
+    import contextlib
+    import io
+    import json
+    COCO, COCOeval = ref_shim.load_cocoeval()
+    out = {}
+    for seed in (0, 1):
+        gt, results = synth_keypoint_eval_case(seed)
+        with tempfile.TemporaryDirectory() as tmp:
+            gt_path, res_path = os.path.join(tmp, "gt.json"), os.path.join(tmp, "res.json")
+            with open(gt_path, "w") as fp:
+                json.dump(gt, fp)
+            with open(res_path, "w") as fp:
+                json.dump(results, fp)
+            with contextlib.redirect_stdout(io.StringIO()):
+                coco = COCO(gt_path)
+                ev = COCOeval(coco, coco.loadRes(res_path), "keypoints")
+                ev.params.useSegm = None
+                ev.evaluate()
+                ev.accumulate()
+                ev.summarize()
+                stats = np.array(ev.stats)
+                per_joint = []
+                for j in range(14):
+                    ev.evaluate(j)
+                    ev.accumulate()
+                    ev.summarize()
+                    per_joint.append(np.array(ev.stats))
+                oks_ref = np.array([float(ev.computeOks(a["image_id"], 1)[0][0]) if len(ev.computeOks(a["image_id"], 1)) else np.nan
+                                    for a in sorted(gt["annotations"], key=lambda a: a["image_id"])])
+        out["seed%d_stats" % seed] = stats
+        out["seed%d_per_joint_stats" % seed] = np.stack(per_joint)
+        out["seed%d_oks" % seed] = oks_ref
+        print("cocoeval seed", seed, "stats", np.round(stats, 4))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "cocoeval_reference.npz"), **out)
+
+
+TARGETS = {"cascade": make_cascade, "dca": make_dca, "model": make_model, "loss": make_loss, "loader": make_loader,
+           "cocoeval": make_cocoeval}
 
 
 def main(argv):

@@ -100,3 +100,20 @@ def load_normalize():
     _install_model_stubs()
     from datasets.base import Normalize
     return Normalize
+
+
+def load_cocoeval():
+    """Return the reference's vendored (COCO, COCOeval) classes (misc/coco.py, misc/cocoeval.py — the files the reference's README
+    copies over pycocotools).  Shims: ``misc.mask`` (compiled RLE helpers, unused for keypoints), matplotlib submodules, ``np.float``."""
+    import importlib
+    import numpy as np
+    _install_model_stubs()
+    _stub("matplotlib.collections", PatchCollection=object)
+    _stub("matplotlib.patches", Polygon=object)
+    _stub("misc.mask")
+    if not hasattr(np, "float"):
+        np.float = float
+    import misc  # noqa: F401  (package from /root/reference)
+    coco = importlib.import_module("misc.coco")
+    cocoeval = importlib.import_module("misc.cocoeval")
+    return coco.COCO, cocoeval.COCOeval

@@ -59,5 +59,10 @@ def test_runner_trains_evaluates_and_resumes(tmp_path, monkeypatch):
     eval_args = types.SimpleNamespace(seed=0, dir="run", visDir="none", gpuIDs=[0], eval=True, sampling_ratio=1, keypoints=False)
     ev = Runner(eval_args, eval_cfg)
     ev.loadModelWeight("checkpoint")
-    ev.eval()
+    ap = ev.eval()
     assert len(json.load(open("logs/run/test_results.json"))) == 4
+    # AP from the device-resident poses (hupr_keypoint_oks) == AP of the written results file through the host evaluator, and the
+    # per-joint variant runs; a random-init network scores ~0 but the statistic is a finite number in [0, 1]
+    assert 0.0 <= ap <= 1.0
+    assert ev.testSet.evaluate("logs/run") == pytest.approx(ap, abs=1e-12)
+    assert 0.0 <= ev.testSet.evaluateEach("logs/run") <= 1.0

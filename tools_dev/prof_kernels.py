@@ -29,5 +29,12 @@ if which in ("attn", "all"):
     out = SplitTensor.empty((b, 1, 1, s, 4 * c), "cuda")
     for _ in range(3):
         ops.attention_fwd(pq, c, pq, 0, vt, c, out, 0, residual=v)
+if which in ("wgrad", "all"):
+    # three template instantiations on training-step shapes: BN = 64 / 128 (level 1, W = 64) and BN = 256 (level 2)
+    for cin, cout, d, h, w in ((64, 64, 8, 64, 64), (64, 128, 8, 64, 64), (128, 256, 4, 32, 32)):
+        x = SplitTensor.from_float(torch.randn(b, d, h, w, cin, device="cuda"))
+        dy = SplitTensor.from_float(torch.randn(b, d, h, w, cout, device="cuda"))
+        out = torch.zeros((27, cin, cout), device="cuda")
+        ops.conv_wgrad_direct(x, 0, cin, dy, 0, cout, (3, 3, 3), (1, 1, 1), out=out)
 torch.cuda.synchronize()
 print("done")
