@@ -28,6 +28,7 @@ class ConvDesc(ctypes.Structure):
         ("w_ld", ctypes.c_int), ("w_ch_off", ctypes.c_int),
         ("a_n_stride", ctypes.c_longlong),
         ("k_split", ctypes.c_int), ("w_k_off", ctypes.c_int),
+        ("row_vec", ctypes.c_void_p), ("row_mode", ctypes.c_int),
     ]
 
 
@@ -40,6 +41,7 @@ class AttnDesc(ctypes.Structure):
         ("r_hi", ctypes.c_void_p), ("r_lo", ctypes.c_void_p), ("r_ld", ctypes.c_int), ("r_off", ctypes.c_int),
         ("o_hi", ctypes.c_void_p), ("o_lo", ctypes.c_void_p), ("o_ld", ctypes.c_int), ("o_off", ctypes.c_int),
         ("batch", ctypes.c_int), ("s", ctypes.c_int), ("c", ctypes.c_int),
+        ("lse", ctypes.c_void_p),
     ]
 
 
@@ -94,6 +96,7 @@ SIGNATURES = {
     "hupr_affine_act": (ctypes.c_int, [_TV, _P, _P, _TV, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_bn_bwd_apply": (ctypes.c_int, [_TV, _TV, _TV, _P, _P, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_act_bwd": (ctypes.c_int, [_TV, _TV, _P, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_rowdot": (ctypes.c_int, [_TV, _TV, _TV, _P, ctypes.c_longlong, _I, _P]),
     "hupr_accumulate": (ctypes.c_int, [_TV, _TV, _P, _I, _I, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_resample_linear_bwd": (ctypes.c_int, [_TV, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "hupr_softmax_bwd_rows": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _P]),

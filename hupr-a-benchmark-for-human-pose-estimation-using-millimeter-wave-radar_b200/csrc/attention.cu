@@ -56,6 +56,7 @@ struct AttnParams {
     const __nv_bfloat16* r_hi; const __nv_bfloat16* r_lo; int r_ld, r_off;
     __nv_bfloat16* o_hi; __nv_bfloat16* o_lo; int o_ld, o_off;
     int s;
+    float* lse;                   // optional [batch][s]: log sum_m exp(logit[n, m]) per query row (saved for the backward pass)
 };
 
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -314,10 +315,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const uint32_t lslot = xch + (uint32_t)(((p.nkv & 1) * 2) * 128 * 4);
         sts_f32(lslot + (uint32_t)((half * 128 + row) * 4), l_run);
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float inv = 1.0f / (l_run + lds_f32(lslot + (uint32_t)(((half ^ 1) * 128 + row) * 4)));
+        const float l_tot = l_run + lds_f32(lslot + (uint32_t)(((half ^ 1) * 128 + row) * 4));
+        const float inv = 1.0f / l_tot;
         mbar_wait(pv_done, (uint32_t)((p.nkv - 1) & 1));
         tc_fence_after();
         const size_t pos = (size_t)b * p.s + q0 + row;
+        if (p.lse && half == 0) p.lse[pos] = m_run + __logf(l_tot);
 #pragma unroll 1
         for (int c = 0; c < OC / 32; ++c) {
             uint32_t v[32];
@@ -381,6 +384,7 @@ static int launch_attention(const hupr_attn_desc* d, cudaStream_t stream) {
     p.r_hi = (const __nv_bfloat16*)d->r_hi; p.r_lo = (const __nv_bfloat16*)d->r_lo; p.r_ld = d->r_ld; p.r_off = d->r_off;
     p.o_hi = (__nv_bfloat16*)d->o_hi; p.o_lo = (__nv_bfloat16*)d->o_lo; p.o_ld = d->o_ld; p.o_off = d->o_off;
     p.s = d->s;
+    p.lse = d->lse;
     const dim3 grid(d->s / AT_BM, d->batch);
     attention_kernel<D, BKV><<<grid, AT_THREADS, AT_SMEM, stream>>>(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p);
     note_launches(1);

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "split.cuh"
 
 namespace hupr {
 
@@ -27,6 +28,8 @@ struct ConvParams {
     int w_k_off;                   // added to the B operand's contracted-axis coordinate (shifted correlation; out of range = zero fill)
     int kb_per_split, k_split, atomic;
     int m_tiles, n_tiles;          // 128-position tiles x BN-column tiles (x k_split slices), walked persistently
+    const float* row_vec;          // per-position vector (row_mode 1: exp(acc - v), 2: r * (acc - v))
+    int row_mode;
 };
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos`.
@@ -39,7 +42,29 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
         const float sh = p.shift ? __ldg(p.shift + ch0 + j) : 0.0f;
         v[j] = fmaf(x, sc, sh);
     }
-    if (p.r_hi) {
+    if (p.row_mode) {
+        const float rv = __ldg(p.row_vec + pos);
+        if (p.row_mode == 1) {
+            const float kLog2e = 1.4426950408889634f;
+            const float nr = -rv * kLog2e;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[j]) : "f"(fmaf(v[j], kLog2e, nr)));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] -= rv;
+        }
+    }
+    if (p.r_hi && p.row_mode == 2) {          // multiplicative operand: out = r * (acc - row_vec)
+        const __nv_bfloat16* rh = p.r_hi + pos * p.r_ld + p.r_ch_off + ch0;
+        const __nv_bfloat16* rl = p.r_lo ? p.r_lo + pos * p.r_ld + p.r_ch_off + ch0 : nullptr;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float r8[8];
+            load8(rh + g * 8, rl ? rl + g * 8 : nullptr, r8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[g * 8 + e] *= r8[e];
+        }
+    } else if (p.r_hi) {
         const uint4* rh = reinterpret_cast<const uint4*>(p.r_hi + pos * p.r_ld + p.r_ch_off + ch0);
         const uint4* rl = p.r_lo ? reinterpret_cast<const uint4*>(p.r_lo + pos * p.r_ld + p.r_ch_off + ch0) : nullptr;
 #pragma unroll
@@ -83,13 +108,7 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
     if (p.o_hi) {
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const __nv_bfloat16 h0b = __float2bfloat16_rn(v[2 * j]), h1b = __float2bfloat16_rn(v[2 * j + 1]);
-            const __nv_bfloat16 l0b = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0b));
-            const __nv_bfloat16 l1b = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1b));
-            hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-            lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
-        }
+        for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);      // same roundings, one cvt.rn.bf16x2 per plane
         uint4* dh = reinterpret_cast<uint4*>(p.o_hi + pos * p.o_ld + p.o_ch_off + ch0);
 #pragma unroll
         for (int g = 0; g < 4; ++g) dh[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);

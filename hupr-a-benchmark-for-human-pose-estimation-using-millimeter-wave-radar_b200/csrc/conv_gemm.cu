@@ -296,6 +296,8 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     p.o_hi = (__nv_bfloat16*)d->o_hi; p.o_lo = (__nv_bfloat16*)d->o_lo; p.o_ld = d->o_ld; p.o_ch_off = d->o_ch_off;
     p.o_f32 = d->o_f32; p.o_f32_ld = d->o_f32_ld;
     p.w_k_off = d->w_k_off;
+    p.row_vec = d->row_vec; p.row_mode = d->row_vec ? d->row_mode : 0;
+    if (p.row_mode < 0 || p.row_mode > 2 || (p.row_mode && (d->scale || d->shift || d->slope || !d->o_hi)) || (p.row_mode == 2 && !d->r_hi)) return HUPR_ERR_BAD_ARG;
     {   // split-K (wgrad-style contractions: few output tiles, very long K): partial sums are added atomically into o_f32
         const int total_kb = taps * p.cin_blocks;
         int ks = d->k_split > 1 ? d->k_split : 1;

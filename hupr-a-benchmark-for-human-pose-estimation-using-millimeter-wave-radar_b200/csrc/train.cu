@@ -194,6 +194,30 @@ accumulate_kernel(TView a, TView b, const float* __restrict__ f, int f_ld, int f
     }
 }
 
+// out[pos] = sum_ch a[pos][ch] * (b[pos][ch] - c[pos][ch]); one warp per position, c multiple of 8 (c.hi may be null).
+__global__ void __launch_bounds__(256)
+rowdot_kernel(TView a, TView b, TView c, float* __restrict__ out, long long positions, int cn) {
+    const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= positions) return;
+    float acc = 0.f;
+    for (int g = lane; g < (cn >> 3); g += 32) {
+        float x[8], y[8], z[8];
+        tv_load8(a, (size_t)warp, g * 8, x);
+        tv_load8(b, (size_t)warp, g * 8, y);
+        if (c.hi) {
+            tv_load8(c, (size_t)warp, g * 8, z);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] -= z[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(x[i], y[i], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[warp] = acc;
+}
+
 struct ResampleBwdParams {
     int n, di, hi, wi, dout, ho, wo, c8;
     int g_ld, g_off, o_ld, o_off;
@@ -386,6 +410,19 @@ extern "C" int hupr_accumulate(const hupr_tensor_view* a, const hupr_tensor_view
     if (rc != HUPR_OK) return rc;
     accumulate_kernel<<<ew_blocks(positions * (c / 8)), 256, 0, (cudaStream_t)stream>>>(mk_view(a && a->hi ? a : nullptr), mk_view(b && b->hi ? b : nullptr),
                                                                                         f, f_ld, f_off, mk_out(out), positions, c);
+    return finish(1);
+}
+
+extern "C" int hupr_rowdot(const hupr_tensor_view* a, const hupr_tensor_view* b, const hupr_tensor_view* c, float* out, long long positions,
+                           int c_n, void* stream) {
+    if (positions < 0 || c_n <= 0 || c_n % 8 || !out) return HUPR_ERR_BAD_ARG;
+    if (positions == 0) return HUPR_OK;
+    if (!view_ok(a, c_n, true) || !view_ok(b, c_n, true) || !view_ok(c, c_n, false)) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    const long long blocks = (positions + 7) / 8;
+    if (blocks > 2147483647LL) return HUPR_ERR_BAD_ARG;
+    rowdot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mk_view(a), mk_view(b), mk_view(c && c->hi ? c : nullptr), out, positions, c_n);
     return finish(1);
 }
 

@@ -71,7 +71,7 @@ class SplitTensor(object):
 
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -91,6 +91,8 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.w_batched = 1 if w_batched else 0
     desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
     desc.k_split, desc.w_k_off = k_split, w_k_off
+    if row_vec is not None:          # per-position vector: 1 = exp(acc - v), 2 = residual * (acc - v)  (attention backward)
+        desc.row_vec, desc.row_mode = row_vec.data_ptr(), row_mode
     if a.hi.stride(0) != d * h * w * ca:        # overlapping sliding-window view over a frame stream
         if tuple(a.hi.stride()[1:]) != (h * w * ca, w * ca, ca, 1) or (a.lo is not None and a.lo.stride() != a.hi.stride()):
             raise ValueError("conv_gemm: only the sample stride of A may be non-dense")
@@ -112,7 +114,7 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     return out if out is not None else out_f32
 
 
-def attention_fwd(q, q_off, k, k_off, vt, c, out, o_off, residual=None, r_off=0):
+def attention_fwd(q, q_off, k, k_off, vt, c, out, o_off, residual=None, r_off=0, lse=None):
     """Fused attention (hupr_attention_fwd): q, k SplitTensors ``[B, .., S, ld]``, vt ``[B, c, S]``, out ``[B, .., S, ld_o]``."""
     b = q.hi.shape[0]
     s = vt.hi.shape[-1]
@@ -124,6 +126,7 @@ def attention_fwd(q, q_off, k, k_off, vt, c, out, o_off, residual=None, r_off=0)
         desc.r_hi, desc.r_lo, desc.r_ld, desc.r_off = residual.hi.data_ptr(), _C.optr(residual.lo), residual.hi.shape[-1], r_off
     desc.o_hi, desc.o_lo, desc.o_ld, desc.o_off = out.hi.data_ptr(), _C.optr(out.lo), out.hi.shape[-1], o_off
     desc.batch, desc.s, desc.c = b, s, c
+    desc.lse = _C.optr(lse)          # float32 [b, s]: log-sum-exp of every query row (training saves it for the backward)
     with torch.cuda.device(q.hi.device), _timed("attention_fwd", 4.0 * b * s * s * c):
         _C.check(_C.lib().hupr_attention_fwd(desc, _C.stream_ptr()), "hupr_attention_fwd")
     return out

@@ -56,6 +56,13 @@ def accumulate(out, c, a=None, b=None, f=None, f_off=0):
         _call("hupr_accumulate", _view(a), _view(b), _p(f), 0 if f is None else f.shape[-1], f_off, _view(out), _positions(out), c, _C.stream_ptr())
 
 
+def rowdot(a, b, c_n, out, sub=None):
+    """out[pos] = sum_ch a[pos, ch] * (b[pos, ch] - sub[pos, ch]) (hupr_rowdot); a, b, sub are views, out float32 [positions]."""
+    with torch.cuda.device(_dev(a)):
+        _call("hupr_rowdot", _view(a), _view(b), _view(sub), _p(out), _positions(a), c_n, _C.stream_ptr())
+    return out
+
+
 def resample_linear_bwd(g, c, din, in_ch_off=0):
     """g: view of the forward OUTPUT gradient [n, do, ho, wo, ld]; din: float32 [n, di, hi, wi, ld_in] (+=, zero-filled by the caller)."""
     t = g if isinstance(g, SplitTensor) else g[0]

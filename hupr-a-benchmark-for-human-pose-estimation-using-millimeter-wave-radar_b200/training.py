@@ -243,11 +243,16 @@ class AttentionLevel(object):
         for key, x in (("ra", self.ra), ("re", self.re)):
             self.vt[key] = ops.transpose_split(x, c, _S((b, c, s), dev))
         cat_s = _rows(cat)
+        self.cat_s = cat_s
+        self.lse = []                # per attention: float32 [b, s] log-sum-exp of the logit rows (fused forward only), else None
         v = {"ra": self.ra, "re": self.re}
         for qs, qo, ks, ko, vs, oo, res in self._plan():
             if c in (64, 128):
-                ops.attention_fwd(self.pr[qs], qo, self.pr[ks], ko, self.vt[vs], c, cat_s, oo, residual=v[vs] if res else None)
+                lse = torch.empty((b, s), dtype=torch.float32, device=dev)
+                ops.attention_fwd(self.pr[qs], qo, self.pr[ks], ko, self.vt[vs], c, cat_s, oo, residual=v[vs] if res else None, lse=lse)
+                self.lse.append(lse)
             else:
+                self.lse.append(None)
                 logits = torch.empty((b, 1, 1, s, s), dtype=torch.float32, device=dev)
                 kview = SplitTensor(self.pr[ks].hi.view(b, s, 4 * c), self.pr[ks].lo.view(b, s, 4 * c))
                 ops.conv_gemm(self.pr[qs], c, kview, s, a_ch_off=qo, w_batched=True, w_ld=4 * c, w_ch_off=ko, out_f32=logits)
@@ -266,15 +271,24 @@ class AttentionLevel(object):
         # contract over the query axis with MN-major tensor-core operands (ops.matmul_tn): no transposed [S, S] copies
         dvf = {"ra": torch.zeros((b, s, c), dtype=torch.float32, device=dev), "re": torch.zeros((b, s, c), dtype=torch.float32, device=dev)}
         dv_res = {}
-        for qs, qo, ks, ko, vs, oo, res in self._plan():
-            scratch = torch.empty((b, 1, 1, s, s), dtype=torch.float32, device=dev)
+        for idx, (qs, qo, ks, ko, vs, oo, res) in enumerate(self._plan()):
             kview = SplitTensor(self.pr[ks].hi.view(b, s, 4 * c), self.pr[ks].lo.view(b, s, 4 * c))
-            ops.conv_gemm(self.pr[qs], c, kview, s, a_ch_off=qo, w_batched=True, w_ld=4 * c, w_ch_off=ko, out_f32=scratch)
-            probs = ops.softmax_rows(scratch, _S((b, 1, 1, s, s), dev))
             vview = SplitTensor(v[vs].hi.view(b, s, c), v[vs].lo.view(b, s, c))
-            ops.conv_gemm(dcat_s, c, vview, s, a_ch_off=oo, w_batched=True, out_f32=scratch)                       # dP = dO V^T
-            dsm = _S((b, 1, 1, s, s), dev)
-            T.softmax_bwd_rows(probs, scratch, dsm)
+            probs, dsm = _S((b, 1, 1, s, s), dev), _S((b, 1, 1, s, s), dev)
+            if self.lse[idx] is not None:
+                # P = exp(logits - lse) in the epilogue of the logits GEMM; dS = P * (dP - rowdot) in the epilogue of the dP GEMM, with
+                # rowdot = sum_m P dP = <dO, P V> = <dO, O - residual> computed from the forward output: no fp32 [S, S] round trips
+                ops.conv_gemm(self.pr[qs], c, kview, s, a_ch_off=qo, w_batched=True, w_ld=4 * c, w_ch_off=ko, out=probs,
+                              row_vec=self.lse[idx], row_mode=1)
+                rowdot = T.rowdot((dcat_s, oo), (self.cat_s, oo), c, torch.empty((b, s), dtype=torch.float32, device=dev),
+                                  sub=v[vs] if res else None)
+                ops.conv_gemm(dcat_s, c, vview, s, a_ch_off=oo, w_batched=True, out=dsm, residual=probs, row_vec=rowdot, row_mode=2)
+            else:
+                scratch = torch.empty((b, 1, 1, s, s), dtype=torch.float32, device=dev)
+                ops.conv_gemm(self.pr[qs], c, kview, s, a_ch_off=qo, w_batched=True, w_ld=4 * c, w_ch_off=ko, out_f32=scratch)
+                ops.softmax_rows(scratch, probs)
+                ops.conv_gemm(dcat_s, c, vview, s, a_ch_off=oo, w_batched=True, out_f32=scratch)                   # dP = dO V^T
+                T.softmax_bwd_rows(probs, scratch, dsm)
             kt = ops.transpose_split(self.pr[ks], c, _S((b, c, s), dev), in_ch_off=ko)
             ops.conv_gemm(dsm, s, kt, c, w_batched=True, out=dpr[qs], o_ch_off=qo)                                 # dQ = dS K
             dkf = torch.zeros((b, s, c), dtype=torch.float32, device=dev)

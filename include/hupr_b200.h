@@ -87,6 +87,10 @@ typedef struct hupr_conv_desc {
                                                                      long K: the weight-gradient GEMMs (K = positions) */
     int w_k_off;                                                  /* added to the weight operand's contracted-axis coordinate (may be negative; out of
                                                                      range reads zero): shifted correlations over position-major operands */
+    const float* row_vec; int row_mode;                           /* per-POSITION vector [positions] applied to the accumulator before the rest of the
+                                                                     epilogue (attention backward, layers.py:126-133 under autograd; no scale/shift/slope):
+                                                                     1: out = exp(acc - row_vec[pos])          P rebuilt from the logits and the saved log-sum-exp
+                                                                     2: out = r * (acc - row_vec[pos])         dS = P * (dP - rowdot): r (the "residual" operand) MULTIPLIES */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
@@ -108,6 +112,8 @@ typedef struct hupr_attn_desc {
     const void* r_hi; const void* r_lo; int r_ld, r_off;
     void* o_hi; void* o_lo; int o_ld, o_off;
     int batch, s, c;
+    float* lse;      /* optional float [batch][s]: log sum_m exp(<Q[n], K[m]>) per query row — lets the backward pass rebuild
+                        P = exp(logits - lse) in a GEMM epilogue (hupr_conv_desc.row_mode) instead of a separate softmax; NULL = not written */
 } hupr_attn_desc;
 
 int hupr_attention_fwd(const hupr_attn_desc* desc, void* stream);
@@ -235,6 +241,10 @@ int hupr_bn_bwd_apply(const hupr_tensor_view* g, const hupr_tensor_view* z, cons
                       const float* k1, const float* k2, const float* k3, const hupr_tensor_view* out, long long positions, int c, void* stream);
 int hupr_act_bwd(const hupr_tensor_view* g, const hupr_tensor_view* s, const float* slope, const hupr_tensor_view* out, long long positions,
                  int c, void* stream);
+/* out[pos] = sum_ch a[pos][ch] * (b[pos][ch] - c[pos][ch])   (c optional) over `c_n` channels: the softmax-backward row term
+ * rowsum(P o dP) = <dO, O - residual> of the attention backward. */
+int hupr_rowdot(const hupr_tensor_view* a, const hupr_tensor_view* b, const hupr_tensor_view* c, float* out, long long positions, int c_n,
+                void* stream);
 int hupr_accumulate(const hupr_tensor_view* a, const hupr_tensor_view* b, const float* f, int f_ld, int f_off, const hupr_tensor_view* out,
                     long long positions, int c, void* stream);
 int hupr_resample_linear_bwd(const hupr_tensor_view* g, int n, int dout, int ho, int wo, int c, float* din, int di, int hi, int wi, int in_ld,

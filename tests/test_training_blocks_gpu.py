@@ -205,3 +205,50 @@ def test_prelu_resample_softmax_backward_match_autograd():
     T.accumulate(O, 64, a=A, b=B, f=f, f_off=64)
     torch.cuda.synchronize()
     assert float((O.float() - (A.float() + B.float() + f[..., 64:])).abs().max()) < 1e-4
+
+
+def test_attention_backward_fused_epilogues_match_float64():
+    """The pieces that rebuild P and dS inside GEMM epilogues (layers.py:126-133 under autograd): the fused forward's saved
+    log-sum-exp, P = exp(QK^T - lse) (hupr_conv_desc.row_mode 1), rowdot = <dO, O - residual> (hupr_rowdot) and
+    dS = P * (dO V^T - rowdot) (row_mode 2), against float64 softmax algebra."""
+    from hupr_b200 import ops
+    from hupr_b200 import train_ops as T
+    from hupr_b200.ops import SplitTensor
+    torch.manual_seed(31)
+    b, s, c = 2, 256, 64
+    q = torch.randn(b, s, c, device="cuda") * 0.6
+    k = torch.randn(b, s, c, device="cuda") * 0.6
+    v = torch.randn(b, s, c, device="cuda")
+    do = torch.randn(b, s, c, device="cuda")
+    Q, K, V, DO = (SplitTensor.from_float(t.view(b, 1, 1, s, c)) for t in (q, k, v, do))
+    qd, kd, vd, dod = (SplitTensor.from_float(t).float().double() for t in (q, k, v, do))
+    logits = qd @ kd.transpose(1, 2)
+    p_ref = torch.softmax(logits, dim=2)
+    o_ref = p_ref @ vd + vd                                          # cross branch: residual V
+    # forward: output and log-sum-exp
+    vt = ops.transpose_split(V, c, SplitTensor.empty((b, c, s), "cuda"))
+    out = SplitTensor.empty((b, 1, 1, s, c), "cuda")
+    lse = torch.empty((b, s), device="cuda")
+    ops.attention_fwd(Q, 0, K, 0, vt, c, out, 0, residual=V, lse=lse)
+    torch.cuda.synchronize()
+    assert float((lse.double() - torch.logsumexp(logits, dim=2)).abs().max()) < 6e-5      # the logits themselves carry ~2e-5 (|q||k| 2^-17)
+    assert float((out.float().double().view(b, s, c) - o_ref).abs().max()) < 1e-4
+    # P = exp(logits - lse)
+    probs = SplitTensor.empty((b, 1, 1, s, s), "cuda")
+    ops.conv_gemm(Q, c, SplitTensor(K.hi.view(b, s, c), K.lo.view(b, s, c)), s, w_batched=True, out=probs, row_vec=lse, row_mode=1)
+    torch.cuda.synchronize()
+    assert float((probs.float().double().view(b, s, s) - p_ref).abs().max()) < 2e-5 * float(p_ref.max())
+    # rowdot and dS
+    rd = T.rowdot(DO, out, c, torch.empty((b, s), device="cuda"), sub=V)
+    dp_ref = dod @ vd.transpose(1, 2)
+    rd_ref = (p_ref * dp_ref).sum(dim=2)
+    torch.cuda.synchronize()
+    assert float((rd.double() - rd_ref).abs().max()) < 1e-4 * float(rd_ref.abs().max())
+    ds = SplitTensor.empty((b, 1, 1, s, s), "cuda")
+    ops.conv_gemm(DO, c, SplitTensor(V.hi.view(b, s, c), V.lo.view(b, s, c)), s, w_batched=True, out=ds, residual=probs, row_vec=rd, row_mode=2)
+    torch.cuda.synchronize()
+    ds_ref = p_ref * (dp_ref - rd_ref.unsqueeze(2))
+    assert float((ds.float().double().view(b, s, s) - ds_ref).abs().max()) < 1e-4 * float(ds_ref.abs().max())
+    # the row modes refuse epilogue combinations they do not define
+    with pytest.raises(RuntimeError):
+        ops.conv_gemm(DO, c, SplitTensor(V.hi.view(b, s, c), V.lo.view(b, s, c)), s, w_batched=True, out=ds, row_vec=rd, row_mode=2)
