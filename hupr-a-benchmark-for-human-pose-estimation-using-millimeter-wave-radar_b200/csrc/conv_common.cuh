@@ -30,6 +30,10 @@ struct ConvParams {
     int m_tiles, n_tiles;          // 128-position tiles x BN-column tiles (x k_split slices), walked persistently
     const float* row_vec;          // per-position vector (row_mode 1: exp(acc - v), 2: r * (acc - v))
     int row_mode;
+    float* coop_ws;                // cooperative split-K: fp32 partial tiles [k_split][tiles][128][BN] ...
+    int* coop_counters;            // ... and one arrival counter per (tile, 32-row quarter); zero before and after every launch
+    int coop;
+    size_t coop_ws_bytes;
 };
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos`.

@@ -180,6 +180,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
             mbar_wait(&accum_full[as], (uint32_t)((li >> 1) & 1));
             tc_fence_after();
+            if (p.coop) {
+                // Cooperative split-K (small grids: batch-1 inference, the PRGCN GEMMs): every slice parks its partial tile in the
+                // workspace; the warp that arrives LAST at a (tile, row quarter) adds the slices in slice order — a fixed order, so the
+                // result does not depend on the arrival order — and runs the normal epilogue.  Counters return to zero.
+                const int tile = item % (p.m_tiles * p.n_tiles);
+                const int z = item / (p.m_tiles * p.n_tiles);
+                const size_t slice_stride = (size_t)p.m_tiles * p.n_tiles * BM * BN;
+                float* mine = p.coop_ws + (size_t)z * slice_stride + ((size_t)tile * BM + row) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&accum_empty[as]);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(mine + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        __stcg(dst + g, make_float4(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]), __uint_as_float(acc[4 * g + 2]),
+                                                    __uint_as_float(acc[4 * g + 3])));
+                }
+                __threadfence();
+                __syncwarp();
+                int arrived = 0;
+                if (lane == 0) arrived = atomicAdd(p.coop_counters + tile * 4 + q, 1);
+                arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                if (arrived == p.k_split - 1) {
+                    __threadfence();
+                    const float* first = p.coop_ws + ((size_t)tile * BM + row) * BN;
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float sum[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+                        for (int zz = 0; zz < p.k_split; zz += 2) {      // two slices in flight, added in slice order
+                            const float4* s0 = reinterpret_cast<const float4*>(first + (size_t)zz * slice_stride + c * 32);
+                            const bool two = zz + 1 < p.k_split;
+                            const float4* s1 = two ? reinterpret_cast<const float4*>(first + (size_t)(zz + 1) * slice_stride + c * 32) : s0;
+                            float4 u[8], w[8];
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) { u[g] = __ldcg(s0 + g); w[g] = __ldcg(s1 + g); }
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                sum[4 * g] += u[g].x; sum[4 * g + 1] += u[g].y; sum[4 * g + 2] += u[g].z; sum[4 * g + 3] += u[g].w;
+                            }
+                            if (two) {
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    sum[4 * g] += w[g].x; sum[4 * g + 1] += w[g].y; sum[4 * g + 2] += w[g].z; sum[4 * g + 3] += w[g].w;
+                                }
+                            }
+                        }
+                        uint32_t acc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
+                        conv_epilogue32(p, acc, pos, n0 + c * 32);
+                    }
+                    if (lane == 0) p.coop_counters[tile * 4 + q] = 0;
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
@@ -246,6 +308,26 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     ConvParams pp = p;
     pp.m_tiles = m_tiles;
     pp.n_tiles = p.cout / BN;
+    pp.coop = 0;
+    if (p.coop_ws && pp.k_split == 1) {     // small grid, long contraction: cooperative split-K with an ordered in-kernel reduction
+        const long long tiles = (long long)pp.m_tiles * pp.n_tiles;
+        const int total_kb = p.kd * p.kh * p.kw * p.cin_blocks;
+        if (tiles * 2 <= num_sms && total_kb >= 24) {     // long contractions only: a slice must outweigh the park / re-read of its tile
+            int ks = (int)(num_sms / tiles);
+            if (ks > total_kb / 8) ks = total_kb / 8;
+            if (ks > 4) ks = 4;
+            const size_t per_slice = (size_t)tiles * BM * BN * sizeof(float);
+            const size_t avail = p.coop_ws_bytes > 4096 ? p.coop_ws_bytes - 4096 : 0;
+            if ((size_t)ks * per_slice > avail) ks = (int)(avail / per_slice);
+            if (ks >= 2 && tiles * 4 * sizeof(int) <= 4096) {
+                pp.kb_per_split = (total_kb + ks - 1) / ks;
+                pp.k_split = (total_kb + pp.kb_per_split - 1) / pp.kb_per_split;
+                pp.coop = pp.k_split > 1 ? 1 : 0;
+                pp.coop_counters = reinterpret_cast<int*>(p.coop_ws);
+                pp.coop_ws = p.coop_ws + 1024;            // slices start 4096 B in
+            }
+        }
+    }
     const long long items = (long long)pp.m_tiles * pp.n_tiles * pp.k_split;
     if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
     dim3 grid((unsigned)(items < num_sms ? items : num_sms), 1, 1);
@@ -297,6 +379,8 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     p.o_f32 = d->o_f32; p.o_f32_ld = d->o_f32_ld;
     p.w_k_off = d->w_k_off;
     p.row_vec = d->row_vec; p.row_mode = d->row_vec ? d->row_mode : 0;
+    p.coop_ws = static_cast<float*>(d->ws); p.coop_ws_bytes = d->ws ? d->ws_bytes : 0; p.coop_counters = nullptr; p.coop = 0;
+    if (d->ws && ((uintptr_t)d->ws & 15)) return HUPR_ERR_ALIGNMENT;
     if (p.row_mode < 0 || p.row_mode > 2 || (p.row_mode && (d->scale || d->shift || d->slope || !d->o_hi)) || (p.row_mode == 2 && !d->r_hi)) return HUPR_ERR_BAD_ARG;
     {   // split-K (wgrad-style contractions: few output tiles, very long K): partial sums are added atomically into o_f32
         const int total_kb = taps * p.cin_blocks;

@@ -1,5 +1,7 @@
 """Python-side wrappers of the dense kernels (C ABI in include/hupr_b200.h).  PyTorch is used only for device
 memory and streams; every arithmetic op here is a call into libhupr_b200.so."""
+import os
+
 import torch
 
 import contextlib
@@ -69,9 +71,30 @@ class SplitTensor(object):
         return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
 
 
+_COOP_WS = {}
+COOP_WS_BYTES = 16 << 20
+_COOP_DEFAULT = os.environ.get("HUPR_NO_COOP", "") == ""      # A/B switch for measurements
+
+
+def coop_workspace(device, stream=None):
+    """Scratch for the cooperative split-K of small-grid contractions (hupr_conv_desc.ws), one per (device, CUDA stream): launches
+    on one stream are ordered, launches on different streams (the two sensor branches of a small-batch forward) may overlap and must
+    not share arrival counters.  Zeroed once; the kernels leave the counters zero."""
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    if stream is None:
+        stream = torch.cuda.current_stream(index).cuda_stream
+    key = (index, int(stream))
+    ws = _COOP_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(COOP_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", index))
+        _COOP_WS[key] = ws
+    return ws
+
+
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -91,6 +114,9 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.w_batched = 1 if w_batched else 0
     desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
     desc.k_split, desc.w_k_off = k_split, w_k_off
+    if k_split <= 1 and coop and _COOP_DEFAULT:     # small grids split their contraction cooperatively (deterministic ordered reduction)
+        ws = coop_workspace(a.hi.device)
+        desc.ws, desc.ws_bytes = ws.data_ptr(), ws.numel()
     if row_vec is not None:          # per-position vector: 1 = exp(acc - v), 2 = residual * (acc - v)  (attention backward)
         desc.row_vec, desc.row_mode = row_vec.data_ptr(), row_mode
     if a.hi.stride(0) != d * h * w * ca:        # overlapping sliding-window view over a frame stream

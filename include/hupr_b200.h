@@ -91,6 +91,12 @@ typedef struct hupr_conv_desc {
                                                                      epilogue (attention backward, layers.py:126-133 under autograd; no scale/shift/slope):
                                                                      1: out = exp(acc - row_vec[pos])          P rebuilt from the logits and the saved log-sum-exp
                                                                      2: out = r * (acc - row_vec[pos])         dS = P * (dP - rowdot): r (the "residual" operand) MULTIPLIES */
+    void* ws; size_t ws_bytes;                                    /* optional scratch (16-B aligned) enabling COOPERATIVE split-K when the output has too few
+                                                                     tiles to fill the GPU (batch-1 inference, the PRGCN GEMMs): slices of the contraction run on
+                                                                     separate CTAs, park fp32 partial tiles here, and the last arrival adds them in slice order
+                                                                     (deterministic) and runs the full epilogue — one launch, any epilogue.  The first 4096 bytes
+                                                                     are arrival counters: zero them once; every launch leaves them zero.  One workspace must not
+                                                                     be shared by launches that may run concurrently (different streams) */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);

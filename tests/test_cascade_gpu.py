@@ -131,3 +131,27 @@ def test_radar_object_generate_heatmap_mirror():
     cube = ro.generateHeatmap(frame)
     assert cube.shape == (16, 64, 64, 8) and cube.dtype == np.complex128
     assert_cube_close(cube, cascade.generate_heatmap(frame))
+
+
+def test_linearity_at_bench_size():
+    """Size-independent property at the bench's full launch size (2048 frame-sensors = 1.5 GiB of words): every stage of the cascade
+    (de-interleave, clutter removal, the three FFTs, crops / shifts / flips) is linear, so cascade(a + b) == cascade(a) + cascade(b)
+    up to fp32 round-off.  No oracle involved: the CPU restatement needs seconds per frame."""
+    from hupr_b200.preprocessing.process_iwr1843 import cascade_i16, FRAME_WORDS
+    n = 2048
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    a = torch.randint(-1000, 1000, (n, FRAME_WORDS), generator=gen, dtype=torch.int16, device="cuda")
+    b = torch.randint(-1000, 1000, (n, FRAME_WORDS), generator=gen, dtype=torch.int16, device="cuda")
+    out = torch.empty((n, 16, 64, 64, 8), dtype=torch.complex64, device="cuda")
+    ref = cascade_i16(a).clone()
+    ref += cascade_i16(b, out)
+    got = cascade_i16(a + b, out)
+    torch.cuda.synchronize()
+    scale = float(torch.view_as_real(ref).abs().max())
+    worst = 0.0
+    for i in range(0, n, 256):                                     # chunked comparison keeps the temporaries small
+        worst = max(worst, float(torch.view_as_real(got[i:i + 256] - ref[i:i + 256]).abs().max()))
+    assert worst < 2e-5 * scale, (worst, scale)
+    # and the launch is deterministic
+    again = cascade_i16(a + b)
+    assert torch.equal(again, got)

@@ -141,3 +141,39 @@ def test_bad_descriptor_is_rejected():
     W = SplitTensor.empty((1, 64, 64), "cuda", zero=True)
     with pytest.raises(RuntimeError):
         conv_gemm(A, 48, W, 64, out_f32=torch.empty(1, 1, 1, 128, 64, device="cuda"))   # cin not a multiple of 64
+
+
+@pytest.mark.parametrize("shape", [
+    # n, d, h, w, cin, cout, kernel, pad
+    (1, 2, 16, 16, 256, 256, (3, 3, 3), (1, 1, 1)),      # level-3 conv at batch 1: 4 x 2 tiles, 108 k-blocks
+    (1, 1, 32, 32, 640, 128, (1, 3, 3), (0, 1, 1)),      # decoder level 2 at batch 1
+    (2, 1, 1, 256, 1024, 1024, (1, 1, 1), (0, 0, 0)),    # PRGCN-shaped GEMM: 4 x 8 tiles, 16 k-blocks
+])
+def test_cooperative_split_k_is_deterministic_and_matches_unsplit(shape):
+    """hupr_conv_desc.ws: small grids split the contraction over CTAs and reduce the partial tiles in slice order inside the kernel.
+    Same epilogue (scale / shift / residual / slope / split stores) as the unsplit launch, results equal to fp32 round-off of the
+    different summation order, and bit-identical from run to run (no atomics on the data)."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    n, d, h, w, cin, cout, kernel, pad = shape
+    torch.manual_seed(41)
+    taps = kernel[0] * kernel[1] * kernel[2]
+    x = SplitTensor.from_float(torch.randn(n, d, h, w, cin, device="cuda"))
+    wt = SplitTensor.from_float(torch.randn(taps, cout, cin, device="cuda") / (cin * taps) ** 0.5)
+    scale = torch.rand(cout, device="cuda") + 0.5
+    shift = torch.randn(cout, device="cuda") * 0.1
+    slope = torch.full((cout,), 0.25, device="cuda")
+    d_out = d + 2 * pad[0] - kernel[0] + 1
+    res = SplitTensor.from_float(torch.randn(n, d_out, h, w, cout, device="cuda"))
+    outs = []
+    for coop in (False, True, True):
+        out = SplitTensor.empty((n, d_out, h, w, cout), "cuda")
+        ops.conv_gemm(x, cin, wt, cout, kernel=kernel, pad=pad, scale=scale, shift=shift, slope=slope, residual=res, out=out, coop=coop)
+        outs.append(out.float())
+    torch.cuda.synchronize()
+    ref, a, b = outs
+    assert torch.equal(a, b)                                             # deterministic
+    # summation order only: fp32 round-off, seen through the hi/lo bf16 output quantisation (one step of lo = 2^-17 of the value)
+    assert float((a - ref).abs().max()) < 3e-5 * float(ref.abs().max())
+    # the arrival counters are back to zero
+    assert int(ops.coop_workspace("cuda")[:4096].view(torch.int32).abs().sum()) == 0
