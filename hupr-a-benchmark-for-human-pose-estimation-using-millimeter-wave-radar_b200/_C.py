@@ -30,6 +30,7 @@ class ConvDesc(ctypes.Structure):
         ("k_split", ctypes.c_int), ("w_k_off", ctypes.c_int),
         ("row_vec", ctypes.c_void_p), ("row_mode", ctypes.c_int),
         ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_size_t),
+        ("no_tma_store", ctypes.c_int),
     ]
 
 

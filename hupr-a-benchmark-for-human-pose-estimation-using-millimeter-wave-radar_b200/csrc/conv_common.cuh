@@ -36,9 +36,9 @@ struct ConvParams {
     size_t coop_ws_bytes;
 };
 
-// acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos`.
-__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0) {
-    float v[32];
+// acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos` -> epilogue values v (everything but the stores).
+// rv = row_vec[pos] (loaded by the caller ahead of time; ignored unless row_mode).
+__device__ __forceinline__ void conv_epilogue_values(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float (&v)[32], float rv) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(acc[j]);
@@ -47,7 +47,6 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
         v[j] = fmaf(x, sc, sh);
     }
     if (p.row_mode) {
-        const float rv = __ldg(p.row_vec + pos);
         if (p.row_mode == 1) {
             const float kLog2e = 1.4426950408889634f;
             const float nr = -rv * kLog2e;
@@ -98,6 +97,11 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
             v[j] = v[j] > 0.0f ? v[j] : v[j] * sl;
         }
     }
+}
+
+__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float rv) {
+    float v[32];
+    conv_epilogue_values(p, acc, pos, ch0, v, rv);
     if (p.atomic) {     // split-K partial sum (no scale / shift / residual / activation on this path)
         float* dst = p.o_f32 + pos * p.o_f32_ld + ch0;
 #pragma unroll
@@ -122,6 +126,10 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
             for (int g = 0; g < 4; ++g) dl[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
         }
     }
+}
+
+__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0) {
+    conv_epilogue32(p, acc, pos, ch0, p.row_mode ? __ldg(p.row_vec + pos) : 0.f);
 }
 
 }  // namespace hupr

@@ -10,7 +10,7 @@
 //   * no im2col buffer: for every filter tap the TMA engine loads the shifted [BH x BW] x 64-channel box straight from
 //     the activation tensor (5-D tiled tensor map, SWIZZLE_128B, out-of-bounds = zero fill gives the conv padding);
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-//     warps 2..5 = epilogue (tcgen05.ld -> scale/shift (+residual) -> PReLU-style slope -> bf16 hi/lo or fp32 stores);
+//     warps 2..9 = epilogue, two per TMEM lane quarter (each half of the tile's columns) (tcgen05.ld -> scale/shift (+residual) -> PReLU-style slope -> bf16 hi/lo or fp32 stores);
 //   * mbarrier ring (full/empty) between TMA and MMA, tcgen05.commit releases stages and publishes the accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -24,29 +24,44 @@ namespace hupr {
 
 constexpr int BM = 128;   // output positions per CTA tile (TMEM lanes)
 constexpr int BK = 64;    // channels per k-block = one 128-byte swizzle row of bf16
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, each owning half of the tile's columns)
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, bool TSTORE = false>
 struct ConvCfg {
     static constexpr int kPlanes = (NPROD == 3) ? 2 : 1;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-    static constexpr int kStages = (200 * 1024 / kStageBytes) > 6 ? 6 : (200 * 1024 / kStageBytes);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    // TSTORE: the output tile is staged in shared memory ([hi | lo] x BN/64 blocks of [128 rows][128 B], 128B-swizzled) and written
+    // with TMA stores instead of one-row-per-thread global stores
+    static constexpr int kStoreBytes = TSTORE ? 2 * BM * BN * 2 : 0;
+    static constexpr int kStagesMax = (200 * 1024 - kStoreBytes) / kStageBytes;
+    static constexpr int kStages = kStagesMax > 6 ? 6 : kStagesMax;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kStages >= 2, "conv smem plan");
 };
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, int NPROD>
+
+template <int BN, int NPROD, bool TSTORE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const ConvParams p) {
     // Persistent: CTA b walks work items b, b + gridDim.x, ... (item = (split-K slice, column tile, 128-position tile)); the smem ring
     // runs continuously across items and two TMEM accumulators let the epilogue of one item overlap the main loop of the next.
-    using Cfg = ConvCfg<BN, NPROD>;
+    using Cfg = ConvCfg<BN, NPROD, TSTORE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes;          // TSTORE: output staging (1024-B aligned: stage sizes are multiples of 1 KiB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::kStoreBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::kStages;
     uint64_t* accum_full = bars + 2 * Cfg::kStages;          // [2]
@@ -65,7 +80,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&accum_full[s], 1);
-            mbar_init(&accum_empty[s], 128);
+            mbar_init(&accum_empty[s], 256);
         }
         fence_mbar_init();
     }
@@ -168,8 +183,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =================
+        // ================= epilogue warps (2..9): TMEM lanes 32*(warp%4) .. +31, column half (warp-2)/4 =================
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int c_begin = half * (BN / 64), c_end = c_begin + BN / 64;       // this warp's 32-column chunks
         const int row = q * 32 + lane;
         int li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
@@ -178,8 +195,56 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int as = li & 1;
             const int ow = w0 + row % p.bw, oh = h0 + row / p.bw;
             const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
+            const float rv = p.row_mode ? __ldg(p.row_vec + pos) : 0.f;        // in flight while the accumulator completes
             mbar_wait(&accum_full[as], (uint32_t)((li >> 1) & 1));
             tc_fence_after();
+            if (TSTORE) {
+                // Row tiles (128 consecutive positions): stage the hi / lo tile in swizzled shared memory, one thread hands it to the TMA
+                // engine.  A thread-per-row global store touches 32 half-filled sectors per instruction; this path touches none.
+                const bool leader = (warp == 2 && lane == 0);
+                if (li > 0) {
+                    if (leader) tma_store_wait_read();               // the previous tile's stores have read the staging buffer
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                const uint32_t xr = (uint32_t)(row & 7);
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
+                    if (c == c_end - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&accum_empty[as]);
+                    }
+                    float v[32];
+                    conv_epilogue_values(p, acc, pos, n0 + c * 32, v, rv);
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                    const uint32_t blk = (uint32_t)(c >> 1);
+                    const uint32_t base_hi = smem_u32(stg) + blk * (BM * 128) + (uint32_t)row * 128;
+                    const uint32_t base_lo = base_hi + (BN / 64) * (BM * 128);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t off = ((((uint32_t)(c & 1) * 4 + g) ^ xr) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base_hi + off), "r"(hi[4 * g]), "r"(hi[4 * g + 1]),
+                                     "r"(hi[4 * g + 2]), "r"(hi[4 * g + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base_lo + off), "r"(lo[4 * g]), "r"(lo[4 * g + 1]),
+                                     "r"(lo[4 * g + 2]), "r"(lo[4 * g + 3]) : "memory");
+                    }
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (leader) {
+                    const int pos0 = (int)(pos - (size_t)row);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b) {
+                        tma_store_2d(&tmO_hi, stg + b * (BM * 128), p.o_ch_off + n0 + 64 * b, pos0);
+                        tma_store_2d(&tmO_lo, stg + (BN / 64 + b) * (BM * 128), p.o_ch_off + n0 + 64 * b, pos0);
+                    }
+                    tma_store_commit();
+                }
+                continue;
+            }
             if (p.coop) {
                 // Cooperative split-K (small grids: batch-1 inference, the PRGCN GEMMs): every slice parks its partial tile in the
                 // workspace; the warp that arrives LAST at a (tile, row quarter) adds the slices in slice order — a fixed order, so the
@@ -189,10 +254,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const size_t slice_stride = (size_t)p.m_tiles * p.n_tiles * BM * BN;
                 float* mine = p.coop_ws + (size_t)z * slice_stride + ((size_t)tile * BM + row) * BN;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t acc[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
-                    if (c == BN / 32 - 1) {
+                    if (c == c_end - 1) {
                         tc_fence_before();
                         mbar_arrive(&accum_empty[as]);
                     }
@@ -205,13 +270,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 __threadfence();
                 __syncwarp();
                 int arrived = 0;
-                if (lane == 0) arrived = atomicAdd(p.coop_counters + tile * 4 + q, 1);
+                if (lane == 0) arrived = atomicAdd(p.coop_counters + (tile * 4 + q) * 2 + half, 1);
                 arrived = __shfl_sync(0xffffffffu, arrived, 0);
                 if (arrived == p.k_split - 1) {
                     __threadfence();
                     const float* first = p.coop_ws + ((size_t)tile * BM + row) * BN;
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
+                    for (int c = c_begin; c < c_end; ++c) {
                         float sum[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) sum[j] = 0.f;
@@ -236,23 +301,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         uint32_t acc[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
-                        conv_epilogue32(p, acc, pos, n0 + c * 32);
+                        conv_epilogue32(p, acc, pos, n0 + c * 32, rv);
                     }
-                    if (lane == 0) p.coop_counters[tile * 4 + q] = 0;
+                    if (lane == 0) p.coop_counters[(tile * 4 + q) * 2 + half] = 0;
                 }
                 continue;
             }
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
-                if (c == BN / 32 - 1) {          // last TMEM read of this accumulator: hand it back before the stores
+                if (c == c_end - 1) {            // last TMEM read of this accumulator by this thread: hand it back before the stores
                     tc_fence_before();
                     mbar_arrive(&accum_empty[as]);
                 }
-                conv_epilogue32(p, acc, pos, n0 + c * 32);
+                conv_epilogue32(p, acc, pos, n0 + c * 32, rv);
             }
         }
+        if (TSTORE && warp == 2 && lane == 0) tma_store_wait_all();      // the CTA's last stores are complete before its smem goes away
     }
     tc_fence_before();
     __syncthreads();
@@ -289,13 +355,25 @@ static int encode_wgt_map(CUtensorMap* map, const void* base, int cin, int cout,
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-template <int BN, int NPROD>
+static int encode_out_map(CUtensorMap* map, const void* base, int ld, long long positions) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return HUPR_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)positions};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
+template <int BN, int NPROD, bool TSTORE>
 static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const ConvParams& p, int m_tiles, cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, NPROD>;
+    using Cfg = ConvCfg<BN, NPROD, TSTORE>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPROD, TSTORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
             cudaSuccess)
             return HUPR_ERR_CUDA;
         configured = true;
@@ -309,7 +387,14 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     pp.m_tiles = m_tiles;
     pp.n_tiles = p.cout / BN;
     pp.coop = 0;
-    if (p.coop_ws && pp.k_split == 1) {     // small grid, long contraction: cooperative split-K with an ordered in-kernel reduction
+    CUtensorMap o_hi = a_hi, o_lo = a_hi;                // placeholders unless TSTORE
+    if (TSTORE) {
+        const long long positions = (long long)p.n * p.d_out * p.h * p.w;
+        int rc;
+        if ((rc = encode_out_map(&o_hi, p.o_hi, p.o_ld, positions)) != HUPR_OK) return rc;
+        if ((rc = encode_out_map(&o_lo, p.o_lo, p.o_ld, positions)) != HUPR_OK) return rc;
+    }
+    if (!TSTORE && p.coop_ws && pp.k_split == 1) {     // small grid, long contraction: cooperative split-K with an ordered in-kernel reduction
         const long long tiles = (long long)pp.m_tiles * pp.n_tiles;
         const int total_kb = p.kd * p.kh * p.kw * p.cin_blocks;
         if (tiles * 2 <= num_sms && total_kb >= 24) {     // long contractions only: a slice must outweigh the park / re-read of its tile
@@ -319,7 +404,7 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
             const size_t per_slice = (size_t)tiles * BM * BN * sizeof(float);
             const size_t avail = p.coop_ws_bytes > 4096 ? p.coop_ws_bytes - 4096 : 0;
             if ((size_t)ks * per_slice > avail) ks = (int)(avail / per_slice);
-            if (ks >= 2 && tiles * 4 * sizeof(int) <= 4096) {
+            if (ks >= 2 && tiles * 8 * sizeof(int) <= 4096) {
                 pp.kb_per_split = (total_kb + ks - 1) / ks;
                 pp.k_split = (total_kb + pp.kb_per_split - 1) / pp.kb_per_split;
                 pp.coop = pp.k_split > 1 ? 1 : 0;
@@ -331,7 +416,7 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     const long long items = (long long)pp.m_tiles * pp.n_tiles * pp.k_split;
     if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
     dim3 grid((unsigned)(items < num_sms ? items : num_sms), 1, 1);
-    conv_gemm_kernel<BN, NPROD><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, pp);
+    conv_gemm_kernel<BN, NPROD, TSTORE><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, pp);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
@@ -418,6 +503,10 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     if (m_tiles_ll > 2147483647LL) return HUPR_ERR_BAD_ARG;
     const int m_tiles = (int)m_tiles_ll;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (bn == 128) return split ? launch_conv<128, 3>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<128, 1>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
-    return split ? launch_conv<64, 3>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    // row tiles with bf16 split output and enough tiles to fill the GPU: TMA-store epilogue
+    const bool tstore = split && bw == BM && d->o_hi && d->o_lo && !d->o_f32 && !p.atomic && m_tiles_ll * (d->cout / bn) >= 148 &&
+                        (long long)d->n * d_out * d->h * d->w < 2147483647LL && !d->no_tma_store;
+    if (tstore) return bn == 128 ? launch_conv<128, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    if (bn == 128) return split ? launch_conv<128, 3, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<128, 1, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    return split ? launch_conv<64, 3, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
 }

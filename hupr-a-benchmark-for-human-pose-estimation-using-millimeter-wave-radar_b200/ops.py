@@ -94,7 +94,7 @@ def coop_workspace(device, stream=None):
 
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True, tma_store=True):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -114,6 +114,8 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.w_batched = 1 if w_batched else 0
     desc.w_ld, desc.w_ch_off = w_ld, w_ch_off
     desc.k_split, desc.w_k_off = k_split, w_k_off
+    if not tma_store or os.environ.get("HUPR_NO_TMA_STORE"):
+        desc.no_tma_store = 1
     if k_split <= 1 and coop and _COOP_DEFAULT:     # small grids split their contraction cooperatively (deterministic ordered reduction)
         ws = coop_workspace(a.hi.device)
         desc.ws, desc.ws_bytes = ws.data_ptr(), ws.numel()

@@ -97,6 +97,8 @@ typedef struct hupr_conv_desc {
                                                                      (deterministic) and runs the full epilogue — one launch, any epilogue.  The first 4096 bytes
                                                                      are arrival counters: zero them once; every launch leaves them zero.  One workspace must not
                                                                      be shared by launches that may run concurrently (different streams) */
+    int no_tma_store;                                             /* 1: keep the thread-per-row global stores even where the shared-memory-staged TMA-store
+                                                                     epilogue applies (row tiles: w a multiple of 128, bf16 split output) — for A/B measurements */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);

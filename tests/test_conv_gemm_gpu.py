@@ -177,3 +177,41 @@ def test_cooperative_split_k_is_deterministic_and_matches_unsplit(shape):
     assert float((a - ref).abs().max()) < 3e-5 * float(ref.abs().max())
     # the arrival counters are back to zero
     assert int(ops.coop_workspace("cuda")[:4096].view(torch.int32).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("shape", [
+    # n, h, w, cin, cout, o_ld, o_off
+    (4, 1, 4096, 64, 256, 256, 0),          # q/k/v projection rows: BN = 128
+    (2, 2, 1024, 128, 64, 192, 64),         # BN = 64, channel offset into a wider output, two rows of tiles per sample
+    (3, 1, 2048, 64, 2048, 2048, 0),        # attention-logit-shaped output (batched B operand)
+])
+def test_tma_store_epilogue_is_bit_identical_to_row_stores(shape):
+    """Row tiles (w a multiple of 128) stage their hi / lo output tile in 128B-swizzled shared memory and write it with TMA stores;
+    the values are the ones the thread-per-row path stores, so the two outputs must agree bit for bit (including a residual, the
+    PReLU-style slope, and untouched channels next to an offset slice)."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    n, h, w, cin, cout, o_ld, o_off = shape
+    torch.manual_seed(43)
+    x = SplitTensor.from_float(torch.randn(n, 1, h, w, cin, device="cuda"))
+    batched = cout == 2048
+    if batched:
+        wt = SplitTensor.from_float(torch.randn(n, cout, cin, device="cuda") * 0.2)
+    else:
+        wt = SplitTensor.from_float(torch.randn(1, cout, cin, device="cuda") * 0.2)
+    res = SplitTensor.from_float(torch.randn(n, 1, h, w, cout, device="cuda"))
+    slope = torch.full((cout,), 0.1, device="cuda")
+    outs = []
+    for tma in (False, True):
+        out = SplitTensor.from_float(torch.full((n, 1, h, w, o_ld), 7.0, device="cuda"))
+        ops.conv_gemm(x, cin, wt, cout, w_batched=batched, residual=res, slope=slope, out=out, o_ch_off=o_off, tma_store=tma)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].hi, outs[1].hi) and torch.equal(outs[0].lo, outs[1].lo)
+    if o_ld > cout:
+        assert float((outs[1].float()[..., :o_off] - 7.0).abs().max()) == 0.0
+    ref = torch.einsum("nhwc,noc->nhwo" if batched else "nhwc,oc->nhwo", x.float()[:, 0].double(), (wt.float() if batched else wt.float()[0]).double())
+    ref = ref + res.float()[:, 0].double()
+    ref = torch.where(ref > 0, ref, 0.1 * ref)
+    got = outs[1].float()[:, 0, :, :, o_off:o_off + cout].double()
+    assert float((got - ref).abs().max()) < 3e-5 * float(ref.abs().max())

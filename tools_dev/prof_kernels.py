@@ -36,5 +36,16 @@ if which in ("wgrad", "all"):
         dy = SplitTensor.from_float(torch.randn(b, d, h, w, cout, device="cuda"))
         out = torch.zeros((27, cin, cout), device="cuda")
         ops.conv_wgrad_direct(x, 0, cin, dy, 0, cout, (3, 3, 3), (1, 1, 1), out=out)
+if which in ("attnbwd",):
+    # the [S, S]-output GEMMs of the attention backward at level 1: P = exp(Q K^T - lse) and dS = P * (dO V^T - rowdot)
+    s_, c = 4096, 64
+    q = SplitTensor.from_float(torch.randn(b, 1, 1, s_, c, device="cuda") * 0.5)
+    k = SplitTensor.from_float(torch.randn(b, s_, c, device="cuda") * 0.5)
+    lse = torch.full((b, s_), 8.0, device="cuda")
+    probs = SplitTensor.empty((b, 1, 1, s_, s_), "cuda")
+    ds = SplitTensor.empty((b, 1, 1, s_, s_), "cuda")
+    for _ in range(2):
+        ops.conv_gemm(q, c, k, s_, w_batched=True, out=probs, row_vec=lse, row_mode=1)
+        ops.conv_gemm(q, c, k, s_, w_batched=True, out=ds, residual=probs, row_vec=lse, row_mode=2)
 torch.cuda.synchronize()
 print("done")
