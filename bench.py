@@ -300,13 +300,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="e2e", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=None, help="e2e: poses (windows) per GPU per step (default 32); train: samples per GPU (default 8)")
+    ap.add_argument("--batch", type=int, default=None, help="e2e: poses (windows) per GPU per step (default 32); train: samples per GPU (default 32 = the per-GPU shard of configs[3])")
     ap.add_argument("--frames-per-step", type=int, default=1024, help="cascade: radar frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-bf16", action="store_true", help="one bf16 product per k-step instead of the fp32-equivalent 3-product split")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 8 if args.workload == "train" else 32
+        args.batch = 32
     args.steps_ref = max(1, min(args.steps, 2))
     args.warmup_ref = 0
 
@@ -402,7 +402,7 @@ def main():
             h_loss[1:2].copy_(l2.reshape(1), non_blocking=True)
         e2e_units, h2d, d2h = units, 2 * h_h.numel() * 4, 8
         profile_step = lambda: trainer.forward_backward(hori, vert, joints)
-        l2_note = "per-step working set (saved activations + gradients, tens of GB at batch 8) exceeds the 126 MB L2"
+        l2_note = "per-step working set (saved activations + gradients, tens of GB) exceeds the 126 MB L2"
         dtype = "bf16 tensor-core products, fp32 accumulate (3-product hi/lo split: fp32-equivalent), fp32 master weights / Adam"
     else:
         torch.manual_seed(0)

@@ -34,6 +34,7 @@ struct ConvParams {
     int* coop_counters;            // ... and one arrival counter per (tile, 32-row quarter); zero before and after every launch
     int coop;
     size_t coop_ws_bytes;
+    int n_fastest;                 // work-item order: column tile fastest (wide outputs) instead of row tile fastest
 };
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos` -> epilogue values v (everything but the stores).

@@ -14,6 +14,7 @@
 //   * mbarrier ring (full/empty) between TMA and MMA, tcgen05.commit releases stages and publishes the accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "hupr_internal.h"
@@ -103,10 +104,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     // item -> (k slice, column tile, sample, depth slice, h block, w block); consecutive items share the weight tile
     auto decode = [&](int item, int& kb_begin, int& kb_end, int& n0, int& n, int& od, int& h0, int& w0) {
-        int t = item % p.m_tiles;
-        int r = item / p.m_tiles;
-        n0 = (r % p.n_tiles) * BN;
-        const int z = r / p.n_tiles;
+        // n_fastest (wide outputs, e.g. the [S, S] matrices of the attention backward): CTAs that run at the same time write the
+        // column tiles of the SAME rows, so a row's bytes reach L2 / DRAM together instead of 256 B at a time across 148 row tiles
+        const int mn = p.m_tiles * p.n_tiles;
+        const int in_slice = item % mn;
+        const int z = item / mn;
+        int t = p.n_fastest ? in_slice / p.n_tiles : in_slice % p.m_tiles;
+        n0 = (p.n_fastest ? in_slice % p.n_tiles : in_slice / p.m_tiles) * BN;
         kb_begin = z * p.kb_per_split;
         kb_end = min(total_kb, kb_begin + p.kb_per_split);
         w0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
@@ -386,6 +390,7 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     ConvParams pp = p;
     pp.m_tiles = m_tiles;
     pp.n_tiles = p.cout / BN;
+    pp.n_fastest = (pp.n_tiles >= 8 && !getenv("HUPR_M_FASTEST")) ? 1 : 0;
     pp.coop = 0;
     CUtensorMap o_hi = a_hi, o_lo = a_hi;                // placeholders unless TSTORE
     if (TSTORE) {
