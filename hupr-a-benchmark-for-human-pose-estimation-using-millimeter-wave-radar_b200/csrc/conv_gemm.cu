@@ -211,14 +211,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
                 const uint32_t xr = (uint32_t)(row & 7);
-#pragma unroll 1
-                for (int c = c_begin; c < c_end; ++c) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
-                    if (c == c_end - 1) {
-                        tc_fence_before();
-                        mbar_arrive(&accum_empty[as]);
-                    }
+                // all of this thread's accumulator columns leave TMEM first, so the MMA warp gets the buffer back before the epilogue math
+                uint32_t accs[BN / 64][32];
+#pragma unroll
+                for (int k = 0; k < BN / 64; ++k)
+                    tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + (c_begin + k) * 32), accs[k]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&accum_empty[as]);
+#pragma unroll
+                for (int k = 0; k < BN / 64; ++k) {
+                    const int c = c_begin + k;
+                    const uint32_t (&acc)[32] = accs[k];
                     float v[32];
                     conv_epilogue_values(p, acc, pos, n0 + c * 32, v, rv);
                     uint32_t hi[16], lo[16];
@@ -311,16 +315,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 continue;
             }
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
-                if (c == c_end - 1) {            // last TMEM read of this accumulator by this thread: hand it back before the stores
-                    tc_fence_before();
-                    mbar_arrive(&accum_empty[as]);
-                }
-                conv_epilogue32(p, acc, pos, n0 + c * 32, rv);
-            }
+            uint32_t accs[BN / 64][32];         // drain this thread's columns, hand the accumulator back, then do the epilogue math
+#pragma unroll
+            for (int k = 0; k < BN / 64; ++k)
+                tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + (c_begin + k) * 32), accs[k]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&accum_empty[as]);
+#pragma unroll
+            for (int k = 0; k < BN / 64; ++k) conv_epilogue32(p, accs[k], pos, n0 + (c_begin + k) * 32, rv);
         }
         if (TSTORE && warp == 2 && lane == 0) tma_store_wait_all();      // the CTA's last stores are complete before its smem goes away
     }
