@@ -98,6 +98,8 @@ SIGNATURES = {
     "hupr_affine_act": (ctypes.c_int, [_TV, _P, _P, _TV, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_bn_bwd_apply": (ctypes.c_int, [_TV, _TV, _TV, _P, _P, _P, _P, _P, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_act_bwd": (ctypes.c_int, [_TV, _TV, _P, _TV, ctypes.c_longlong, _I, _P]),
+    "hupr_bn_finalize": (ctypes.c_int, [_P, _P, ctypes.c_longlong, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "hupr_bn_bwd_finalize": (ctypes.c_int, [_P, _P, ctypes.c_longlong, _P, _P, _P, _P, _I, _P]),
     "hupr_rowdot": (ctypes.c_int, [_TV, _TV, _TV, _P, ctypes.c_longlong, _I, _P]),
     "hupr_accumulate": (ctypes.c_int, [_TV, _TV, _P, _I, _I, _TV, ctypes.c_longlong, _I, _P]),
     "hupr_resample_linear_bwd": (ctypes.c_int, [_TV, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),

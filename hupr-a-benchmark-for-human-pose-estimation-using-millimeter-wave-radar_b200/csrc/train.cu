@@ -218,6 +218,44 @@ rowdot_kernel(TView a, TView b, TView c, float* __restrict__ out, long long posi
     if (lane == 0) out[warp] = acc;
 }
 
+// Per-channel BatchNorm bookkeeping of the training forward in ONE launch (it was ~20 element-wise launches on [C] vectors):
+// batch mean / biased variance from the double sums, rstd, the fused affine (scale, shift) of the normalise kernel, and the
+// running-statistics update with momentum (unbiased variance), exactly as nn.BatchNorm3d does in train mode.
+__global__ void bn_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int c) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (ch >= c) return;
+    const double m = s1[ch] / count;
+    double var = s2[ch] / count - m * m;
+    var = var > 0.0 ? var : 0.0;
+    const float mf = (float)m;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[ch] * rs;
+    mean[ch] = mf;
+    rstd[ch] = rs;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - mf * sc;
+    if (running_mean) running_mean[ch] = running_mean[ch] * (1.0f - momentum) + momentum * mf;
+    if (running_var) {
+        const double unbiased = var * (count / (count > 1.0 ? count - 1.0 : 1.0));
+        running_var[ch] = running_var[ch] * (1.0f - momentum) + momentum * (float)unbiased;
+    }
+}
+
+// ... and of the backward: k2 = mean(g'), k3 = mean(g' zhat) for hupr_bn_bwd_apply, dgamma = sum g' zhat, dbeta = sum g'.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ t1, const double* __restrict__ t2, double count, float* __restrict__ k2,
+                                       float* __restrict__ k3, float* __restrict__ dgamma, float* __restrict__ dbeta, int c) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    k2[ch] = (float)(t1[ch] / count);
+    k3[ch] = (float)(t2[ch] / count);
+    dgamma[ch] = (float)t2[ch];
+    dbeta[ch] = (float)t1[ch];
+}
+
 struct ResampleBwdParams {
     int n, di, hi, wi, dout, ho, wo, c8;
     int g_ld, g_off, o_ld, o_off;
@@ -410,6 +448,26 @@ extern "C" int hupr_accumulate(const hupr_tensor_view* a, const hupr_tensor_view
     if (rc != HUPR_OK) return rc;
     accumulate_kernel<<<ew_blocks(positions * (c / 8)), 256, 0, (cudaStream_t)stream>>>(mk_view(a && a->hi ? a : nullptr), mk_view(b && b->hi ? b : nullptr),
                                                                                         f, f_ld, f_off, mk_out(out), positions, c);
+    return finish(1);
+}
+
+extern "C" int hupr_bn_finalize(const double* s1, const double* s2, long long count, const float* gamma, const float* beta, float eps, float momentum,
+                                float* mean, float* rstd, float* scale, float* shift, float* running_mean, float* running_var,
+                                long long* num_batches_tracked, int c, void* stream) {
+    if (!s1 || !s2 || !gamma || !beta || !mean || !rstd || !scale || !shift || c <= 0 || count <= 0) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s1, s2, (double)count, gamma, beta, eps, momentum, mean, rstd, scale, shift,
+                                                                          running_mean, running_var, num_batches_tracked, c);
+    return finish(1);
+}
+
+extern "C" int hupr_bn_bwd_finalize(const double* t1, const double* t2, long long count, float* k2, float* k3, float* dgamma, float* dbeta, int c,
+                                    void* stream) {
+    if (!t1 || !t2 || !k2 || !k3 || !dgamma || !dbeta || c <= 0 || count <= 0) return HUPR_ERR_BAD_ARG;
+    int rc = train_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t1, t2, (double)count, k2, k3, dgamma, dbeta, c);
     return finish(1);
 }
 

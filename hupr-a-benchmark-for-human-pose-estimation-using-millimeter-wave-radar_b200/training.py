@@ -75,7 +75,7 @@ class ConvOp(object):
         acc = ops.conv_wgrad_direct(x, x_off, self.cin_pad, dy, dy_off, self.cout, self.kernel, self.pad)      # [taps, cin_pad, cout]
         o = 0
         for name, c, cp in zip(self.names, self.couts, self.cout_pads):
-            grads[name] = acc[:, :self.cin, o:o + c].permute(2, 1, 0).reshape((c, self.cin) + self.kernel)
+            grads[name] = acc[:, :self.cin, o:o + c].permute(2, 1, 0)      # strided view [c, cin, taps]: copied once, into the flat gradient buffer
             o += cp
         if self.bias_name:
             s1 = torch.zeros(self.cout, dtype=torch.float64, device=dev)
@@ -91,30 +91,37 @@ class BNOp(object):
     def forward_stats(self, z, z_off, params, buffers, count):
         """Batch statistics of z[..., z_off:z_off+c]; updates running stats; returns (scale, shift) for the affine kernel."""
         dev = z.hi.device
-        s1 = torch.zeros(self.c, dtype=torch.float64, device=dev)
-        s2 = torch.zeros_like(s1)
-        T.channel_sums(T.SUMS_STATS, (z, z_off), self.c, s1, s2)
+        sums = torch.zeros((2, self.c), dtype=torch.float64, device=dev)
+        T.channel_sums(T.SUMS_STATS, (z, z_off), self.c, sums[0], sums[1])
+        gamma, beta = params[self.prefix + ".weight"].detach(), params[self.prefix + ".bias"].detach()
+        rm, rv = buffers[self.prefix + ".running_mean"], buffers[self.prefix + ".running_var"]
+        nbt = buffers[self.prefix + ".num_batches_tracked"]
+        ok = all(t.dtype == torch.float32 and t.is_contiguous() for t in (gamma, beta, rm, rv)) and nbt.dtype == torch.int64
+        if ok:      # one launch: mean, rstd, fused affine, running statistics (hupr_bn_finalize)
+            st = T.bn_finalize(sums, count, gamma, beta, EPS, MOMENTUM, rm, rv, nbt)
+            self.mean, self.rstd, self.scale, self.shift = st[0], st[1], st[2], st[3]
+            return self.scale, self.shift
+        s1, s2 = sums[0], sums[1]          # parameters / buffers kept in another dtype (tests drive float64 state): same algebra in torch
         mean = s1 / count
         var = (s2 / count - mean * mean).clamp_min(0.0)
         self.mean, self.rstd = mean.float(), (1.0 / torch.sqrt(var + EPS)).float()
-        gamma, beta = params[self.prefix + ".weight"].detach().float(), params[self.prefix + ".bias"].detach().float()
+        gamma, beta = gamma.float(), beta.float()
         self.scale = (gamma * self.rstd).contiguous()
         self.shift = (beta - self.mean * self.scale).contiguous()
-        rm, rv = buffers[self.prefix + ".running_mean"], buffers[self.prefix + ".running_var"]
         rm.mul_(1 - MOMENTUM).add_(mean.float(), alpha=MOMENTUM)
         rv.mul_(1 - MOMENTUM).add_((var * (count / max(count - 1, 1))).float(), alpha=MOMENTUM)
-        buffers[self.prefix + ".num_batches_tracked"].add_(1)
+        nbt.add_(1)
         return self.scale, self.shift
 
     def backward(self, g, z, z_off, mask, out, out_off, count, grads):
         """g: gradient w.r.t. the activation output (masked by mask > 0 when given) -> out[..., out_off:+c] = dz; fills dgamma, dbeta."""
         dev = z.hi.device
-        t1 = torch.zeros(self.c, dtype=torch.float64, device=dev)
-        t2 = torch.zeros_like(t1)
-        T.channel_sums(T.SUMS_BN_BWD, g, self.c, t1, t2, b=(z, z_off), mask=mask, mean=self.mean, rstd=self.rstd)
-        T.bn_bwd_apply(g, (z, z_off), self.c, self.mean, self.rstd, self.scale, (t1 / count).float(), (t2 / count).float(), (out, out_off), mask=mask)
-        grads[self.prefix + ".weight"] = t2.float()
-        grads[self.prefix + ".bias"] = t1.float()
+        sums = torch.zeros((2, self.c), dtype=torch.float64, device=dev)
+        T.channel_sums(T.SUMS_BN_BWD, g, self.c, sums[0], sums[1], b=(z, z_off), mask=mask, mean=self.mean, rstd=self.rstd)
+        st = T.bn_bwd_finalize(sums, count)                      # k2, k3, dgamma, dbeta in one launch
+        T.bn_bwd_apply(g, (z, z_off), self.c, self.mean, self.rstd, self.scale, st[0], st[1], (out, out_off), mask=mask)
+        grads[self.prefix + ".weight"] = st[2]
+        grads[self.prefix + ".bias"] = st[3]
 
 
 class Block3D(object):
@@ -528,7 +535,11 @@ class TrainStep(object):
             grads[net + ".temporalConvWx1x1.bias"] = db.float()
         # ---- scatter into the flat gradient buffer (views installed as param.grad)
         for name, q in params.items():
-            q.grad.copy_(grads[name].reshape(q.shape))
+            g = grads[name]
+            if g.shape != q.shape and g.numel() == q.numel() and not g.is_contiguous():
+                q.grad.view(g.shape).copy_(g)                     # e.g. a conv filter gradient view [c, cin, taps] -> [c, cin, kd, kh, kw]
+            else:
+                q.grad.copy_(g.reshape(q.shape))
         self.last_grads = grads
         return losses[0], losses[1]
 

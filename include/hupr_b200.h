@@ -249,6 +249,17 @@ int hupr_bn_bwd_apply(const hupr_tensor_view* g, const hupr_tensor_view* z, cons
                       const float* k1, const float* k2, const float* k3, const hupr_tensor_view* out, long long positions, int c, void* stream);
 int hupr_act_bwd(const hupr_tensor_view* g, const hupr_tensor_view* s, const float* slope, const hupr_tensor_view* out, long long positions,
                  int c, void* stream);
+/* Per-channel BatchNorm bookkeeping (nn.BatchNorm3d in train mode, /root/reference/models/layers.py:45-53, eps 1e-5, momentum 0.1) in one
+ * launch each:
+ *   hupr_bn_finalize      double sums s1 = sum z, s2 = sum z^2 over `count` positions -> mean, rstd = 1/sqrt(biased var + eps), the fused
+ *                         affine scale = gamma*rstd, shift = beta - mean*scale, running_mean/var (unbiased variance) += momentum * (new - old),
+ *                         num_batches_tracked += 1 (the three running-state pointers may be NULL)
+ *   hupr_bn_bwd_finalize  double sums t1 = sum g', t2 = sum g' zhat -> k2 = t1/count, k3 = t2/count (hupr_bn_bwd_apply), dgamma = t2, dbeta = t1 */
+int hupr_bn_finalize(const double* s1, const double* s2, long long count, const float* gamma, const float* beta, float eps, float momentum,
+                     float* mean, float* rstd, float* scale, float* shift, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, int c, void* stream);
+int hupr_bn_bwd_finalize(const double* t1, const double* t2, long long count, float* k2, float* k3, float* dgamma, float* dbeta, int c,
+                         void* stream);
 /* out[pos] = sum_ch a[pos][ch] * (b[pos][ch] - c[pos][ch])   (c optional) over `c_n` channels: the softmax-backward row term
  * rowsum(P o dP) = <dO, O - residual> of the attention backward. */
 int hupr_rowdot(const hupr_tensor_view* a, const hupr_tensor_view* b, const hupr_tensor_view* c, float* out, long long positions, int c_n,
