@@ -47,3 +47,43 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The descriptor structs are passed by pointer across the boundary, so the ctypes mirrors in _C.py must have the C compiler's
+    layout for include/hupr_b200.h: compile a C program that prints sizeof / offsetof of every mirrored field and compare."""
+    import shutil
+    import subprocess
+    from hupr_b200 import _C
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    mirrors = {"hupr_conv_desc": _C.ConvDesc, "hupr_attn_desc": _C.AttnDesc, "hupr_wgrad_desc": _C.WgradDesc,
+               "hupr_tensor_view": _C.TensorView}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hupr_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for field, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, field, cname, field))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line:
+            continue
+        cname, field, value = line.split()
+        cls = mirrors[cname]
+        if field == "sizeof":
+            assert ctypes.sizeof(cls) == int(value), "%s: ctypes size %d, C size %s" % (cname, ctypes.sizeof(cls), value)
+        else:
+            assert getattr(cls, field).offset == int(value), "%s.%s" % (cname, field)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
+    # and the header has no field the mirror lacks: the C struct would then be larger than the last mirrored field's end
+    for cname, cls in mirrors.items():
+        last, ctype = cls._fields_[-1]
+        assert getattr(cls, last).offset + ctypes.sizeof(ctype) + 8 > ctypes.sizeof(cls)
