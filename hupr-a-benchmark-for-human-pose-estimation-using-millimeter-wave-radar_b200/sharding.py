@@ -39,3 +39,13 @@ def gather_keypoints(local, n_windows, world=None, rank=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def average_gradients(flat):
+    """Data-parallel training (SURVEY.md §8 e): ONE sum all-reduce over the flat gradient buffer, then divide by the world size —
+    every rank computed the mean loss of its own equally sized shard, so the result is the gradient of the global mean loss
+    (tools/run.py:76-79 run on one device with the whole batch).  No-op without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+    return flat

@@ -581,7 +581,5 @@ class TrainStep(object):
 
     def all_reduce_gradients(self):
         """Data-parallel training (SURVEY.md §8 e): ONE sum all-reduce over the flat gradient buffer, then divide by the world size."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-            self.flat_g.div_(dist.get_world_size())
+        from .sharding import average_gradients
+        average_gradients(self.flat_g)

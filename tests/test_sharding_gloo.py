@@ -57,3 +57,48 @@ def test_window_shard_partition_properties():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
     with pytest.raises(ValueError):
         sharding.window_shard(4, 2, 2)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hupr_b200 import sharding
+    torch.manual_seed(0)
+    w = torch.randn(5, 3, dtype=torch.float64, requires_grad=True)          # identical replicas
+    x = torch.randn(8, 5, dtype=torch.float64)                              # the global batch, same on every rank
+    y = torch.randn(8, 3, dtype=torch.float64)
+    per = 8 // world
+    xs, ys = x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per]
+    loss = torch.nn.functional.binary_cross_entropy(torch.sigmoid(xs @ w), torch.sigmoid(ys))      # mean over the LOCAL shard
+    loss.backward()
+    flat = w.grad.reshape(-1).clone()
+    sharding.average_gradients(flat)
+    torch.save(flat, os.path.join(out_dir, "grad%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_averaged_shard_gradients_equal_global_batch_gradient(world, tmp_path):
+    """The training collective (TrainStep.all_reduce_gradients -> sharding.average_gradients): per-rank mean losses over equal shards,
+    one sum all-reduce, divide by the world size == the gradient of the mean loss over the whole batch on one device."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    torch.manual_seed(0)
+    w = torch.randn(5, 3, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(8, 5, dtype=torch.float64)
+    y = torch.randn(8, 3, dtype=torch.float64)
+    torch.nn.functional.binary_cross_entropy(torch.sigmoid(x @ w), torch.sigmoid(y)).backward()
+    for r in range(world):
+        flat = torch.load(os.path.join(str(tmp_path), "grad%d.pt" % r))
+        assert float((flat - w.grad.reshape(-1)).abs().max()) < 1e-14
+
+
+def test_average_gradients_is_a_no_op_without_a_process_group():
+    from hupr_b200 import sharding
+    flat = torch.arange(4, dtype=torch.float32)
+    assert torch.equal(sharding.average_gradients(flat.clone()), flat)
