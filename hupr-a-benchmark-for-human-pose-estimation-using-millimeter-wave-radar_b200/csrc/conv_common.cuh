@@ -31,7 +31,7 @@ struct ConvParams {
     const float* row_vec;          // per-position vector (row_mode 1: exp(acc - v), 2: r * (acc - v))
     int row_mode;
     float* coop_ws;                // cooperative split-K: fp32 partial tiles [k_split][tiles][128][BN] ...
-    int* coop_counters;            // ... and one arrival counter per (tile, 32-row quarter); zero before and after every launch
+    int* coop_counters;            // ... and one arrival counter per (tile, 32-row quarter, column half); zero before and after every launch
     int coop;
     size_t coop_ws_bytes;
     int n_fastest;                 // work-item order: column tile fastest (wide outputs) instead of row tile fastest

@@ -89,7 +89,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // work item: (split-K slice, column tile of cout, group of accumulator slots)
+    // work item: (sample [batched mode], split-K slice, column tile of cout, group of accumulator slots)
     int item = blockIdx.x;
     const int group = item % p.groups; item /= p.groups;
     const int n0 = (item % p.n_tiles) * BN; item /= p.n_tiles;
