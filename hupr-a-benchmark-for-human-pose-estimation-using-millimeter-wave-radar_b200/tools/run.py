@@ -5,8 +5,10 @@ Same constructor ``Runner(args, cfg)``, methods (``loadModelWeight``, ``train``,
 checkpoint dictionary (``epoch``, ``model_state_dict``, ``optimizer_state_dict`` in torch.optim.Adam's own format, ``accuracy``), so
 checkpoints written by either implementation load in the other.  The arithmetic runs through hupr_b200: ``HuPRNet`` (inference),
 ``TrainStep`` (forward + backward + Adam), ``LossComputer`` (loss / keypoint decode).
-Differences: visualisation (``plotHumanPose``, needs RGB frames) is not provided; when pycocotools is not installed ``eval`` still
-writes the results file and returns ``nan`` for the AP instead of failing.
+Differences: visualisation (``plotHumanPose``, needs RGB frames) is not provided; ``eval`` keeps the poses on the device, writes the
+results file from one transfer after the loop and computes AP with ``hupr_b200.misc.keypoint_eval`` (a mirror of the reference's
+vendored COCO evaluator), so no pycocotools install is needed.  One process drives one GPU; data-parallel training over several GPUs
+is ``TrainStep`` + ``all_reduce_gradients`` under torchrun (``bench.py --workload train`` shows the loop).
 """
 import json
 import math
