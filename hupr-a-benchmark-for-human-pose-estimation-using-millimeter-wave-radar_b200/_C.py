@@ -47,6 +47,21 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class AttnBwdDesc(ctypes.Structure):
+    """Mirror of ``hupr_attn_bwd_desc``."""
+    _fields_ = [
+        ("q_hi", ctypes.c_void_p), ("q_lo", ctypes.c_void_p), ("q_ld", ctypes.c_int), ("q_off", ctypes.c_int),
+        ("k_hi", ctypes.c_void_p), ("k_lo", ctypes.c_void_p), ("k_ld", ctypes.c_int), ("k_off", ctypes.c_int),
+        ("v_hi", ctypes.c_void_p), ("v_lo", ctypes.c_void_p), ("v_ld", ctypes.c_int), ("v_off", ctypes.c_int),
+        ("do_hi", ctypes.c_void_p), ("do_lo", ctypes.c_void_p), ("do_ld", ctypes.c_int), ("do_off", ctypes.c_int),
+        ("lse", ctypes.c_void_p), ("rowdot", ctypes.c_void_p),
+        ("dq", ctypes.c_void_p), ("dq_ld", ctypes.c_int), ("dq_off", ctypes.c_int),
+        ("dk", ctypes.c_void_p), ("dk_ld", ctypes.c_int), ("dk_off", ctypes.c_int),
+        ("dv", ctypes.c_void_p), ("dv_ld", ctypes.c_int), ("dv_off", ctypes.c_int),
+        ("batch", ctypes.c_int), ("s", ctypes.c_int), ("c", ctypes.c_int),
+    ]
+
+
 class WgradDesc(ctypes.Structure):
     """Mirror of ``hupr_wgrad_desc``."""
     _fields_ = [
@@ -78,6 +93,7 @@ SIGNATURES = {
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
     "hupr_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), ctypes.c_void_p]),
+    "hupr_attention_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdDesc), ctypes.c_void_p]),
     "hupr_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttnDesc), ctypes.c_void_p]),
     "hupr_window_normalize": (ctypes.c_int, [_P, _P, _I, _P, _P]),
     "hupr_frame_features_workspace_bytes": (ctypes.c_size_t, [_I]),

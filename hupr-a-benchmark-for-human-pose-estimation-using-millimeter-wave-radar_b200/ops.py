@@ -160,6 +160,25 @@ def attention_fwd(q, q_off, k, k_off, vt, c, out, o_off, residual=None, r_off=0,
     return out
 
 
+def attention_bwd(q, q_off, k, k_off, v, v_off, do, do_off, lse, rowdot, dq, dq_off, dk, dk_off, dv, dv_off, c=64):
+    """Fused attention backward (hupr_attention_bwd, c == 64): q, k, v, do SplitTensors ``[B, .., S, ld]``; lse, rowdot float32 ``[B, S]``;
+    dq, dk, dv float32 ``[B, S, ld]`` — the three gradients are ADDED at their channel offsets."""
+    b = q.hi.shape[0]
+    s = lse.shape[-1]
+    desc = _C.AttnBwdDesc()
+    desc.q_hi, desc.q_lo, desc.q_ld, desc.q_off = q.hi.data_ptr(), _C.optr(q.lo), q.hi.shape[-1], q_off
+    desc.k_hi, desc.k_lo, desc.k_ld, desc.k_off = k.hi.data_ptr(), _C.optr(k.lo), k.hi.shape[-1], k_off
+    desc.v_hi, desc.v_lo, desc.v_ld, desc.v_off = v.hi.data_ptr(), _C.optr(v.lo), v.hi.shape[-1], v_off
+    desc.do_hi, desc.do_lo, desc.do_ld, desc.do_off = do.hi.data_ptr(), _C.optr(do.lo), do.hi.shape[-1], do_off
+    desc.lse, desc.rowdot = lse.data_ptr(), rowdot.data_ptr()
+    desc.dq, desc.dq_ld, desc.dq_off = dq.data_ptr(), dq.shape[-1], dq_off
+    desc.dk, desc.dk_ld, desc.dk_off = dk.data_ptr(), dk.shape[-1], dk_off
+    desc.dv, desc.dv_ld, desc.dv_off = dv.data_ptr(), dv.shape[-1], dv_off
+    desc.batch, desc.s, desc.c = b, s, c
+    with torch.cuda.device(q.hi.device), _timed("attention_bwd", 10.0 * b * s * s * c):
+        _C.check(_C.lib().hupr_attention_bwd(desc, _C.stream_ptr()), "hupr_attention_bwd")
+
+
 def launch_count():
     """Kernels launched by libhupr_b200.so in this process so far (hupr_launch_count)."""
     return int(_C.lib().hupr_launch_count())

@@ -126,6 +126,26 @@ typedef struct hupr_attn_desc {
 
 int hupr_attention_fwd(const hupr_attn_desc* desc, void* stream);
 
+/* Fused backward of the attention above for c == 64 (no [S, S] matrix in memory): given the forward's operands, the gradient dO of its
+ * output, the saved log-sum-exp rows (hupr_attn_desc.lse) and rowdot[b][n] = <dO[n], (P V)[n]> (hupr_rowdot on the forward output minus
+ * the residual), ADDS  dQ = dS K,  dK = dS^T Q,  dV = P^T dO  to fp32 buffers, where P = exp(Q K^T - lse), dS = P o (dO V^T - rowdot)
+ * (autograd of /root/reference/models/layers.py:126-133).  q, k, v, do: bf16 split rows [batch][s][*_ld] with the 64 channels at *_off
+ * (v is NOT transposed here); dq, dk, dv: float [batch][s][*_ld] at *_off, zero-filled (or holding earlier contributions) by the caller.
+ * s a multiple of 128.  First version: not yet called by the training step. */
+typedef struct hupr_attn_bwd_desc {
+    const void* q_hi; const void* q_lo; int q_ld, q_off;
+    const void* k_hi; const void* k_lo; int k_ld, k_off;
+    const void* v_hi; const void* v_lo; int v_ld, v_off;
+    const void* do_hi; const void* do_lo; int do_ld, do_off;
+    const float* lse; const float* rowdot;
+    float* dq; int dq_ld, dq_off;
+    float* dk; int dk_ld, dk_off;
+    float* dv; int dv_ld, dv_off;
+    int batch, s, c;
+} hupr_attn_bwd_desc;
+
+int hupr_attention_bwd(const hupr_attn_bwd_desc* desc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Loader bridge.  Replaces Normalize.__call__ + the window assembly of HuPR3D_horivert.__getitem__
  *   /root/reference/datasets/base.py:13-24, /root/reference/datasets/dataset.py:120-150
