@@ -12,6 +12,8 @@ tensors the forward saved —
   PRGCN        : the transposed-layout GEMMs of the forward with W^T, adjacency mixes with A^T, adjoint resampling
 This first version favours exactness over speed (fp32-equivalent hi/lo arithmetic everywhere, unfused backward attention).
 """
+import os
+
 import torch
 
 from . import ops
@@ -228,6 +230,7 @@ class AttentionLevel(object):
     def __init__(self, level, c, hw, prev):
         p = "radarDecoder."
         self.c, self.hw, self.s, self.prev = c, hw, hw * hw, prev
+        self.fused_bwd = False       # hupr_attention_bwd for head dim 64 (opt-in until it has been timed inside the step: DESIGN.md §3b)
         self.proj_h = ConvOp([p + "%s.%d.weight" % (n, level) for n in L.PROJ_HORI], c, [c] * 4, (1, 1, 1), (0, 0, 0))
         self.proj_v = ConvOp([p + "%s.%d.weight" % (n, level) for n in L.PROJ_VERT], c, [c] * 4, (1, 1, 1), (0, 0, 0))
 
@@ -278,7 +281,23 @@ class AttentionLevel(object):
         # contract over the query axis with MN-major tensor-core operands (ops.matmul_tn): no transposed [S, S] copies
         dvf = {"ra": torch.zeros((b, s, c), dtype=torch.float32, device=dev), "re": torch.zeros((b, s, c), dtype=torch.float32, device=dev)}
         dv_res = {}
-        for idx, (qs, qo, ks, ko, vs, oo, res) in enumerate(self._plan()):
+        if self.fused_bwd and c == 64 and all(l is not None for l in self.lse):
+            # fused flash-style backward: no [S, S] matrix in memory; dQ / dK of the four attentions accumulate in fp32 projection-gradient
+            # buffers (one conversion to hi/lo afterwards), dV in the per-source buffers
+            dprf = {key: torch.zeros((b, s, 4 * c), dtype=torch.float32, device=dev) for key in ("ra", "re")}
+            for idx, (qs, qo, ks, ko, vs, oo, res) in enumerate(self._plan()):
+                rowdot = T.rowdot((dcat_s, oo), (self.cat_s, oo), c, torch.empty((b, s), dtype=torch.float32, device=dev),
+                                  sub=v[vs] if res else None)
+                ops.attention_bwd(self.pr[qs], qo, self.pr[ks], ko, v[vs], 0, dcat_s, oo, self.lse[idx], rowdot,
+                                  dprf[qs], qo, dprf[ks], ko, dvf[vs], 0)
+                if res:
+                    dv_res[vs] = oo
+            for key in ("ra", "re"):
+                T.accumulate(dpr[key], 4 * c, f=dprf[key].view(b * s, 4 * c))
+            plan = []
+        else:
+            plan = list(enumerate(self._plan()))
+        for idx, (qs, qo, ks, ko, vs, oo, res) in plan:
             kview = SplitTensor(self.pr[ks].hi.view(b, s, 4 * c), self.pr[ks].lo.view(b, s, 4 * c))
             vview = SplitTensor(v[vs].hi.view(b, s, c), v[vs].lo.view(b, s, c))
             probs, dsm = _S((b, 1, 1, s, s), dev), _S((b, 1, 1, s, s), dev)
@@ -376,12 +395,18 @@ class TrainStep(object):
     """``loss, loss2 = step.forward_backward(hori, vert, joints)`` fills ``param.grad`` of every model parameter;
     ``step.optimizer_step()`` applies Adam (coupled L2) in place.  ``model`` is a ``hupr_b200.models.HuPRNet`` on a CUDA device."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused_attention_bwd=None):
+        """``fused_attention_bwd``: use hupr_attention_bwd for the head-dim-64 attentions (default: off unless HUPR_FUSED_ATTN_BWD=1 —
+        the kernel is parity-tested on its own but has not been run inside the step yet)."""
         self.model = model
         nf, g, kp = model.numFilters, model.numGroupFrames, model.numKeypoints
         self.nf, self.g, self.kp = nf, g, kp
         self.enc = {"ra": Encoder("RAradarEncoder", nf, g), "re": Encoder("REradarEncoder", nf, g)}
         self.levels = [AttentionLevel(0, 8 * nf, 16, 0), AttentionLevel(1, 4 * nf, 32, 4 * nf), AttentionLevel(2, 2 * nf, 64, 2 * nf)]
+        if fused_attention_bwd is None:
+            fused_attention_bwd = os.environ.get("HUPR_FUSED_ATTN_BWD") == "1"
+        for level in self.levels:
+            level.fused_bwd = bool(fused_attention_bwd)
         p = "radarDecoder."
         self.dblocks = [Block2D(p + "decoderLayer3.0", 32 * nf, 8 * nf), Block2D(p + "decoderLayer3.1", 8 * nf, 4 * nf),
                         Block2D(p + "decoderLayer2.0", 20 * nf, 4 * nf), Block2D(p + "decoderLayer2.1", 4 * nf, 2 * nf),

@@ -7,6 +7,8 @@ and ONE such flip changes a weight gradient by ~1/sqrt(#positions) in relative L
 elements; 7e-6 with no flip).  The per-block tests therefore search for a seed without flips (checked against a float64
 reference) and assert tight agreement there; the whole-network test asserts loss parity and direction/L2 agreement of every
 gradient tensor with flip-sized tolerances."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -273,3 +275,29 @@ def test_graph_replayed_training_equals_eager_training():
         diff = (p_e[k] - p_g[k]).abs()
         assert float(diff.max()) < 5 * 2e-4 + 1e-5, k
         assert float(diff.mean()) < 1e-4, (k, float(diff.mean()))       # 3 steps of lr 1e-4: a tensor whose gradient is at noise level
+
+
+@pytest.mark.skipif(os.environ.get("HUPR_FUSED_ATTN_BWD") != "1",
+                    reason="opt-in: the fused attention backward is parity-tested on its own (test_attention_bwd_gpu.py) but not yet enabled in TrainStep")
+def test_training_step_with_fused_attention_backward_matches_unfused():
+    """TrainStep(fused_attention_bwd=True) against the default step on the same weights and batch: every gradient tensor to 1e-3
+    relative L2 (both are fp32-equivalent; they differ by summation order and by P = exp(S - lse) vs the two-pass softmax)."""
+    from hupr_b200.models import HuPRNet
+    from hupr_b200.training import TrainStep
+    from oracle import model as om
+    from tests.test_model_gpu import make_cfg
+    sd = om.make_state_dict(6)
+    hori, vert = (t.cuda() for t in om.make_vrdae(1, 6))
+    joints = torch.randint(0, 256, (1, 14, 2), generator=torch.Generator().manual_seed(7)).cuda()
+    grads = []
+    for fused in (False, True):
+        net = HuPRNet(make_cfg())
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        step = TrainStep(net, fused_attention_bwd=fused)
+        step.forward_backward(hori, vert, joints)
+        grads.append({k: q.grad.detach().clone() for k, q in net.named_parameters()})
+    torch.cuda.synchronize()
+    for k in grads[0]:
+        a, b = grads[0][k].double(), grads[1][k].double()
+        assert float((a - b).norm() / (a.norm() + 1e-30)) < 1e-3, k
