@@ -50,3 +50,10 @@ def convert(src_dir, dst_dir, device="cuda", frames_per_launch=32):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             np.save(out, p)
     return len(todo)
+
+
+if __name__ == "__main__":          # python -m hupr_b200.datasets.cubecache <cube cache dir> <plane cache dir>
+    import sys
+    if len(sys.argv) != 3:
+        raise SystemExit("usage: python -m hupr_b200.datasets.cubecache <src dir of [16,64,64,8] .npy cubes> <dst dir>")
+    print("%d files converted" % convert(sys.argv[1], sys.argv[2]))
