@@ -44,7 +44,7 @@ WORKLOADS = {
     "cascade-sweep": "fft-cascade throughput sweep 1k-1M radar frames (BASELINE.json configs[4]), frames sharded over the ranks, "
                      "resident chunks of 1024 frames (2048 frame-sensors: 1.5 GiB int16 in, 8 GiB complex64 out)",
     "train": "MSCSA-PRGCN training step (BASELINE.json configs[3] per-GPU shard): train-mode forward + backward + gradient all-reduce + Adam, "
-             "fp32-equivalent hi/lo bf16 tensor-core arithmetic, synthetic VRDAE inputs and joints",
+             "synthetic VRDAE inputs and joints",
 }
 MODEL_FWD_FLOPS = 137.09e9      # per sample, SURVEY.md §8 d (2 x MACs of the reference forward)
 
@@ -242,6 +242,93 @@ def summarise_profile(rec):
     return fam, sub
 
 
+def count_graph_kernels(replay):
+    """Kernel launches of ONE graph replay by origin, from a CUPTI trace (torch.profiler): {"hupr": n, "other": m, "other_names": [...]}.
+    ``other`` are kernels that do not come from libhupr_b200.so (framework element-wise kernels, NCCL); memsets / memcpys are DMA nodes,
+    counted separately.  None if no trace can be taken on this box."""
+    import torch
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        replay()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            replay()
+            torch.cuda.synchronize()
+        hupr, other, memops, names = 0, 0, 0, {}
+        for ev in prof.events():
+            if ev.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            name = ev.name
+            if name.startswith("Memset") or name.startswith("Memcpy"):
+                memops += 1
+            elif "hupr::" in name:
+                hupr += 1
+            else:
+                other += 1
+                names[name[:80]] = names.get(name[:80], 0) + 1
+        if hupr + other == 0:
+            return None
+        return {"hupr": hupr, "other": other, "memset_memcpy_nodes": memops,
+                "other_names": sorted(names.items(), key=lambda kv: -kv[1])[:8]}
+    except Exception as exc:      # no CUPTI on the box, or the profiler refuses graphs
+        return {"error": str(exc)[:200]}
+
+
+def train_probe(dev, world, gen, steps, products):
+    """Data-parallel training evidence inside the default multi-rank run (BASELINE.json configs[3]; reference semantics
+    /root/reference/tools/run.py:74-79): graph-replayed forward+backward at 32 samples per GPU, ONE NCCL all-reduce over the flat
+    gradient buffer, Adam.  Returns per-step and exposed-collective times (CUDA events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from hupr_b200.models import HuPRNet
+    from hupr_b200.training import TrainStep
+    torch.manual_seed(0)
+    model = HuPRNet(make_cfg()).to(dev).train()
+    trainer = TrainStep(model, products=products)
+    b = 32
+    hori = torch.randn((b, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
+    vert = torch.randn((b, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
+    joints = torch.randint(0, 256, (b, 14, 2), generator=gen, device=dev)
+    replay = trainer.capture(hori, vert, joints, with_optimizer=False)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ar_ms, losses = [], []
+
+    def one(timed):
+        loss, _ = replay()
+        if timed:
+            ev[1].record()
+        trainer.all_reduce_gradients()
+        if timed:
+            ev[2].record()
+        trainer.optimizer_step()
+        return loss
+    for _ in range(2):
+        one(False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        losses.append(one(True))
+        torch.cuda.current_stream().synchronize()
+        ar_ms.append(ev[1].elapsed_time(ev[2]))
+    ev[3].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[3]) / steps, sum(ar_ms) / len(ar_ms)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # replicas must stay identical: the all-reduced gradient (and so the weights) agree across ranks to the bit
+    chk = torch.stack([trainer.flat_p.double().sum(), trainer.flat_p.double().abs().max()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ms, ar = float(t[0]), float(t[1])
+    return {"what": "graph-replayed train step (forward+backward) + ONE NCCL sum all-reduce of the flat fp32 gradient buffer + Adam",
+            "samples_per_gpu": b, "global_batch": b * world, "steps": steps, "ms_per_step": ms, "allreduce_ms": ar,
+            "allreduce_bytes": trainer.flat_g.numel() * 4, "samples_per_s": b * world / (ms * 1e-3),
+            "products_per_k_step": products, "replicas_identical": bool(torch.equal(lo, hi)),
+            "loss_first_last": [float(losses[0]), float(losses[-1])]}
+
+
 def run_cascade_sweep(args, dev, world, rank, local_rank, peaks, gen, sync_all):
     """BASELINE.json configs[4]: N radar frames (hori + vert) through hupr_fft_cascade_i16, N/world per rank, in resident chunks.
     The chunk's int16 words are generated once on the device and re-used for every chunk (the arithmetic does not depend on the
@@ -303,6 +390,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="e2e: poses (windows) per GPU per step (default 32); train: samples per GPU (default 32 = the per-GPU shard of configs[3])")
     ap.add_argument("--frames-per-step", type=int, default=1024, help="cascade: radar frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-probe", action="store_true", help="multi-rank e2e runs: skip the data-parallel training probe record")
     ap.add_argument("--single-bf16", action="store_true", help="one bf16 product per k-step instead of the fp32-equivalent 3-product split")
     args = ap.parse_args()
     if args.batch is None:
@@ -371,12 +459,13 @@ def main():
         from hupr_b200.training import TrainStep
         torch.manual_seed(0)
         model = HuPRNet(make_cfg()).to(dev).train()
-        trainer = TrainStep(model)
+        products = 1 if args.single_bf16 else 3
+        trainer = TrainStep(model, products=products)
         units = args.batch
         hori = torch.randn((units, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
         vert = torch.randn((units, 8, 8, 2, 64, 64, 8), generator=gen, device=dev)
         joints = torch.randint(0, 256, (units, 14, 2), generator=gen, device=dev)
-        h_h, h_v = hori.cpu().pin_memory(), vert.cpu().pin_memory()
+        h_h, h_v, h_j = hori.cpu().pin_memory(), vert.cpu().pin_memory(), joints.cpu().pin_memory()
         h_loss = torch.empty(2, dtype=torch.float32).pin_memory()
 
         before = ops.launch_count()
@@ -394,16 +483,22 @@ def main():
                 trainer.optimizer_step()
             return out
 
+        trainer.prefetch(h_h, h_v, h_j)
+
         def e2e_step():
-            hori.copy_(h_h, non_blocking=True)
-            vert.copy_(h_v, non_blocking=True)
+            # public ingest API: the upload of the NEXT batch (copy stream, pinned host tensors) overlaps this step's compute; every step
+            # still moves its own inputs host->device and its two loss scalars device->host inside the timed region
+            trainer.take_prefetched(hori, vert, joints)
+            trainer.prefetch(h_h, h_v, h_j)
             l, l2 = step()
             h_loss[0:1].copy_(l.reshape(1), non_blocking=True)
             h_loss[1:2].copy_(l2.reshape(1), non_blocking=True)
-        e2e_units, h2d, d2h = units, 2 * h_h.numel() * 4, 8
+        e2e_units, h2d, d2h = units, 2 * h_h.numel() * 4 + h_j.numel() * 8, 8
         profile_step = lambda: trainer.forward_backward(hori, vert, joints)
         l2_note = "per-step working set (saved activations + gradients, tens of GB) exceeds the 126 MB L2"
-        dtype = "bf16 tensor-core products, fp32 accumulate (3-product hi/lo split: fp32-equivalent), fp32 master weights / Adam"
+        dtype = ("bf16 tensor-core products, fp32 accumulate, in every convolution / data-gradient / weight-gradient launch (attention and "
+                 "element-wise kernels keep hi/lo inputs), fp32 master weights / Adam" if args.single_bf16 else
+                 "bf16 tensor-core products, fp32 accumulate (3-product hi/lo split: fp32-equivalent), fp32 master weights / Adam")
     else:
         torch.manual_seed(0)
         model = HuPRNet(make_cfg(), split=not args.single_bf16).to(dev).eval()      # random-init weights of the reference architecture
@@ -525,10 +620,31 @@ def main():
                     "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "algorithmic_flops_per_step": conv["flops"],
                     "kernel_ms_per_step": conv["ms"], "share_of_step": conv["ms"] / total_ms,
                     "executed_tensor_tflops": achieved * (1 if args.single_bf16 else 3)}
+        # the other named kernel families of this step against their own rooflines (algorithmic work / CUDA-event time of the family)
+        families = {}
+        for key in ("attention_fwd", "attention_bwd", "conv_wgrad", "matmul_tn"):
+            if key in fam and fam[key]["flops"] > 0:
+                tf = fam[key]["flops"] / (fam[key]["ms"] * 1e-3) / 1e12
+                three = key.startswith("attention") or not args.single_bf16
+                families[key] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                 "executed_frac": tf * (3 if three else 1) / peak, "ms": fam[key]["ms"]}
+        if "fft_cascade_i16" in fam and args.workload == "e2e":
+            n_fs = 2 * (units + 7)
+            gbs = n_fs * (FS_IN_BYTES + FS_OUT_BYTES) / (fam["fft_cascade_i16"]["ms"] * 1e-3) / 1e9
+            families["fft_cascade_i16"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                           "ms": fam["fft_cascade_i16"]["ms"], "frame_sensors": n_fs}
+        roofline["families"] = families
         breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "calls": v["launch_calls"]}
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         breakdown["conv_gemm_by_shape"] = {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2), "calls": v["calls"]}
                                            for k, v in sorted(sub.items(), key=lambda kv: -kv[1]["ms"])}
+
+    kernels = None
+    if args.workload == "train" and rank == 0:
+        kernels = count_graph_kernels(replay)
+    probe = None
+    if world > 1 and args.workload == "e2e" and not args.no_train_probe:
+        probe = train_probe(dev, world, gen, 5, 1 if args.single_bf16 else 3)
 
     if rank == 0:
         cpu = None
@@ -550,6 +666,10 @@ def main():
         }
         if breakdown is not None:
             line["breakdown"] = breakdown
+        if kernels is not None:
+            line["kernels_per_replay"] = kernels
+        if probe is not None:
+            line["train_probe"] = probe
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,6 +31,7 @@ class ConvDesc(ctypes.Structure):
         ("row_vec", ctypes.c_void_p), ("row_mode", ctypes.c_int),
         ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_size_t),
         ("no_tma_store", ctypes.c_int),
+        ("nprod", ctypes.c_int),
     ]
 
 
@@ -73,6 +74,7 @@ class WgradDesc(ctypes.Structure):
         ("pd", ctypes.c_int), ("ph", ctypes.c_int), ("pw", ctypes.c_int),
         ("dw", ctypes.c_void_p), ("dw_ld", ctypes.c_int),
         ("batched", ctypes.c_int), ("dw_batch_stride", ctypes.c_longlong),
+        ("nprod", ctypes.c_int),
     ]
 
 
@@ -127,10 +129,18 @@ SIGNATURES = {
     "hupr_to_kmajor": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong, _P]),
     "hupr_to_kmajor_multi": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, ctypes.c_longlong,
                                             ctypes.c_longlong, _P]),
-    "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "hupr_heatmap_loss_bwd": (ctypes.c_int, [_P, _P, _P, _I, _I, ctypes.c_float, ctypes.c_float, _P, _P, _P]),
+    "hupr_heatmap_bwd": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "hupr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                      ctypes.c_float, _I, _P, _P]),
+                                      ctypes.c_float, _I, _P, _P, _P]),
     "hupr_heatmap_loss_fwd": (ctypes.c_int, [_P, _P, _P, _I, _P, ctypes.c_size_t, _P, _P, _P, _P]),
+    "hupr_pack_conv_weights": (ctypes.c_int, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "hupr_unpack_wgrad": (ctypes.c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "hupr_reduce_f64": (ctypes.c_int, [_P, _I, _I, _P, _P]),
+    "hupr_broadcast_f32": (ctypes.c_int, [_P, _P, _I, _P]),
+    "hupr_gcn_bias_rows": (ctypes.c_int, [_P, _I, _I, _P, _P, _P]),
+    "hupr_bump_i32": (ctypes.c_int, [_P, _P]),
+    "hupr_memset_zero": (ctypes.c_int, [_P, ctypes.c_size_t, _P]),
 }
 
 

@@ -365,11 +365,8 @@ static int encode_rows_map(CUtensorMap* map, const void* base, int row_len, int 
 
 template <int D, int BKV>
 static int launch_attention(const hupr_attn_desc* d, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(attention_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return HUPR_ERR_CUDA;
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    if (int crc = ensure_smem_optin(attention_kernel<D, BKV>, AT_SMEM, configured)) return crc;
     CUtensorMap q_hi, q_lo, k_hi, k_lo, v_hi, v_lo;
     int rc;
     if ((rc = encode_rows_map(&q_hi, d->q_hi, d->q_ld, d->s, d->batch, AT_BM)) != HUPR_OK) return rc;
@@ -404,13 +401,6 @@ extern "C" int hupr_attention_fwd(const hupr_attn_desc* d, void* stream) {
     const uintptr_t align_or = (uintptr_t)d->q_hi | (uintptr_t)d->q_lo | (uintptr_t)d->k_hi | (uintptr_t)d->k_lo | (uintptr_t)d->vt_hi |
                                (uintptr_t)d->vt_lo | (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo;
     if (align_or & 15) return HUPR_ERR_ALIGNMENT;
-    static int arch_ok = 0;
-    if (!arch_ok) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        if (prop.major != 10) return HUPR_ERR_ARCH;
-        arch_ok = 1;
-    }
+    if (int arch_rc = device_check_sm100()) return arch_rc;
     return c == 64 ? launch_attention<64, 128>(d, (cudaStream_t)stream) : launch_attention<128, 64>(d, (cudaStream_t)stream);
 }

@@ -316,19 +316,9 @@ extern "C" int hupr_attention_bwd(const hupr_attn_bwd_desc* d, void* stream) {
                                (uintptr_t)d->do_hi | (uintptr_t)d->do_lo | (uintptr_t)d->lse | (uintptr_t)d->rowdot | (uintptr_t)d->dq | (uintptr_t)d->dk |
                                (uintptr_t)d->dv;
     if (align_or & 15) return HUPR_ERR_ALIGNMENT;
-    static int arch_ok = 0;
-    if (!arch_ok) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        if (prop.major != 10) return HUPR_ERR_ARCH;
-        arch_ok = 1;
-    }
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM) != cudaSuccess) return HUPR_ERR_CUDA;
-        configured = true;
-    }
+    if (int arch_rc = device_check_sm100()) return arch_rc;
+    static bool configured[kMaxDevices] = {};
+    if (int crc = ensure_smem_optin(attention_bwd_kernel, AB_SMEM, configured)) return crc;
     CUtensorMap q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, o_hi, o_lo;
     int rc;
     if ((rc = ab_rows_map(&q_hi, d->q_hi, d->q_ld, d->s, d->batch)) != HUPR_OK) return rc;

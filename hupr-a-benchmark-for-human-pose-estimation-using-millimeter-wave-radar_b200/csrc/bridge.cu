@@ -335,14 +335,7 @@ transpose_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, in
 }
 
 static int check_sm100() {
-    static int cached = -100;
-    if (cached == -100) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
-    }
-    return cached;
+    return device_check_sm100();      // cached per device (capi.cu)
 }
 
 int fast_transpose_dense(const void* in_hi, const void* in_lo, int n, int s, int c, int in_ld, int in_ch_off, void* out_hi, void* out_lo,

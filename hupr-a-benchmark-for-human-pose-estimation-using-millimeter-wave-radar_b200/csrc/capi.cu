@@ -7,6 +7,40 @@ static std::atomic<long long> g_launches{0};
 
 namespace hupr {
 void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int device_index() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+// [device] -> 0 unknown, else 1 + (major * 100000 + SM count); written once per device (benign race: every writer stores the same value)
+static std::atomic<int> g_dev_info[kMaxDevices];
+
+static int device_info() {
+    const int dev = device_index();
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    int v = g_dev_info[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int major = 0, sms = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return 0;
+        v = 1 + major * 100000 + sms;
+        g_dev_info[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+int device_check_sm100() {
+    const int v = device_info();
+    if (v == 0) return HUPR_ERR_CUDA;
+    return (v - 1) / 100000 == 10 ? HUPR_OK : HUPR_ERR_ARCH;
+}
+
+int device_sm_count() {
+    const int v = device_info();
+    return v == 0 ? 0 : (v - 1) % 100000;
+}
 }  // namespace hupr
 
 extern "C" long long hupr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

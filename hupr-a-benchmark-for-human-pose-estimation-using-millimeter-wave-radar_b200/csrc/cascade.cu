@@ -305,19 +305,10 @@ extern "C" int hupr_fft_cascade_i16(const int16_t* adc, void* cube, int n_frame_
     if (n_frame_sensors == 0) return HUPR_OK;
     if (adc == nullptr || cube == nullptr) return HUPR_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(adc) & 15) || (reinterpret_cast<uintptr_t>(cube) & 15)) return HUPR_ERR_ALIGNMENT;
-    static int num_sms = 0;
-    static bool configured = false;
-    if (!configured) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        if (prop.major != 10) return HUPR_ERR_ARCH;
-        num_sms = prop.multiProcessorCount;
-        if (cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_CASCADE_TOTAL) != cudaSuccess)
-            return HUPR_ERR_CUDA;
-        configured = true;
-    }
+    if (int arch_rc = device_check_sm100()) return arch_rc;
+    const int num_sms = device_sm_count();
+    static bool configured[kMaxDevices] = {};
+    if (int crc = ensure_smem_optin(cascade_kernel, SM_CASCADE_TOTAL, configured)) return crc;
     int clusters = num_sms / 2;
     if (clusters > n_frame_sensors) clusters = n_frame_sensors;
     cascade_kernel<<<2 * clusters, kCascadeThreads, SM_CASCADE_TOTAL, static_cast<cudaStream_t>(stream)>>>(

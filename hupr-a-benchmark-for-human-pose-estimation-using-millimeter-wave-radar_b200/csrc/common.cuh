@@ -16,6 +16,23 @@
 namespace hupr {
 
 void note_launches(int n);   // capi.cu: kernel-launch counter behind hupr_launch_count()
+// Per-device host-side caches (capi.cu).  A process may drive several GPUs (one after the other or from several threads), and both the
+// architecture check and cudaFuncSetAttribute(MaxDynamicSharedMemorySize) are per-device state, so nothing here is cached process-wide.
+constexpr int kMaxDevices = 64;
+int device_index();            // current CUDA device ordinal, or -1
+int device_check_sm100();      // HUPR_OK on an sm_100 device, HUPR_ERR_ARCH otherwise (HUPR_ERR_CUDA if the query fails)
+int device_sm_count();         // multiprocessor count of the current device (0 if the query fails)
+// Opt-in dynamic shared memory for `func` on the current device, once per (kernel, device): `flags` is a per-kernel static array.
+template <typename F>
+static inline int ensure_smem_optin(F func, int bytes, bool (&flags)[kMaxDevices]) {
+    const int dev = device_index();
+    if (dev < 0 || dev >= kMaxDevices) return HUPR_ERR_CUDA;
+    if (!flags[dev]) {
+        if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return HUPR_ERR_CUDA;
+        flags[dev] = true;
+    }
+    return HUPR_OK;
+}
 
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }

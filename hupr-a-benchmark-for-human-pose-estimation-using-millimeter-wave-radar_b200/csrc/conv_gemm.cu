@@ -378,18 +378,10 @@ template <int BN, int NPROD, bool TSTORE>
 static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const ConvParams& p, int m_tiles, cudaStream_t stream) {
     using Cfg = ConvCfg<BN, NPROD, TSTORE>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(conv_gemm_kernel<BN, NPROD, TSTORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
-            cudaSuccess)
-            return HUPR_ERR_CUDA;
-        configured = true;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-    }
+    static bool configured[kMaxDevices] = {};
+    if (int crc = ensure_smem_optin(conv_gemm_kernel<BN, NPROD, TSTORE>, Cfg::kSmemBytes, configured)) return crc;
+    const int num_sms = device_sm_count();
+    if (num_sms <= 0) return HUPR_ERR_CUDA;
     ConvParams pp = p;
     pp.m_tiles = m_tiles;
     pp.n_tiles = p.cout / BN;
@@ -436,7 +428,9 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
 extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     using namespace hupr;
     if (!d || !d->a_hi || !d->w_hi) return HUPR_ERR_BAD_ARG;
-    if ((d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    if (d->nprod != 0 && d->nprod != 1 && d->nprod != 3) return HUPR_ERR_BAD_ARG;
+    if (d->nprod != 1 && (d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
+    if (d->nprod == 3 && !d->a_lo) return HUPR_ERR_BAD_ARG;
     if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
     if (d->a_n_stride < 0 || d->a_n_stride % 8) return HUPR_ERR_BAD_ARG;
     if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > ((d->ca + BK - 1) / BK) * BK) return HUPR_ERR_BAD_ARG;
@@ -499,7 +493,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
     const __nv_bfloat16* w_lo = d->w_lo ? static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off : nullptr;
     if ((rc = encode_wgt_map(&b_hi, w_hi, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
-    const bool split = d->a_lo != nullptr;
+    const bool split = d->a_lo != nullptr && d->w_lo != nullptr && d->nprod != 1;      // nprod == 1: the lo planes are not read
     if (split) {
         if ((rc = encode_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh, d->a_n_stride)) != HUPR_OK) return rc;
         if ((rc = encode_wgt_map(&b_lo, w_lo, d->cin, d->cout, wdim2, bn, w_ld)) != HUPR_OK) return rc;
@@ -512,9 +506,10 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     const int m_tiles = (int)m_tiles_ll;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // row tiles with bf16 split output and enough tiles to fill the GPU: TMA-store epilogue
-    const bool tstore = split && bw == BM && d->o_hi && d->o_lo && !d->o_f32 && !p.atomic && m_tiles_ll * (d->cout / bn) >= 148 &&
+    const bool tstore = bw == BM && d->o_hi && d->o_lo && !d->o_f32 && !p.atomic && m_tiles_ll * (d->cout / bn) >= 148 &&
                         (long long)d->n * d_out * d->h * d->w < 2147483647LL && !d->no_tma_store;
-    if (tstore) return bn == 128 ? launch_conv<128, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    if (tstore && split) return bn == 128 ? launch_conv<128, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
+    if (tstore) return bn == 128 ? launch_conv<128, 1, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
     if (bn == 128) return split ? launch_conv<128, 3, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<128, 1, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
     return split ? launch_conv<64, 3, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
 }

@@ -13,6 +13,8 @@
 //   * the kernel is persistent (one CTA per SM walks the tiles) with two accumulator sets in TMEM, so the epilogue of one tile
 //     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
+#include <stdlib.h>
+
 #include "tc.cuh"
 #include "conv_common.cuh"
 
@@ -26,7 +28,8 @@ struct HaloGeom {
     int halo_rows;                 // (bh + 2) * bw
     int a_plane_bytes;             // halo_rows * 64
     int b_tile_bytes;              // BN * 64
-    int stage_bytes;               // 2 * a_plane_bytes + 6 * b_tile_bytes
+    int nprod;                     // 3: hi/lo planes, three products per k-step; 1: hi planes only
+    int stage_bytes;               // planes * (a_plane_bytes + 3 * b_tile_bytes), planes = 2 (nprod 3) or 1
     int stages;
     int tap_stride_bytes;          // bw * 64: one h-row of the halo
     int acc_stride_bytes;          // (bh / 2) * bw * 64: first row of accumulator 1
@@ -62,6 +65,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
+    const bool three = g.nprod == 3;
     const int total_tiles = g.m_tiles * g.n_tiles;
 
     if (threadIdx.x == 0) {
@@ -111,13 +115,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
                     const int ac = p.a_ch_off + cb * HK;
                     tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                    tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                    uint8_t* sb = st + 2 * g.a_plane_bytes;
+                    if (three) tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                    uint8_t* sb = st + (three ? 2 : 1) * g.a_plane_bytes;
 #pragma unroll
                     for (int tkh = 0; tkh < 3; ++tkh) {
                         const int tap = (tkd * 3 + tkh) * p.kw + tkw;
                         tma_load_3d(sb + tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
-                        tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                        if (three) tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
                     }
                 }
             }
@@ -138,7 +142,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * g.stage_bytes);
-                    const uint32_t sb = st + 2 * g.a_plane_bytes;
+                    const uint32_t sb = st + (three ? 2 : 1) * g.a_plane_bytes;
 #pragma unroll
                     for (int tkh = 0; tkh < 3; ++tkh) {
                         const uint64_t db_hi = make_smem_desc_sw64(sb + tkh * g.b_tile_bytes);
@@ -152,9 +156,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                             for (int k = 0; k < HK / 16; ++k) {
                                 const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
-                                umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, (gi | tkh | k) != 0);
-                                umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
-                                umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                                const uint32_t acc_flag = (gi | tkh | k) != 0;
+                                if (three) {
+                                    umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
+                                    umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                                    umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                                } else {
+                                    umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, acc_flag);
+                                }
                             }
                         }
                     }
@@ -229,19 +238,13 @@ static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int 
 template <int BN>
 static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
-    static bool configured = false;
+    static bool configured[kMaxDevices] = {};
     const int smem_max = 232448;
-    if (!configured) {
-        if (cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) return HUPR_ERR_CUDA;
-        configured = true;
-    }
+    if (int crc = ensure_smem_optin(conv_halo_kernel<BN>, smem_max, configured)) return crc;
     const int smem = g.stages * g.stage_bytes + 1024 + 256;
     if (smem > smem_max) return HUPR_ERR_BAD_ARG;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-    }
+    const int num_sms = device_sm_count();
+    if (num_sms <= 0) return HUPR_ERR_CUDA;
     HaloGeom gg = g;
     gg.m_tiles = m_tiles;
     gg.n_tiles = p.cout / BN;
@@ -255,7 +258,9 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
 // Returns HUPR_OK after launching, or a positive value (1) if the shape is not handled here (caller falls through to the
 // generic kernel).  Arguments were validated by hupr_conv_gemm.
 int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream) {
-    if (d->a_lo == nullptr || d->w_batched || d->k_split > 1 || d->w_k_off != 0) return 1;
+    const bool three = d->a_lo != nullptr && d->w_lo != nullptr && d->nprod != 1;
+    if (d->w_batched || d->k_split > 1 || d->w_k_off != 0) return 1;
+    if (!three && getenv("HUPR_HALO1_OFF")) return 1;      // A/B switch: single-product convolutions on the generic kernel
     if (d->kh != 3 || d->ph != 1 || d->kw != 2 * d->pw + 1) return 1;
     if (d->w != 16 && d->w != 32 && d->w != 64) return 1;
     const int bw = d->w, bh = HM / bw;
@@ -276,7 +281,8 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     g.halo_rows = (bh + 2) * bw;
     g.a_plane_bytes = g.halo_rows * 64;
     g.b_tile_bytes = bn * 64;
-    g.stage_bytes = 2 * g.a_plane_bytes + 6 * g.b_tile_bytes;
+    g.nprod = three ? 3 : 1;
+    g.stage_bytes = (three ? 2 : 1) * (g.a_plane_bytes + 3 * g.b_tile_bytes);
     g.stages = (232448 - 1024 - 256) / g.stage_bytes;
     if (g.stages > 4) g.stages = 4;
     if (g.stages < 2) return 1;
@@ -287,11 +293,11 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     const int taps = d->kd * d->kh * d->kw;
     const int w_ld = d->w_ld ? d->w_ld : d->cin;
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
-    const __nv_bfloat16* w_lo = static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off;
+    const __nv_bfloat16* w_lo = three ? static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off : w_hi;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
-    if ((rc = encode_halo_act_map(&a_lo, d->a_lo, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
+    if ((rc = encode_halo_act_map(&a_lo, three ? d->a_lo : d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
     return bn == 128 ? launch_halo<128>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)

@@ -111,14 +111,7 @@ gcn_heads_kernel(const float* __restrict__ y, int y_ld, float* __restrict__ gcn_
 }
 
 static int gcn_check_sm100() {
-    static int cached = -100;
-    if (cached == -100) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
-    }
-    return cached;
+    return device_check_sm100();      // cached per device (capi.cu)
 }
 
 }  // namespace hupr

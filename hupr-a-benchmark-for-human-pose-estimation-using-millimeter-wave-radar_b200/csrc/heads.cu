@@ -266,14 +266,7 @@ __global__ void loss_final_kernel(const double* __restrict__ partial, int maps, 
 }
 
 static int heads_check_sm100() {
-    static int cached = -100;
-    if (cached == -100) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
-    }
-    return cached;
+    return device_check_sm100();      // cached per device (capi.cu)
 }
 
 }  // namespace hupr
@@ -371,7 +364,7 @@ extern "C" int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heat
 }
 
 // ================================================================================================================================
-// Training building blocks (row a-17 of SURVEY.md §8; the full backward pass is not assembled yet — DESIGN.md §8).
+// Training building blocks (row a-17 of SURVEY.md §8; assembled into the whole backward pass by hupr_b200/training.py — DESIGN.md §3b).
 //   hupr_heatmap_loss_bwd  d(loss1 + loss2)/d(logits) through BCE(mean) and the sigmoids  (reference: autograd of misc/losses.py:23-48)
 //   hupr_adam_step         torch.optim.Adam with coupled L2 weight decay on a flat fp32 buffer (reference: tools/base.py:47)
 // ================================================================================================================================
@@ -386,27 +379,44 @@ __device__ __forceinline__ float bce_sigmoid_grad(float p, float t, float inv_n)
 // One CTA per (b, k) map.  d_heat_logits: channels-last [B][4096][ld] (the head conv's output layout); d_gcn_pre: [B][14][64][64].
 __global__ void __launch_bounds__(256)
 loss_bwd_kernel(const float* __restrict__ heatmap, const float* __restrict__ gcn, const long long* __restrict__ joints, int ld,
-                float inv_n, float* __restrict__ d_heat_logits, float* __restrict__ d_gcn_pre) {
+                float inv_n1, float inv_n2, float* __restrict__ d_heat_logits, float* __restrict__ d_gcn_pre) {
     const int bk = blockIdx.x;
     const int b = bk / kJ, k = bk % kJ;
     int mx, my;
     const bool valid = joint_center(joints, bk, mx, my);
     for (int i = threadIdx.x; i < 4096; i += 256) {
         const float t = target_value(valid, mx, my, i & 63, i >> 6);
-        d_heat_logits[((size_t)b * 4096 + i) * ld + k] = bce_sigmoid_grad(__ldg(heatmap + (size_t)bk * 4096 + i), t, inv_n);
-        d_gcn_pre[(size_t)bk * 4096 + i] = bce_sigmoid_grad(__ldg(gcn + (size_t)bk * 4096 + i), t, inv_n);
+        d_heat_logits[((size_t)b * 4096 + i) * ld + k] = bce_sigmoid_grad(__ldg(heatmap + (size_t)bk * 4096 + i), t, inv_n1);
+        d_gcn_pre[(size_t)bk * 4096 + i] = bce_sigmoid_grad(__ldg(gcn + (size_t)bk * 4096 + i), t, inv_n2);
+    }
+}
+
+// Sigmoid backward for caller-supplied output gradients (the autograd bridge of HuPRNet.forward in train() mode): g_* are dL/d(post-sigmoid
+// maps) [B][14][64][64]; writes dL/d(pre-sigmoid) in the layouts loss_bwd_kernel uses.
+__global__ void __launch_bounds__(256)
+heatmap_bwd_kernel(const float* __restrict__ heatmap, const float* __restrict__ gcn, const float* __restrict__ g_heat,
+                   const float* __restrict__ g_gcn, int ld, float* __restrict__ d_heat_logits, float* __restrict__ d_gcn_pre) {
+    const int bk = blockIdx.x;
+    const int b = bk / kJ, k = bk % kJ;
+    for (int i = threadIdx.x; i < 4096; i += 256) {
+        const size_t at = (size_t)bk * 4096 + i;
+        const float h = __ldg(heatmap + at), s = __ldg(gcn + at);
+        d_heat_logits[((size_t)b * 4096 + i) * ld + k] = g_heat ? __ldg(g_heat + at) * h * (1.0f - h) : 0.0f;
+        d_gcn_pre[at] = g_gcn ? __ldg(g_gcn + at) * s * (1.0f - s) : 0.0f;
     }
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-            float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float weight_decay, float lr,
-            const int* __restrict__ step_dev) {
+            float step_size, float bc2_sqrt, float beta1, float beta2, float eps, float weight_decay, float lr, double bc1,
+            const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
     if (step_dev) {      // step count lives on the device (CUDA-graph replays): derive the bias corrections here
         const double t = (double)__ldg(step_dev);
-        step_size = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+        bc1 = 1.0 - pow((double)beta1, t);
         bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
     }
+    if (lr_dev) lr = __ldg(lr_dev);      // learning rate lives on the device: a schedule keeps working under CUDA-graph replay
+    if (step_dev || lr_dev) step_size = (float)((double)lr / bc1);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const float pi = p[i];
         const float gi = fmaf(weight_decay, pi, g[i]);            // coupled L2: grad += wd * param
@@ -421,21 +431,33 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 }  // namespace hupr
 
+extern "C" int hupr_heatmap_bwd(const float* heatmap, const float* gcn_heatmap, const float* g_heat, const float* g_gcn, int batch, int ld,
+                                float* d_heat_logits, float* d_gcn_pre, void* stream) {
+    if (batch < 0) return HUPR_ERR_BAD_ARG;
+    if (batch == 0) return HUPR_OK;
+    if (!heatmap || !gcn_heatmap || !d_heat_logits || !d_gcn_pre || ld < kJ) return HUPR_ERR_BAD_ARG;
+    int rc = heads_check_sm100();
+    if (rc != HUPR_OK) return rc;
+    heatmap_bwd_kernel<<<batch * kJ, 256, 0, (cudaStream_t)stream>>>(heatmap, gcn_heatmap, g_heat, g_gcn, ld, d_heat_logits, d_gcn_pre);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
 extern "C" int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
-                                     float* d_heat_logits, float* d_gcn_pre, void* stream) {
+                                     float w1, float w2, float* d_heat_logits, float* d_gcn_pre, void* stream) {
     if (batch < 0) return HUPR_ERR_BAD_ARG;
     if (batch == 0) return HUPR_OK;
     if (!heatmap || !gcn_heatmap || !joints || !d_heat_logits || !d_gcn_pre || ld < kJ) return HUPR_ERR_BAD_ARG;
     int rc = heads_check_sm100();
     if (rc != HUPR_OK) return rc;
     const float inv_n = 1.0f / ((float)batch * kJ * 4096.0f);
-    loss_bwd_kernel<<<batch * kJ, 256, 0, (cudaStream_t)stream>>>(heatmap, gcn_heatmap, joints, ld, inv_n, d_heat_logits, d_gcn_pre);
+    loss_bwd_kernel<<<batch * kJ, 256, 0, (cudaStream_t)stream>>>(heatmap, gcn_heatmap, joints, ld, w1 * inv_n, w2 * inv_n, d_heat_logits, d_gcn_pre);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
 extern "C" int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream) {
+                              float beta2, float eps, float weight_decay, int step, const int* step_dev, const float* lr_dev, void* stream) {
     if (n < 0 || (step < 1 && !step_dev)) return HUPR_ERR_BAD_ARG;
     if (step < 1) step = 1;
     if (n == 0) return HUPR_OK;
@@ -446,7 +468,7 @@ extern "C" int hupr_adam_step(float* params, const float* grads, float* exp_avg,
     long long blocks = (n + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)((double)lr / bc1),
-                                                                    (float)sqrt(bc2), beta1, beta2, eps, weight_decay, lr, step_dev);
+                                                                    (float)sqrt(bc2), beta1, beta2, eps, weight_decay, lr, bc1, step_dev, lr_dev);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

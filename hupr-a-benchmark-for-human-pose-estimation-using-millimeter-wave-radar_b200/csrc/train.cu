@@ -345,14 +345,7 @@ softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p_hi, const __nv_bfloa
 }
 
 static int train_check_sm100() {
-    static int cached = -100;
-    if (cached == -100) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
-    }
-    return cached;
+    return device_check_sm100();      // cached per device (capi.cu)
 }
 
 static inline TView mk_view(const hupr_tensor_view* v) {

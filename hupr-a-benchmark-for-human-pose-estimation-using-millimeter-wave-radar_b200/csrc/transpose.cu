@@ -77,14 +77,7 @@ tile_transpose_kernel(const uint16_t* __restrict__ src_hi, const uint16_t* __res
 }
 
 static int tt_check_sm100() {
-    static int cached = -100;
-    if (cached == -100) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        cached = (prop.major == 10) ? HUPR_OK : HUPR_ERR_ARCH;
-    }
-    return cached;
+    return device_check_sm100();      // cached per device (capi.cu)
 }
 
 // Dense [n][s][ld] (channels ch_off .. +c) -> [n][c][s].  Caller guarantees s % 64 == 0, c % 64 == 0, 16-byte aligned rows.

@@ -53,6 +53,7 @@ struct WgParams {
     float* out;
     int out_ld;
     long long out_batch_stride;            // batched mode: the samples are independent problems, dw[sample] = out + sample * stride
+    int nprod;                             // 3: hi/lo planes, three products per k-step; 1: hi planes only (lo regions of a stage stay unused)
 };
 
 // MN-major, SWIZZLE_128B operand: rows (K) of 128 B = 64 channels; 8-row groups SBO = 1024 B apart; 64-channel atoms LBO apart.
@@ -88,6 +89,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool three = p.nprod == 3;
 
     // work item: (sample [batched mode], split-K slice, column tile of cout, group of accumulator slots)
     int item = blockIdx.x;
@@ -128,17 +130,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
                 const int n = sample + t / p.d_out;
                 const int i = kb - kb_begin, yb = i & 1;
                 mbar_wait(&y_empty[yb], (uint32_t)(((i >> 1) & 1) ^ 1));
-                mbar_expect_tx(&y_full[yb], Cfg::kYBytes);
+                mbar_expect_tx(&y_full[yb], three ? Cfg::kYBytes : Cfg::kYBytes / 2);
                 uint8_t* ys = sm_y + yb * Cfg::kYBytes;
 #pragma unroll
                 for (int j = 0; j < Cfg::kYAtoms; ++j) {
                     tma_load_5d(ys + j * WG_ATOM, &tmY_hi, &y_full[yb], p.y_ch_off + n0 + 64 * j, w0, h0, od, n);
-                    tma_load_5d(ys + (Cfg::kYAtoms + j) * WG_ATOM, &tmY_lo, &y_full[yb], p.y_ch_off + n0 + 64 * j, w0, h0, od, n);
+                    if (three) tma_load_5d(ys + (Cfg::kYAtoms + j) * WG_ATOM, &tmY_lo, &y_full[yb], p.y_ch_off + n0 + 64 * j, w0, h0, od, n);
                 }
                 for (int sl = 0; sl < nslots; ++sl, ++it) {
                     const int s = it % Cfg::kStages;
                     mbar_wait(&a_empty[s], (uint32_t)(((it / Cfg::kStages) & 1) ^ 1));
-                    mbar_expect_tx(&a_full[s], Cfg::kABytes);
+                    mbar_expect_tx(&a_full[s], three ? Cfg::kABytes : Cfg::kABytes / 2);
                     uint8_t* as = sm_a + s * Cfg::kABytes;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -148,7 +150,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
                         const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
                         const int xc = p.x_ch_off + cb * 64, xw = w0 + tkw - p.pw, xh = h0 + tkh - p.ph, xd = od + tkd - p.pd;
                         tma_load_5d(as + half * WG_ATOM, &tmX_hi, &a_full[s], xc, xw, xh, xd, n);
-                        tma_load_5d(as + (2 + half) * WG_ATOM, &tmX_lo, &a_full[s], xc, xw, xh, xd, n);
+                        if (three) tma_load_5d(as + (2 + half) * WG_ATOM, &tmX_lo, &a_full[s], xc, xw, xh, xd, n);
                     }
                 }
             }
@@ -177,9 +179,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
                         const uint64_t da_lo = make_smem_desc_mn(as + 2 * WG_ATOM + koff, WG_ATOM);
                         const uint64_t dy_hi = make_smem_desc_mn(ys + koff, WG_ATOM);
                         const uint64_t dy_lo = make_smem_desc_mn(ys + Cfg::kYAtoms * WG_ATOM + koff, WG_ATOM);
-                        umma_bf16(tacc, da_lo, dy_hi, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
-                        umma_bf16(tacc, da_hi, dy_lo, idesc, 1u);
-                        umma_bf16(tacc, da_hi, dy_hi, idesc, 1u);
+                        const uint32_t acc_flag = (kb != kb_begin || k != 0) ? 1u : 0u;
+                        if (three) {
+                            umma_bf16(tacc, da_lo, dy_hi, idesc, acc_flag);
+                            umma_bf16(tacc, da_hi, dy_lo, idesc, 1u);
+                            umma_bf16(tacc, da_hi, dy_hi, idesc, 1u);
+                        } else {
+                            umma_bf16(tacc, da_hi, dy_hi, idesc, acc_flag);
+                        }
                     }
                     tc_commit(&a_empty[s]);
                 }
@@ -235,11 +242,8 @@ template <int BN>
 static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi, const CUtensorMap& y_lo, WgParams p,
                         int cout, int problems, int num_sms, cudaStream_t stream) {
     using Cfg = WgCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return HUPR_ERR_CUDA;
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    if (int crc = ensure_smem_optin(wgrad_kernel<BN>, Cfg::kSmemBytes, configured)) return crc;
     p.groups = (p.slots + Cfg::kSlots - 1) / Cfg::kSlots;
     p.n_tiles = cout / BN;
     const long long tiles = (long long)p.groups * p.n_tiles * problems;
@@ -259,7 +263,10 @@ static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const 
 
 extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     using namespace hupr;
-    if (!d || !d->x_hi || !d->x_lo || !d->dy_hi || !d->dy_lo || !d->dw) return HUPR_ERR_BAD_ARG;
+    if (!d || !d->x_hi || !d->dy_hi || !d->dw) return HUPR_ERR_BAD_ARG;
+    if (d->nprod != 0 && d->nprod != 1 && d->nprod != 3) return HUPR_ERR_BAD_ARG;
+    const bool three = d->nprod != 1;
+    if (three && (!d->x_lo || !d->dy_lo)) return HUPR_ERR_BAD_ARG;
     if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
     if (d->kd <= 0 || d->kh <= 0 || d->kw <= 0 || d->pd < 0) return HUPR_ERR_BAD_ARG;
     if (d->kh != 2 * d->ph + 1 || d->kw != 2 * d->pw + 1) return HUPR_ERR_BAD_ARG;            // H, W are 'same' convolutions
@@ -273,16 +280,10 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     if (WG_KB % bw || d->w % bw) return HUPR_ERR_BAD_ARG;
     const int bh = WG_KB / bw;
     if (d->h % bh) return HUPR_ERR_BAD_ARG;
-    const uintptr_t align_or = (uintptr_t)d->x_hi | (uintptr_t)d->x_lo | (uintptr_t)d->dy_hi | (uintptr_t)d->dy_lo | (uintptr_t)d->dw;
+    const uintptr_t align_or = (uintptr_t)d->x_hi | (uintptr_t)(three ? d->x_lo : nullptr) | (uintptr_t)d->dy_hi | (uintptr_t)(three ? d->dy_lo : nullptr) | (uintptr_t)d->dw;
     if (align_or & 15) return HUPR_ERR_ALIGNMENT;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return HUPR_ERR_CUDA;
-        if (prop.major != 10) return HUPR_ERR_ARCH;
-        num_sms = prop.multiProcessorCount;
-    }
+    if (int arch_rc = device_check_sm100()) return arch_rc;
+    const int num_sms = device_sm_count();
     const int problems = d->batched ? d->n : 1;
     if (d->batched && (d->dw_batch_stride < 0 || d->dw_batch_stride % 4)) return HUPR_ERR_BAD_ARG;
     const long long kblocks = (long long)(d->batched ? 1 : d->n) * d_out * (d->h / bh) * (d->w / bw);
@@ -298,13 +299,14 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     p.groups = 0; p.n_tiles = 0;
     p.kblocks = (int)kblocks; p.kb_per_split = 0; p.k_split = 0;
     p.out = d->dw; p.out_ld = d->dw_ld; p.out_batch_stride = d->batched ? d->dw_batch_stride : 0;
+    p.nprod = three ? 3 : 1;
 
     CUtensorMap x_hi, x_lo, y_hi, y_lo;
     int rc;
     if ((rc = encode_pos_map(&x_hi, d->x_hi, d->cx, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
-    if ((rc = encode_pos_map(&x_lo, d->x_lo, d->cx, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
+    if ((rc = encode_pos_map(&x_lo, three ? d->x_lo : d->x_hi, d->cx, d->w, d->h, d->d, d->n, bw, bh)) != HUPR_OK) return rc;
     if ((rc = encode_pos_map(&y_hi, d->dy_hi, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
-    if ((rc = encode_pos_map(&y_lo, d->dy_lo, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
+    if ((rc = encode_pos_map(&y_lo, three ? d->dy_lo : d->dy_hi, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (d->cout % 256 == 0) return launch_wgrad<256>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
     if (d->cout % 128 == 0) return launch_wgrad<128>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);

@@ -81,7 +81,9 @@ class HuPR3D_horivert(data.Dataset):
         self.gtFile = generateGTAnnot(cfg, phase)
         with open(self.gtFile) as fp:
             gt = json.load(fp)
-        self.imageIds = sorted(img["id"] for img in gt["images"])          # COCO.getImgIds() order
+        # COCO.getImgIds() with no filter returns list(self.imgs.keys()): the FILE's insertion order (not sorted — train/val/test name lists are
+        # not ascending), so dataset index i addresses the same sample as in the reference (dataset.py:38; sampling_ratio, seeded shuffles)
+        self.imageIds = list(dict.fromkeys(img["id"] for img in gt["images"]))
         by_image = collections.defaultdict(list)
         for ann in gt["annotations"]:
             if not ann.get("iscrowd", 0):

@@ -6,7 +6,8 @@ convention (losses.py:23-45): ``loss``/``loss2`` are 0-dim float32 tensors on th
 arrays ``[B, 14, 2]`` of heatmap-pixel (x, y).  The reference synthesises the Gaussian targets on the CPU, copies them to the GPU
 and copies the heatmaps back for a numpy argmax; here one kernel pair (``hupr_heatmap_loss_fwd``) builds the targets on the fly and
 reduces both BCE terms, and ``hupr_keypoints_argmax`` decodes the keypoints — the only D2H traffic is the ``[B,14,2]`` results.
-Forward only: the loss tensors carry no autograd graph (the training backward is not built yet).
+The loss tensors carry no autograd graph: training differentiates the same loss inside ``hupr_b200.training.TrainStep``
+(``hupr_heatmap_loss_bwd``), or through ``HuPRNet.forward`` in ``train()`` mode, whose outputs are autograd-connected (models/networks.py).
 """
 import numpy as np
 import torch
@@ -37,6 +38,29 @@ def get_max_preds(batch_heatmaps):
     return preds.cpu().numpy(), maxvals.unsqueeze(-1).cpu().numpy()
 
 
+class _HeatmapBCE(torch.autograd.Function):
+    """loss = w1*BCE(heat, T) + w2*BCE(gcn, T) and loss2 = BCE(gcn, T) as autograd nodes over the library kernels: forward =
+    hupr_heatmap_loss_fwd (targets synthesised on the fly), backward = the closed form of nn.BCELoss's gradient, (p - T) / (p (1 - p)) / N
+    with torch's 1e-12 clamp — so ``loss.backward()`` of the reference loop (tools/run.py:77-78) reaches HuPRNet's train-mode outputs."""
+
+    @staticmethod
+    def forward(ctx, heat, gcn, joints, w1, w2):
+        losses, gt2d, targets = ops.heatmap_loss_fwd(heat.detach(), gcn.detach(), joints, want_targets=True)
+        ctx.save_for_backward(heat.detach(), gcn.detach(), targets)
+        ctx.w = (float(w1), float(w2))
+        ctx.mark_non_differentiable(gt2d)
+        return w1 * losses[2] + w2 * losses[1], losses[1].clone(), gt2d
+
+    @staticmethod
+    def backward(ctx, g_loss, g_loss2, _g_gt2d):
+        heat, gcn, targets = ctx.saved_tensors
+        w1, w2 = ctx.w
+        inv_n = 1.0 / heat.numel()
+        dh = (heat - targets) / (heat * (1.0 - heat)).clamp_min(1e-12) * (g_loss * (w1 * inv_n))
+        dg = (gcn - targets) / (gcn * (1.0 - gcn)).clamp_min(1e-12) * ((g_loss * w2 + g_loss2) * inv_n)
+        return dh, dg, None, None, None
+
+
 class LossComputer(object):
     def __init__(self, cfg, device):
         self.device = device
@@ -58,15 +82,18 @@ class LossComputer(object):
         b = gt.size(0)
         heat = heat.reshape(b, self.numKeypoints, self.height, self.width).contiguous()
         gcn = gcn.reshape(b, self.numKeypoints, self.height, self.width).contiguous()
-        losses, gt2d, _ = ops.heatmap_loss_fwd(heat, gcn, gt)
-        pred2d = ops.keypoints_argmax(gcn)
         if self.alpha < 1.0:
             self.alpha += self.lossDecay
             self.beta -= self.lossDecay
-        if self.lossDecay != -1:
-            loss = self.alpha * losses[2] + self.beta * losses[1]
+        w1, w2 = (self.alpha, self.beta) if self.lossDecay != -1 else (1.0, 1.0)
+        if torch.is_grad_enabled() and (heat.requires_grad or gcn.requires_grad):
+            # train-mode predictions of HuPRNet.forward carry an autograd graph: keep the loss connected to it
+            loss, loss2, gt2d = _HeatmapBCE.apply(heat, gcn, gt, w1, w2)
         else:
-            loss = losses[0]
+            losses, gt2d, _ = ops.heatmap_loss_fwd(heat, gcn, gt)
+            loss2 = losses[1]
+            loss = w1 * losses[2] + w2 * losses[1] if self.lossDecay != -1 else losses[0]
+        pred2d = ops.keypoints_argmax(gcn.detach())
         if not host:
-            return loss, losses[1], pred2d, gt2d
-        return loss, losses[1], pred2d.cpu().numpy(), gt2d.cpu().numpy()
+            return loss, loss2, pred2d, gt2d
+        return loss, loss2, pred2d.cpu().numpy(), gt2d.cpu().numpy()

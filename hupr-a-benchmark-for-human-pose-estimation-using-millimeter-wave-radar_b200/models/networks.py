@@ -6,8 +6,12 @@ networks.py:17-21), so reference checkpoints load unchanged.  The arithmetic is 
 libhupr_b200.so (MNet kernel, tcgen05 implicit-GEMM convolutions / attention matmuls, resampling, softmax, fused PRGCN).
 There is no CPU path — calling ``forward`` without a B200 raises.
 
-Inference semantics only (``model.eval()``: BatchNorm uses running statistics, reference tools/run.py:36); the training
-backward is not part of this module yet.
+``model.eval()`` (BatchNorm uses running statistics, reference tools/run.py:36) runs the planned inference launch sequence below.
+``model.train()`` routes ``forward`` through ``hupr_b200.training.TrainStep`` (batch statistics, running-stat updates) and returns
+outputs that are connected to the parameters by a ``torch.autograd.Function`` whose backward is TrainStep's hand-written backward
+pass — so the reference loop ``preds = model(h, v); loss.backward(); optimizer.step()`` (tools/run.py:76-79) drives this module with
+any torch optimiser.  The fused path (``TrainStep.forward_backward`` + ``hupr_adam_step``, one CUDA graph) is what ``Runner`` and
+``bench.py`` use.
 """
 import math
 
@@ -81,6 +85,25 @@ def _block2d(root, name, cin, cout):
     _register(root, name + ".relu.weight", torch.full((1,), 0.25), "param")
 
 
+class _TrainForward(torch.autograd.Function):
+    """Autograd bridge of the train-mode forward: forward = TrainStep.forward, backward = TrainStep.backward (every parameter gradient
+    computed by the library in one pass), handed to autograd as the gradients of the parameter inputs."""
+
+    @staticmethod
+    def forward(ctx, step, hori, vert, *params):
+        heat, gcn = step.forward(hori, vert)
+        ctx.step = step
+        ctx.names = [n for n, _ in step.model.named_parameters()]
+        return heat, gcn
+
+    @staticmethod
+    def backward(ctx, g_heat, g_gcn):
+        step = ctx.step
+        step.backward(g_heat, g_gcn)
+        grads = tuple(step.gview[n].clone() for n in ctx.names)      # the flat gradient buffer is overwritten by the next backward
+        return (None, None, None) + grads
+
+
 class HuPRNet(nn.Module):
     def __init__(self, cfg, split=True):
         """``split=True``: bf16 hi/lo activations and weights, three tensor-core products per k-step — fp32-equivalent
@@ -130,6 +153,7 @@ class HuPRNet(nn.Module):
                 _conv(self, dec + ".%s.%d" % (name, i), c, c, (1, 1), False)
         self._packed = None
         self._plans = {}
+        self._train_step = None      # the TrainStep that owns this model's flat parameter buffer (set by TrainStep.__init__)
 
     # ------------------------------------------------------------------------------------------ weights
     def load_state_dict(self, state_dict, strict=True, **kwargs):
@@ -140,6 +164,7 @@ class HuPRNet(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         out = super(HuPRNet, self)._apply(fn, *args, **kwargs)
         self.invalidate()
+        self._train_step = None      # parameter storage was replaced: a TrainStep's flat views are stale
         return out
 
     def invalidate(self):
@@ -174,6 +199,7 @@ class HuPRNet(nn.Module):
                 "enc_ra": L.EncoderBuffers(batch, nf, g, dev, self.split),
                 "enc_re": L.EncoderBuffers(batch, nf, g, dev, self.split),
                 "dec": L.DecoderBuffers(batch, nf, self.numKeypoints, dev, self.split),
+                "coop": ops.CoopWorkspaces(dev),      # split-K scratch of this plan's launch sequence (slot 1 = side stream)
             }
             self._plans = {batch: plan}      # one live plan: the buffers are sized by batch
         return pk, plan
@@ -203,6 +229,10 @@ class HuPRNet(nn.Module):
         plan's output buffers — valid until the next forward)."""
         batch = chirp_ra.hi.shape[0]
         pk, plan = self._plan(batch)
+        with ops.coop_scope(plan["coop"]):
+            return self._forward_features(pk, plan, batch, chirp_ra, chirp_re)
+
+    def _forward_features(self, pk, plan, batch, chirp_ra, chirp_re):
         if batch <= 4 and ops._PROFILE is None:
             # small batches leave most SMs idle inside one encoder (level 2/3 convolutions launch 16-64 CTAs): run the two
             # independent sensor branches on two streams (fork/join with events, captured into the CUDA graph as parallel branches)
@@ -211,7 +241,7 @@ class HuPRNet(nn.Module):
             if side is None:
                 side = plan["side_stream"] = torch.cuda.Stream(device=pk["device"])
             side.wait_stream(main)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), ops.coop_slot(1):
                 feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
             feats_ra = L.run_encoder(chirp_ra, pk["RAradarEncoder"], plan["enc_ra"])
             main.wait_stream(side)
@@ -220,10 +250,24 @@ class HuPRNet(nn.Module):
             feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
         return L.run_decoder(pk["decoder"], plan["dec"], feats_ra, feats_re, pk["adj"])
 
+    def _forward_train(self, hori, vert):
+        """networks.py:35-41 under ``model.train()`` (tools/run.py:66,76): batch-statistics BatchNorm, outputs connected to autograd."""
+        from ..training import TrainStep
+        if not self.split:
+            raise RuntimeError("train-mode forward needs the hi/lo (split=True) model")
+        step = self._train_step
+        if step is None:
+            step = TrainStep(self, install_grads=False)       # registers itself as self._train_step
+        for q in self.parameters():
+            if q.grad is not None and q.grad.data_ptr() == step.gview_ptr(q):
+                q.grad = None            # gradients installed by the fused path alias the flat buffer: autograd must own .grad here
+        step._dirty = True               # any optimiser may have updated the parameters in place since the last pass
+        heat, gcn = _TrainForward.apply(step, hori.float().contiguous(), vert.float().contiguous(), *self.parameters())
+        return heat.unsqueeze(2), gcn.unsqueeze(1)
+
     def forward(self, VRDAEmaps_hori, VRDAEmaps_vert):
         if self.training:
-            raise RuntimeError("hupr_b200.HuPRNet implements the inference path (model.eval()); training-mode BatchNorm and the "
-                               "backward pass are not built yet")
+            return self._forward_train(VRDAEmaps_hori, VRDAEmaps_vert)
         ra, re = self.forward_chirp(VRDAEmaps_hori, VRDAEmaps_vert)
         heatmap, gcn = self.forward_features(ra, re)
         return heatmap.unsqueeze(2), gcn.unsqueeze(1)

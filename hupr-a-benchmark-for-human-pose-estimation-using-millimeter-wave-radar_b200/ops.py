@@ -71,36 +71,103 @@ class SplitTensor(object):
         return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
 
 
-_COOP_WS = {}
 COOP_WS_BYTES = 16 << 20
 _COOP_DEFAULT = os.environ.get("HUPR_NO_COOP", "") == ""      # A/B switch for measurements
 
 
-def coop_workspace(device, stream=None):
-    """Scratch for the cooperative split-K of small-grid contractions (hupr_conv_desc.ws), one per (device, CUDA stream): launches
-    on one stream are ordered, launches on different streams (the two sensor branches of a small-batch forward) may overlap and must
-    not share arrival counters.  Zeroed once; the kernels leave the counters zero."""
+class CoopWorkspaces(object):
+    """Scratch buffers for the cooperative split-K of small-grid contractions (hupr_conv_desc.ws), owned by whoever owns the launch
+    sequence (a HuPRNet plan, a TrainStep): one buffer per SLOT, where a slot is a set of launches that are ordered among themselves
+    (slot 0 = the main stream, slot 1 = the side stream of the two-branch small-batch forward).  Buffers are allocated and zeroed
+    EAGERLY; the kernels leave the arrival counters zero.  A slot that is first requested while a CUDA graph is being captured is an
+    error: its zero-fill would only be recorded into that graph (and never run for other graphs sharing the buffer), so owners run an
+    eager warm-up pass before capturing — which they need anyway for lazy weight packing."""
+
+    def __init__(self, device):
+        dev = torch.device(device)
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self._slots = {}
+
+    def get(self, slot=0):
+        ws = self._slots.get(slot)
+        if ws is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("hupr_b200: split-K workspace slot %r first requested during CUDA-graph capture — run one eager "
+                                   "warm-up pass of the same launch sequence before capturing" % (slot,))
+            ws = torch.zeros(COOP_WS_BYTES, dtype=torch.uint8, device=self.device)
+            self._slots[slot] = ws
+        return ws
+
+
+_COOP_GLOBAL = {}        # device index -> CoopWorkspaces used outside any owner scope, slots keyed by CUDA stream
+_COOP_ACTIVE = None      # CoopWorkspaces of the owner whose launch sequence is running (coop_scope)
+_COOP_SLOT = 0
+
+
+@contextlib.contextmanager
+def coop_scope(workspaces):
+    """Route the split-K scratch of every conv_gemm call in the block to ``workspaces`` (a CoopWorkspaces owned by the caller)."""
+    global _COOP_ACTIVE
+    prev, _COOP_ACTIVE = _COOP_ACTIVE, workspaces
+    try:
+        yield workspaces
+    finally:
+        _COOP_ACTIVE = prev
+
+
+@contextlib.contextmanager
+def coop_slot(slot):
+    """Launches in the block use scratch slot ``slot`` of the active scope (a branch that may run concurrently with slot 0)."""
+    global _COOP_SLOT
+    prev, _COOP_SLOT = _COOP_SLOT, slot
+    try:
+        yield
+    finally:
+        _COOP_SLOT = prev
+
+
+def coop_workspace(device):
+    """The scratch buffer for a conv_gemm launch on the current stream: the active owner scope's slot, else a process-wide buffer per
+    (device, CUDA stream) — launches on one stream are ordered, launches on different streams must not share arrival counters."""
+    if _COOP_ACTIVE is not None:
+        return _COOP_ACTIVE.get(_COOP_SLOT)
     dev = torch.device(device)
     index = dev.index if dev.index is not None else torch.cuda.current_device()
-    if stream is None:
-        stream = torch.cuda.current_stream(index).cuda_stream
-    key = (index, int(stream))
-    ws = _COOP_WS.get(key)
-    if ws is None:
-        ws = torch.zeros(COOP_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", index))
-        _COOP_WS[key] = ws
-    return ws
+    pool = _COOP_GLOBAL.get(index)
+    if pool is None:
+        pool = _COOP_GLOBAL[index] = CoopWorkspaces(torch.device("cuda", index))
+    return pool.get(("stream", int(torch.cuda.current_stream(index).cuda_stream)))
+
+
+_NPROD = 0      # tensor-core products per k-step requested by the running launch sequence (0 = by operands; see products())
+
+
+@contextlib.contextmanager
+def products(n):
+    """Launches in the block use ``n`` tensor-core products per k-step in hupr_conv_gemm / hupr_conv_wgrad: 3 = fp32-equivalent hi/lo
+    arithmetic (default when lo planes exist), 1 = plain bf16 products with fp32 accumulation (lo planes of the operands are not read)."""
+    global _NPROD
+    if n not in (0, 1, 3):
+        raise ValueError("products must be 0, 1 or 3")
+    prev, _NPROD = _NPROD, n
+    try:
+        yield
+    finally:
+        _NPROD = prev
 
 
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
-              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True, tma_store=True):
+              out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True, tma_store=True,
+              nprod=None, lcin=None, lcout=None, lrows=None):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
     weight   : SplitTensor [taps | N, cout, cin]
     out      : SplitTensor [N, Dout, H, W, Co] (written at channel offset o_ch_off) and/or
     out_f32  : fp32 tensor [N, Dout, H, W, ld]
+    lcin, lcout, lrows : LOGICAL contraction / output widths / GEMM rows of the reference layer when the call is zero-padded to the
+                         kernel's 64-channel / 128-row granularity — only used for the algorithmic FLOP count of the profile.
     """
     n, d, h, w, ca = a.hi.shape
     desc = _C.ConvDesc()
@@ -116,6 +183,7 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     desc.k_split, desc.w_k_off = k_split, w_k_off
     if not tma_store or os.environ.get("HUPR_NO_TMA_STORE"):
         desc.no_tma_store = 1
+    desc.nprod = _NPROD if nprod is None else nprod
     if k_split <= 1 and coop and _COOP_DEFAULT:     # small grids split their contraction cooperatively (deterministic ordered reduction)
         ws = coop_workspace(a.hi.device)
         desc.ws, desc.ws_bytes = ws.data_ptr(), ws.numel()
@@ -135,7 +203,8 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     if out_f32 is not None:
         desc.o_f32, desc.o_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
     d_out = d + 2 * pad[0] - kernel[0] + 1
-    flops = 2.0 * n * d_out * h * w * cout * cin * kernel[0] * kernel[1] * kernel[2]
+    rows = n * d_out * h * w if lrows is None else lrows
+    flops = 2.0 * rows * (cout if lcout is None else lcout) * (min(cin, ca - a_ch_off) if lcin is None else lcin) * kernel[0] * kernel[1] * kernel[2]
     tag = "conv_gemm.%s" % ("attn" if w_batched else ("k%dx%dx%d" % tuple(kernel)))
     with torch.cuda.device(a.hi.device), _timed(tag, flops):
         _C.check(_C.lib().hupr_conv_gemm(desc, _C.stream_ptr()), "hupr_conv_gemm")
@@ -317,30 +386,40 @@ def heatmap_loss_fwd(heatmap, gcn_heatmap, joints, want_targets=False):
     return losses, gt2d, targets
 
 
-def heatmap_loss_bwd(heatmap, gcn_heatmap, joints, d_heat_logits, d_gcn_pre):
-    """Gradient of loss1 + loss2 w.r.t. the pre-sigmoid logits (hupr_heatmap_loss_bwd).
+def heatmap_loss_bwd(heatmap, gcn_heatmap, joints, d_heat_logits, d_gcn_pre, weights=(1.0, 1.0)):
+    """Gradient of weights[0]*loss1 + weights[1]*loss2 w.r.t. the pre-sigmoid logits (hupr_heatmap_loss_bwd).
     d_heat_logits float32 [B, 4096, ld] channels-last (14 channels written), d_gcn_pre float32 [B, 14, 64, 64]."""
     batch = joints.shape[0]
     joints = joints.to(device=heatmap.device, dtype=torch.int64).contiguous()
     with torch.cuda.device(heatmap.device):
         _call("hupr_heatmap_loss_bwd", _p(heatmap), _p(gcn_heatmap), _p(joints), batch, d_heat_logits.shape[-1],
+              float(weights[0]), float(weights[1]), _p(d_heat_logits), _p(d_gcn_pre), _C.stream_ptr())
+    return d_heat_logits, d_gcn_pre
+
+
+def heatmap_bwd(heatmap, gcn_heatmap, g_heat, g_gcn, d_heat_logits, d_gcn_pre):
+    """Sigmoid backward of both output maps for caller-supplied gradients (hupr_heatmap_bwd); g_heat / g_gcn float32 [B,14,64,64] or None."""
+    batch = heatmap.shape[0]
+    with torch.cuda.device(heatmap.device):
+        _call("hupr_heatmap_bwd", _p(heatmap), _p(gcn_heatmap), _p(g_heat), _p(g_gcn), batch, d_heat_logits.shape[-1],
               _p(d_heat_logits), _p(d_gcn_pre), _C.stream_ptr())
     return d_heat_logits, d_gcn_pre
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, step_dev=None):
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, step_dev=None, lr_dev=None):
     """One Adam step with coupled L2 on flat float32 CUDA buffers (hupr_adam_step); defaults = reference tools/base.py:47.
-    ``step_dev``: optional int32 device scalar holding the 1-based step count (used instead of ``step``; CUDA-graph friendly)."""
+    ``step_dev``: optional int32 device scalar holding the 1-based step count (used instead of ``step``; CUDA-graph friendly).
+    ``lr_dev``: optional float32 device scalar holding the learning rate (used instead of ``lr``; lets a schedule act on a captured step)."""
     n = params.numel()
     if not (grads.numel() == exp_avg.numel() == exp_avg_sq.numel() == n):
         raise ValueError("adam_step: buffer sizes differ")
     with torch.cuda.device(params.device):
         _call("hupr_adam_step", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), n, lr, betas[0], betas[1], eps, weight_decay, step,
-              _p(step_dev), _C.stream_ptr())
+              _p(step_dev), _p(lr_dev), _C.stream_ptr())
     return params
 
 
-def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=None, batched=False, tag="conv_wgrad"):
+def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=None, batched=False, tag="conv_wgrad", nprod=None, lcin=None, lcout=None):
     """dW[tap, ci, co] of a stride-1 convolution straight from the channels-last tensors (hupr_conv_wgrad): x SplitTensor
     [n, d, h, w, cx], dy SplitTensor [n, d_out, h, w, cy] -> float32 [taps, cin, cout] (ACCUMULATED into ``out`` when given).
     ``batched``: no sum over the samples, out is [n, taps, cin, cout]."""
@@ -359,11 +438,70 @@ def conv_wgrad_direct(x, x_ch_off, cin, dy, y_ch_off, cout, kernel, pad, out=Non
     desc.dw, desc.dw_ld = out.data_ptr(), out.shape[-1]
     if batched:
         desc.batched, desc.dw_batch_stride = 1, out.stride(0)
+    desc.nprod = _NPROD if nprod is None else nprod
     d_out = d + 2 * pad[0] - kernel[0] + 1
-    flops = 2.0 * n * d_out * h * w * cout * cin * taps
+    flops = 2.0 * n * d_out * h * w * (cout if lcout is None else lcout) * (cin if lcin is None else lcin) * taps
     with torch.cuda.device(x.hi.device), _timed(tag, flops):
         _C.check(_C.lib().hupr_conv_wgrad(desc, _C.stream_ptr()), "hupr_conv_wgrad")
     return out
+
+
+def pack_conv_weights(w, fwd, cout_off=0, dgrad=None):
+    """w float32 [cout, cin, *k] (a parameter in torch layout) -> rows cout_off.. of fwd SplitTensor [taps, cout_total, cin_pad] and, when
+    given, columns cout_off.. of dgrad SplitTensor [taps, cin_pad, cout_total] (flipped taps) — hupr_pack_conv_weights."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cin)
+    t2, cout_total, cin_pad = fwd.hi.shape
+    if t2 != taps or not w.is_contiguous() or w.dtype != torch.float32:
+        raise ValueError("pack_conv_weights: weight %s does not match the packed layout %s" % (tuple(w.shape), tuple(fwd.hi.shape)))
+    with torch.cuda.device(w.device):
+        _call("hupr_pack_conv_weights", _p(w), cout, cin, taps, _p(fwd.hi), _p(fwd.lo), cout_total, cin_pad, cout_off,
+              None if dgrad is None else _p(dgrad.hi), None if dgrad is None else _p(dgrad.lo), _C.stream_ptr())
+
+
+def unpack_wgrad(acc, cout_off, dst):
+    """acc float32 [taps, cin_pad, cout_total] (conv_wgrad_direct) -> dst float32 [cout, cin, *k] (torch layout) — hupr_unpack_wgrad."""
+    taps, cin_pad, cout_total = acc.shape
+    cout, cin = dst.shape[0], dst.shape[1]
+    if dst.numel() != cout * cin * taps or not dst.is_contiguous():
+        raise ValueError("unpack_wgrad: gradient %s does not match the accumulator %s" % (tuple(dst.shape), tuple(acc.shape)))
+    with torch.cuda.device(acc.device):
+        _call("hupr_unpack_wgrad", _p(acc), taps, cin_pad, cout_total, cout_off, _p(dst), cout, cin, _C.stream_ptr())
+
+
+def reduce_f64(src, groups, n, dst):
+    """dst[g] = float(sum_i src[g*n + i]) — hupr_reduce_f64 (float64 partial sums -> float32 gradient storage)."""
+    with torch.cuda.device(src.device):
+        _call("hupr_reduce_f64", _p(src), groups, n, _p(dst), _C.stream_ptr())
+
+
+def broadcast_f32(src, dst):
+    with torch.cuda.device(dst.device):
+        _call("hupr_broadcast_f32", _p(src), _p(dst), dst.numel(), _C.stream_ptr())
+
+
+def gcn_bias_rows(bias, batch, rows):
+    """bias float32 [1024, 14] -> rows SplitTensor [.., n_rows, 1024] (hupr_gcn_bias_rows)."""
+    with torch.cuda.device(bias.device):
+        _call("hupr_gcn_bias_rows", _p(bias), batch, rows.hi.shape[-2], _p(rows.hi), _p(rows.lo), _C.stream_ptr())
+
+
+def bump_i32(counter):
+    with torch.cuda.device(counter.device):
+        _call("hupr_bump_i32", _p(counter), _C.stream_ptr())
+
+
+def zero_(t):
+    """Stream-ordered zero fill of a contiguous tensor through cudaMemsetAsync (hupr_memset_zero): a memset node under graph capture."""
+    if not t.is_contiguous():
+        raise ValueError("zero_: tensor must be contiguous")
+    with torch.cuda.device(t.device):
+        _call("hupr_memset_zero", _p(t), t.numel() * t.element_size(), _C.stream_ptr())
+    return t
+
+
+def zeros(shape, dtype, device):
+    return zero_(torch.empty(shape, dtype=dtype, device=device))
 
 
 def matmul_tn(a, b, b_ch_off, c, out):

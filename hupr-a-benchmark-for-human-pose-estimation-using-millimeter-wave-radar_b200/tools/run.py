@@ -71,28 +71,26 @@ class Runner(object):
 
     def _optimizer_state_dict(self):
         """torch.optim.Adam.state_dict() layout, one entry per parameter in model.parameters() order."""
-        t, state, o = self.trainer, {}, 0
-        for i, p in enumerate(self.model.parameters()):
-            k = p.numel()
+        t, state = self.trainer, {}
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            o, k = t.offsets[name], p.numel()
             state[i] = {"step": torch.tensor(float(t.step_count)), "exp_avg": t.exp_avg[o:o + k].view(p.shape).clone(),
                         "exp_avg_sq": t.exp_avg_sq[o:o + k].view(p.shape).clone()}
-            o += k
         group = dict(lr=t.hyper["lr"], betas=t.hyper["betas"], eps=t.hyper["eps"], weight_decay=t.hyper["weight_decay"], amsgrad=False,
                      params=list(range(len(state))))
         return {"state": state, "param_groups": [group]}
 
     def _load_optimizer_state_dict(self, sd):
-        t, o = self.trainer, 0
-        for i, p in enumerate(self.model.parameters()):
-            k = p.numel()
+        t = self.trainer
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            o, k = t.offsets[name], p.numel()
             entry = sd["state"].get(i)
             if entry is not None:
                 t.exp_avg[o:o + k].copy_(entry["exp_avg"].reshape(-1))
                 t.exp_avg_sq[o:o + k].copy_(entry["exp_avg_sq"].reshape(-1))
                 t.step_count = int(float(entry["step"]))
-            o += k
         t.step_dev.fill_(t.step_count)
-        t.hyper["lr"] = sd["param_groups"][0]["lr"]
+        t.set_lr(sd["param_groups"][0]["lr"])
 
     def saveModelWeight(self, epoch, acc):
         is_best = (acc == acc) and acc > self.bestAP
@@ -120,8 +118,7 @@ class Runner(object):
         checkpoint = torch.load(path, map_location=self.device, weights_only=False)
         self.model.load_state_dict(checkpoint["model_state_dict"])
         if self.trainer is not None:
-            self.trainer.flat_p.copy_(torch.cat([p.detach().reshape(-1) for p in self.model.parameters()]))
-            self.trainer._dirty = True
+            self.trainer._dirty = True           # load_state_dict copied in place into the views of the trainer's flat parameter buffer
             if not getattr(self.args, "pretrained", False):          # the reference reads args.pretrained without defining it (base.py:112)
                 print("==========>Load the previous optimizer")
                 self._load_optimizer_state_dict(checkpoint["optimizer_state_dict"])
@@ -183,6 +180,15 @@ class Runner(object):
         self.testSet._print_stats(stats)
         return float(stats[0])
 
+    def _loss_weights(self):
+        """The (alpha, beta) schedule LossComputer.computeLoss applies per call (misc/losses.py:36-42 of the reference): with
+        TRAINING.lossDecay == -1 the objective is loss1 + loss2; otherwise alpha*loss1 + beta*loss2 with alpha ramping up by lossDecay."""
+        lc = self.lossComputer
+        if lc.alpha < 1.0:
+            lc.alpha += lc.lossDecay
+            lc.beta -= lc.lossDecay
+        return (1.0, 1.0) if lc.lossDecay == -1 else (lc.alpha, lc.beta)
+
     def train(self):
         for epoch in range(self.start_epoch, self.cfg.TRAINING.epochs):
             self.model.train()
@@ -190,7 +196,10 @@ class Runner(object):
             for idxBatch, batch in enumerate(self.trainLoader):
                 hori = batch["VRDAEmap_hori"].float().to(self.device)
                 vert = batch["VRDAEmap_vert"].float().to(self.device)
-                loss, loss2 = self.trainer.forward_backward(hori, vert, batch["jointsGroup"])
+                w1, w2 = self._loss_weights()
+                loss, loss2 = self.trainer.forward_backward(hori, vert, batch["jointsGroup"], loss_weights=(w1, w2))
+                if (w1, w2) != (1.0, 1.0):               # the reported loss is the optimised objective, as in the reference
+                    loss = w1 * self.trainer.last_losses[2] + w2 * loss2
                 self.trainer.all_reduce_gradients()
                 self.trainer.optimizer_step()
                 if idxBatch % self.cfg.TRAINING.lrDecayIter == 0:

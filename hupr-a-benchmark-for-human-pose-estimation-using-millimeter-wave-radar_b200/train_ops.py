@@ -67,12 +67,14 @@ def bn_finalize(sums, count, gamma, beta, eps, momentum, running_mean=None, runn
     return out
 
 
-def bn_bwd_finalize(sums, count):
-    """sums: float64 [2, c] (sum g', sum g' zhat) -> float32 [4, c] rows (k2, k3, dgamma, dbeta) (hupr_bn_bwd_finalize)."""
+def bn_bwd_finalize(sums, count, dgamma=None, dbeta=None):
+    """sums: float64 [2, c] (sum g', sum g' zhat) -> float32 [4, c] rows (k2, k3, dgamma, dbeta) (hupr_bn_bwd_finalize).  When ``dgamma`` /
+    ``dbeta`` (contiguous float32 [c], e.g. the parameters' .grad views) are given, the two gradients are written there directly."""
     c = sums.shape[1]
     out = torch.empty((4, c), dtype=torch.float32, device=sums.device)
     with torch.cuda.device(sums.device):
-        _call("hupr_bn_bwd_finalize", _p(sums[0]), _p(sums[1]), int(count), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), c, _C.stream_ptr())
+        _call("hupr_bn_bwd_finalize", _p(sums[0]), _p(sums[1]), int(count), _p(out[0]), _p(out[1]), _p(out[2] if dgamma is None else dgamma),
+              _p(out[3] if dbeta is None else dbeta), c, _C.stream_ptr())
     return out
 
 

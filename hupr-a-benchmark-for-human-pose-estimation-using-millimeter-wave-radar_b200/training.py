@@ -7,11 +7,19 @@ tensors the forward saved —
   convolutions : dgrad = the implicit-GEMM kernel with flipped filters; wgrad = hupr_conv_wgrad: positions contracted on the tensor
                  cores with MN-major operands read straight from the channels-last tensors — ops.conv_wgrad_direct
   BatchNorm    : batch statistics (double sums), affine + ReLU, standard three-term backward — train_ops
-  attention    : P is recomputed (QK^T GEMM + row softmax), then dV = P^T dO, dP = dO V^T, dS = P*(dP - rowsum), dQ = dS K, dK = dS^T Q
+  attention    : head dim 64 (level 1, 94 % of the work): hupr_attention_bwd, the fused flash-style backward (no [S, S] matrix in memory);
+                 other levels: P = exp(QK^T - lse) and dS = P o (dP - rowdot) rebuilt in GEMM epilogues, dQ = dS K, dK = dS^T Q, dV = P^T dO
                  (the two A^T B products contract over queries with MN-major operands — ops.matmul_tn, no transposed [S,S] copies)
   PRGCN        : the transposed-layout GEMMs of the forward with W^T, adjacency mixes with A^T, adjoint resampling
-This first version favours exactness over speed (fp32-equivalent hi/lo arithmetic everywhere, unfused backward attention).
+Inside a step NO framework kernel runs: the operand layouts of the tensor-core kernels are rebuilt from the flat fp32 parameter buffer by
+hupr_pack_conv_weights, weight gradients land in the flat fp32 gradient buffer through hupr_unpack_wgrad / direct stores, and every
+zero-initialised scratch tensor of the step comes out of ONE arena cleared by a single memset (``ZeroArena``).
+
+Precision: ``products=3`` (default) keeps the fp32-equivalent hi/lo arithmetic everywhere; ``products=1`` runs every convolution, data
+gradient and weight gradient as plain bf16 tensor-core products with fp32 accumulation (the "training bf16" of BASELINE.json configs[3]):
+master weights, gradients and Adam moments stay fp32, BatchNorm / element-wise kernels and the attention kernels keep their hi/lo inputs.
 """
+import contextlib
 import os
 
 import torch
@@ -26,8 +34,69 @@ EPS = 1e-5
 MOMENTUM = 0.1
 
 
-def _S(shape, dev, zero=False):
-    return SplitTensor.empty(tuple(shape), dev, True, zero=zero)
+# ------------------------------------------------------------------------------------------------------------------ scratch memory
+class ZeroArena(object):
+    """Zero-initialised scratch of ONE step for ONE batch size.  The first pass through the step ("planning") hands out individually
+    cleared tensors and records their sizes; from the second pass on the same sequence of requests is served from one contiguous
+    buffer that a single hupr_memset_zero clears at the start of the step."""
+
+    def __init__(self, device):
+        self.device = device
+        self.sizes = []          # aligned byte sizes in request order
+        self.buf = None
+        self.cursor = 0
+        self.offset = 0
+
+    def begin(self):
+        if self.buf is None and self.sizes and not torch.cuda.is_current_stream_capturing():
+            self.buf = torch.empty(sum(self.sizes), dtype=torch.uint8, device=self.device)
+        self.cursor, self.offset = 0, 0
+        if self.buf is not None:
+            ops.zero_(self.buf)
+        else:
+            self.sizes = []
+
+    def take(self, shape, dtype):
+        n = torch.empty((), dtype=dtype).element_size()
+        for d in shape:
+            n *= d
+        aligned = -(-n // 256) * 256
+        if self.buf is None:
+            self.sizes.append(aligned)
+            return ops.zeros(tuple(shape), dtype, self.device)
+        if self.cursor >= len(self.sizes) or self.sizes[self.cursor] != aligned:
+            raise RuntimeError("hupr_b200.training: the step's scratch request sequence changed between passes (request %d: %d bytes)"
+                               % (self.cursor, aligned))
+        t = self.buf[self.offset:self.offset + n].view(dtype).view(tuple(shape))
+        self.cursor += 1
+        self.offset += aligned
+        return t
+
+
+_ARENA = None
+
+
+@contextlib.contextmanager
+def _arena_scope(arena):
+    global _ARENA
+    prev, _ARENA = _ARENA, arena
+    try:
+        if arena is not None:
+            arena.begin()
+        yield
+    finally:
+        _ARENA = prev
+
+
+def _zeros(shape, dtype, dev):
+    """Zero-initialised scratch for the running step: from the step's arena when one is active, else an individually cleared tensor."""
+    if _ARENA is not None:
+        return _ARENA.take(shape, dtype)
+    return ops.zeros(tuple(shape), dtype, dev)
+
+
+def _S(shape, dev):
+    return SplitTensor.empty(tuple(shape), dev, True)
 
 
 def _rows(t):
@@ -37,8 +106,17 @@ def _rows(t):
     return SplitTensor(t.hi.view(n, 1, 1, s, c), t.lo.view(n, 1, 1, s, c))
 
 
+def _grad_out(grads, name, shape, dev):
+    """Destination of a parameter gradient: the pre-installed tensor of ``grads`` (TrainStep: a view of the flat gradient buffer) or a
+    fresh float32 tensor stored under ``name`` (block-level use with a plain dict)."""
+    t = grads.get(name)
+    if t is None:
+        t = grads[name] = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+    return t
+
+
 class ConvOp(object):
-    """One (possibly cout-concatenated) stride-1 convolution: forward / dgrad / wgrad packs and gradient bookkeeping."""
+    """One (possibly cout-concatenated) stride-1 convolution: forward / dgrad / wgrad operand packs and gradient bookkeeping."""
 
     def __init__(self, names, cin, couts, kernel, pad, bias_name=None):
         self.names, self.cin, self.couts = names, cin, couts
@@ -46,44 +124,55 @@ class ConvOp(object):
         self.cin_pad = L.pad64(cin)
         self.cout_pads = [L.pad64(c) for c in couts]
         self.cout = sum(self.cout_pads)
+        self.lcout = sum(couts)
         self.taps = kernel[0] * kernel[1] * kernel[2]
-
-    def _w5(self, w):
-        return w if w.dim() == 5 else w.unsqueeze(2)
+        self.w = self.wd = None
+        self.shapes = {}
 
     def pack(self, sd):
-        ws = [self._w5(sd[n].detach().float()) for n in self.names]
-        self.w = L.pack_conv(ws, self.cin_pad, self.cout_pads)
-        full = torch.zeros((self.cout, self.cin_pad) + self.kernel, dtype=torch.float32, device=ws[0].device)
+        """sd: name -> float32 parameter (torch layout).  Rebuilds the forward [taps, cout, cin_pad] and data-gradient
+        [flipped taps, cin_pad, cout] hi/lo operands in place (hupr_pack_conv_weights; the zero padding is written once, here)."""
+        ws = [sd[n].detach() for n in self.names]
+        dev = ws[0].device
+        if self.w is None or self.w.hi.device != dev:
+            self.w = SplitTensor.empty((self.taps, self.cout, self.cin_pad), dev, True, zero=True)
+            self.wd = SplitTensor.empty((self.taps, self.cin_pad, self.cout), dev, True, zero=True)
         o = 0
-        for w, cp in zip(ws, self.cout_pads):
-            full[o:o + w.shape[0], :w.shape[1]] = w
+        for n, w, cp in zip(self.names, ws, self.cout_pads):
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                w = w.float().contiguous()
+            self.shapes[n] = tuple(w.shape)
+            ops.pack_conv_weights(w, self.w, o, self.wd)
             o += cp
-        self.wd = L.pack_dgrad(full, self.cout, self.cin_pad)
-        self.bias = sd[self.bias_name].detach().float().contiguous() if self.bias_name else None
+        b = sd[self.bias_name].detach() if self.bias_name else None
+        self.bias = b if b is None or (b.dtype == torch.float32 and b.is_contiguous()) else b.float().contiguous()
+        if self.bias_name:
+            self.shapes[self.bias_name] = tuple(self.bias.shape)
 
     def forward(self, x, out, **kw):
-        return ops.conv_gemm(x, self.cin_pad, self.w, self.cout, kernel=self.kernel, pad=self.pad, shift=self.bias, out=out, **kw)
+        return ops.conv_gemm(x, self.cin_pad, self.w, self.cout, kernel=self.kernel, pad=self.pad, shift=self.bias, out=out,
+                             lcin=self.cin, lcout=self.lcout, **kw)
 
     def dgrad(self, dy, out, **kw):
         """dy: SplitTensor [..., self.cout] (or a wider tensor with a_ch_off) -> out [..., cin_pad]."""
         dpad = (self.kernel[0] - 1 - self.pad[0], self.pad[1], self.pad[2])
-        return ops.conv_gemm(dy, self.cout, self.wd, self.cin_pad, kernel=self.kernel, pad=dpad, out=out, **kw)
+        return ops.conv_gemm(dy, self.cout, self.wd, self.cin_pad, kernel=self.kernel, pad=dpad, out=out, lcin=self.lcout, lcout=self.cin, **kw)
 
     def wgrad(self, x, x_off, dy, dy_off, grads):
         """x: saved input [n, d, h, w, ld]; dy: output gradient [n, d_out, h, w, ld'] -> grads[name] (+ bias gradient).
-        One hupr_conv_wgrad launch: positions are contracted on the tensor cores straight from the channels-last tensors."""
+        One hupr_conv_wgrad launch (positions contracted on the tensor cores straight from the channels-last tensors) into a zeroed
+        [taps, cin_pad, cout] accumulator, then one hupr_unpack_wgrad per parameter into its torch-layout gradient."""
         dev = x.hi.device
-        acc = ops.conv_wgrad_direct(x, x_off, self.cin_pad, dy, dy_off, self.cout, self.kernel, self.pad)      # [taps, cin_pad, cout]
+        acc = _zeros((self.taps, self.cin_pad, self.cout), torch.float32, dev)
+        ops.conv_wgrad_direct(x, x_off, self.cin_pad, dy, dy_off, self.cout, self.kernel, self.pad, out=acc, lcin=self.cin, lcout=self.lcout)
         o = 0
-        for name, c, cp in zip(self.names, self.couts, self.cout_pads):
-            grads[name] = acc[:, :self.cin, o:o + c].permute(2, 1, 0)      # strided view [c, cin, taps]: copied once, into the flat gradient buffer
+        for name, cp in zip(self.names, self.cout_pads):
+            ops.unpack_wgrad(acc, o, _grad_out(grads, name, self.shapes[name], dev))
             o += cp
         if self.bias_name:
-            s1 = torch.zeros(self.cout, dtype=torch.float64, device=dev)
-            s2 = torch.zeros_like(s1)
-            T.channel_sums(T.SUMS_PRELU, (dy, dy_off), self.cout, s1, s2)
-            grads[self.bias_name] = s2[:self.couts[0]].float()
+            sums = _zeros((2, self.cout), torch.float64, dev)
+            T.channel_sums(T.SUMS_PRELU, (dy, dy_off), self.cout, sums[0], sums[1])
+            ops.reduce_f64(sums[1], self.couts[0], 1, _grad_out(grads, self.bias_name, self.shapes[self.bias_name], dev))
 
 
 class BNOp(object):
@@ -93,7 +182,7 @@ class BNOp(object):
     def forward_stats(self, z, z_off, params, buffers, count):
         """Batch statistics of z[..., z_off:z_off+c]; updates running stats; returns (scale, shift) for the affine kernel."""
         dev = z.hi.device
-        sums = torch.zeros((2, self.c), dtype=torch.float64, device=dev)
+        sums = _zeros((2, self.c), torch.float64, dev)
         T.channel_sums(T.SUMS_STATS, (z, z_off), self.c, sums[0], sums[1])
         gamma, beta = params[self.prefix + ".weight"].detach(), params[self.prefix + ".bias"].detach()
         rm, rv = buffers[self.prefix + ".running_mean"], buffers[self.prefix + ".running_var"]
@@ -118,12 +207,11 @@ class BNOp(object):
     def backward(self, g, z, z_off, mask, out, out_off, count, grads):
         """g: gradient w.r.t. the activation output (masked by mask > 0 when given) -> out[..., out_off:+c] = dz; fills dgamma, dbeta."""
         dev = z.hi.device
-        sums = torch.zeros((2, self.c), dtype=torch.float64, device=dev)
+        sums = _zeros((2, self.c), torch.float64, dev)
         T.channel_sums(T.SUMS_BN_BWD, g, self.c, sums[0], sums[1], b=(z, z_off), mask=mask, mean=self.mean, rstd=self.rstd)
-        st = T.bn_bwd_finalize(sums, count)                      # k2, k3, dgamma, dbeta in one launch
+        st = T.bn_bwd_finalize(sums, count, dgamma=_grad_out(grads, self.prefix + ".weight", (self.c,), dev),
+                               dbeta=_grad_out(grads, self.prefix + ".bias", (self.c,), dev))      # k2, k3, dgamma, dbeta in one launch
         T.bn_bwd_apply(g, (z, z_off), self.c, self.mean, self.rstd, self.scale, st[0], st[1], (out, out_off), mask=mask)
-        grads[self.prefix + ".weight"] = st[2]
-        grads[self.prefix + ".bias"] = st[3]
 
 
 class Block3D(object):
@@ -182,13 +270,19 @@ class Block2D(object):
         self.prefix, self.cp, self.cout = prefix, L.pad64(cout), cout
         self.conv1 = ConvOp([prefix + ".main.0.weight", prefix + ".downsample.0.weight"], cin, [cout, cout], (1, 3, 3), (0, 1, 1))
         self.conv2 = ConvOp([prefix + ".main.2.weight"], cout, [cout], (1, 3, 3), (0, 1, 1))
+        self.a1 = self.a2 = None
 
     def pack(self, sd):
         self.conv1.pack(sd)
         self.conv2.pack(sd)
-        dev = sd[self.prefix + ".relu.weight"].device
-        self.a1 = sd[self.prefix + ".main.1.weight"].detach().float().expand(self.cp).contiguous()
-        self.a2 = sd[self.prefix + ".relu.weight"].detach().float().expand(self.cp).contiguous()
+        s1, s2 = sd[self.prefix + ".main.1.weight"].detach(), sd[self.prefix + ".relu.weight"].detach()
+        dev = s1.device
+        if self.a1 is None or self.a1.device != dev:
+            self.a1 = torch.empty(self.cp, dtype=torch.float32, device=dev)
+            self.a2 = torch.empty(self.cp, dtype=torch.float32, device=dev)
+        # nn.PReLU's single slope -> the per-channel slope arrays of the kernels (hupr_broadcast_f32 reads the parameter in place)
+        ops.broadcast_f32(s1 if s1.dtype == torch.float32 else s1.float(), self.a1)
+        ops.broadcast_f32(s2 if s2.dtype == torch.float32 else s2.float(), self.a2)
 
     def forward(self, x, out=None, out_off=0):
         dev, cp = x.hi.device, self.cp
@@ -197,7 +291,8 @@ class Block2D(object):
         self.zc = self.conv1.forward(x, _S(shape + (2 * cp,), dev))
         self.t = _S(shape + (cp,), dev)
         T.affine_act((self.zc, 0), cp, self.t, slope=self.a1)
-        self.s = ops.conv_gemm(self.t, cp, self.conv2.w, cp, kernel=(1, 3, 3), pad=(0, 1, 1), residual=self.zc, r_ch_off=cp, out=_S(shape + (cp,), dev))
+        self.s = ops.conv_gemm(self.t, cp, self.conv2.w, cp, kernel=(1, 3, 3), pad=(0, 1, 1), residual=self.zc, r_ch_off=cp, out=_S(shape + (cp,), dev),
+                               lcin=self.cout, lcout=self.cout)
         self.out = _S(shape + (cp,), dev) if out is None else out
         T.affine_act(self.s, cp, (self.out, out_off), slope=self.a2)
         return self.out
@@ -207,18 +302,16 @@ class Block2D(object):
         shape = self.s.hi.shape[:-1]
         ds = _S(shape + (cp,), dev)
         T.act_bwd((dout, dout_off), self.s, cp, self.a2, ds)
-        p1 = torch.zeros(cp, dtype=torch.float64, device=dev)
-        p2 = torch.zeros_like(p1)
-        T.channel_sums(T.SUMS_PRELU, (dout, dout_off), cp, p1, p2, b=self.s)
-        grads[self.prefix + ".relu.weight"] = p1.sum().float().reshape(1)
+        p = _zeros((2, cp), torch.float64, dev)
+        T.channel_sums(T.SUMS_PRELU, (dout, dout_off), cp, p[0], p[1], b=self.s)
+        ops.reduce_f64(p[0], 1, cp, _grad_out(grads, self.prefix + ".relu.weight", (1,), dev))
         self.conv2.wgrad(self.t, 0, ds, 0, grads)
         dt = self.conv2.dgrad(ds, _S(shape + (cp,), dev))
         dzc = _S(shape + (2 * cp,), dev)
         T.act_bwd(dt, (self.zc, 0), cp, self.a1, (dzc, 0))
-        q1 = torch.zeros(cp, dtype=torch.float64, device=dev)
-        q2 = torch.zeros_like(q1)
-        T.channel_sums(T.SUMS_PRELU, dt, cp, q1, q2, b=(self.zc, 0))
-        grads[self.prefix + ".main.1.weight"] = q1.sum().float().reshape(1)
+        q = _zeros((2, cp), torch.float64, dev)
+        T.channel_sums(T.SUMS_PRELU, dt, cp, q[0], q[1], b=(self.zc, 0))
+        ops.reduce_f64(q[0], 1, cp, _grad_out(grads, self.prefix + ".main.1.weight", (1,), dev))
         T.accumulate((dzc, cp), cp, a=ds)
         self.conv1.wgrad(self.x, 0, dzc, 0, grads)
         return self.conv1.dgrad(dzc, _S(shape + (self.conv1.cin_pad,), dev))
@@ -230,7 +323,7 @@ class AttentionLevel(object):
     def __init__(self, level, c, hw, prev):
         p = "radarDecoder."
         self.c, self.hw, self.s, self.prev = c, hw, hw * hw, prev
-        self.fused_bwd = False       # hupr_attention_bwd for head dim 64 (opt-in until it has been timed inside the step: DESIGN.md §3b)
+        self.fused_bwd = True        # hupr_attention_bwd where it applies (head dim 64); other levels keep the GEMM-epilogue formulation
         self.proj_h = ConvOp([p + "%s.%d.weight" % (n, level) for n in L.PROJ_HORI], c, [c] * 4, (1, 1, 1), (0, 0, 0))
         self.proj_v = ConvOp([p + "%s.%d.weight" % (n, level) for n in L.PROJ_VERT], c, [c] * 4, (1, 1, 1), (0, 0, 0))
 
@@ -279,12 +372,12 @@ class AttentionLevel(object):
         dpr = {"ra": _S((b, 1, 1, s, 4 * c), dev), "re": _S((b, 1, 1, s, 4 * c), dev)}
         # dV of both attentions that read a map as V accumulate in one fp32 buffer; the A^T B products (dK = dS^T Q, dV = P^T dO)
         # contract over the query axis with MN-major tensor-core operands (ops.matmul_tn): no transposed [S, S] copies
-        dvf = {"ra": torch.zeros((b, s, c), dtype=torch.float32, device=dev), "re": torch.zeros((b, s, c), dtype=torch.float32, device=dev)}
+        dvf = {"ra": _zeros((b, s, c), torch.float32, dev), "re": _zeros((b, s, c), torch.float32, dev)}
         dv_res = {}
         if self.fused_bwd and c == 64 and all(l is not None for l in self.lse):
             # fused flash-style backward: no [S, S] matrix in memory; dQ / dK of the four attentions accumulate in fp32 projection-gradient
             # buffers (one conversion to hi/lo afterwards), dV in the per-source buffers
-            dprf = {key: torch.zeros((b, s, 4 * c), dtype=torch.float32, device=dev) for key in ("ra", "re")}
+            dprf = {key: _zeros((b, s, 4 * c), torch.float32, dev) for key in ("ra", "re")}
             for idx, (qs, qo, ks, ko, vs, oo, res) in enumerate(self._plan()):
                 rowdot = T.rowdot((dcat_s, oo), (self.cat_s, oo), c, torch.empty((b, s), dtype=torch.float32, device=dev),
                                   sub=v[vs] if res else None)
@@ -317,7 +410,7 @@ class AttentionLevel(object):
                 T.softmax_bwd_rows(probs, scratch, dsm)
             kt = ops.transpose_split(self.pr[ks], c, _S((b, c, s), dev), in_ch_off=ko)
             ops.conv_gemm(dsm, s, kt, c, w_batched=True, out=dpr[qs], o_ch_off=qo)                                 # dQ = dS K
-            dkf = torch.zeros((b, s, c), dtype=torch.float32, device=dev)
+            dkf = _zeros((b, s, c), torch.float32, dev)
             ops.matmul_tn(SplitTensor(dsm.hi.view(b, s, s), dsm.lo.view(b, s, s)), SplitTensor(self.pr[qs].hi.view(b, s, 4 * c), self.pr[qs].lo.view(b, s, 4 * c)),
                           qo, c, dkf)                                                                              # dK = dS^T Q
             T.accumulate((dpr[ks], ko), c, f=dkf.view(b * s, c))
@@ -375,13 +468,13 @@ class Encoder(object):
         self.merges[2].wgrad(self.l3, 0, df3, 0, grads)
         dl3 = self.merges[2].dgrad(df3, _S((b, g // 4, 16, 16, 8 * nf), dev))
         d = self.blocks[3].backward(self.blocks[4].backward(dl3, grads), grads)                 # -> d l3in [B, 2, 16, 16, 128]
-        acc = torch.zeros((b, g // 2, 32, 32, 4 * nf), dtype=torch.float32, device=dev)
+        acc = _zeros((b, g // 2, 32, 32, 4 * nf), torch.float32, dev)
         T.resample_linear_bwd(d, 4 * nf, acc)
         self.merges[1].wgrad(self.l2, 0, df2, 0, grads)
         dl2 = self.merges[1].dgrad(df2, _S((b, g // 2, 32, 32, 4 * nf), dev))
         T.accumulate(dl2, 4 * nf, a=dl2, f=acc.view(-1, 4 * nf))
         d = self.blocks[1].backward(self.blocks[2].backward(dl2, grads), grads)                 # -> d l2in [B, 4, 32, 32, 64]
-        acc = torch.zeros((b, g, 64, 64, 2 * nf), dtype=torch.float32, device=dev)
+        acc = _zeros((b, g, 64, 64, 2 * nf), torch.float32, dev)
         T.resample_linear_bwd(d, 2 * nf, acc)
         self.merges[0].wgrad(self.l1, 0, df1, 0, grads)
         dl1 = self.merges[0].dgrad(df1, _S((b, g, 64, 64, 2 * nf), dev))
@@ -391,20 +484,31 @@ class Encoder(object):
         return self.conv0.dgrad(dl1a, _S((b, g, 64, 64, L.pad64(nf)), dev))
 
 
+class _Saved(object):
+    """Tensors one forward pass leaves for its backward pass."""
+
+
 class TrainStep(object):
     """``loss, loss2 = step.forward_backward(hori, vert, joints)`` fills ``param.grad`` of every model parameter;
-    ``step.optimizer_step()`` applies Adam (coupled L2) in place.  ``model`` is a ``hupr_b200.models.HuPRNet`` on a CUDA device."""
+    ``step.optimizer_step()`` applies Adam (coupled L2) in place.  ``model`` is a ``hupr_b200.models.HuPRNet`` on a CUDA device.
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused_attention_bwd=None):
-        """``fused_attention_bwd``: use hupr_attention_bwd for the head-dim-64 attentions (default: off unless HUPR_FUSED_ATTN_BWD=1 —
-        the kernel is parity-tested on its own but has not been run inside the step yet)."""
+    ``products``: 3 = fp32-equivalent hi/lo tensor-core arithmetic (default), 1 = bf16 products with fp32 accumulation in every
+    convolution / data-gradient / weight-gradient launch (fp32 master weights and Adam state either way).
+    ``fused_attention_bwd``: hupr_attention_bwd for the head-dim-64 level (default on; ``HUPR_FUSED_ATTN_BWD=0`` or False selects the
+    GEMM-epilogue formulation for A/B measurements)."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, fused_attention_bwd=None, products=3,
+                 install_grads=True):
+        if products not in (1, 3):
+            raise ValueError("products must be 1 (bf16 products) or 3 (fp32-equivalent hi/lo products)")
         self.model = model
+        self.products = products
         nf, g, kp = model.numFilters, model.numGroupFrames, model.numKeypoints
         self.nf, self.g, self.kp = nf, g, kp
         self.enc = {"ra": Encoder("RAradarEncoder", nf, g), "re": Encoder("REradarEncoder", nf, g)}
         self.levels = [AttentionLevel(0, 8 * nf, 16, 0), AttentionLevel(1, 4 * nf, 32, 4 * nf), AttentionLevel(2, 2 * nf, 64, 2 * nf)]
         if fused_attention_bwd is None:
-            fused_attention_bwd = os.environ.get("HUPR_FUSED_ATTN_BWD") == "1"
+            fused_attention_bwd = os.environ.get("HUPR_FUSED_ATTN_BWD", "1") != "0"
         for level in self.levels:
             level.fused_bwd = bool(fused_attention_bwd)
         p = "radarDecoder."
@@ -417,41 +521,92 @@ class TrainStep(object):
         # flat parameter / gradient / moment buffers: parameters become views of one fp32 buffer so Adam is a single launch
         params = [q for q in model.parameters()]
         dev = params[0].device
-        n = sum(q.numel() for q in params)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.device = dev
+        # every parameter starts on a 16-byte boundary of the flat buffers (the 1-element PReLU slopes would otherwise misalign their
+        # successors; GEMM kernels store straight into gradient views); the few padding elements stay zero under Adam
+        self.offsets, n = {}, 0
+        for name, q in model.named_parameters():
+            self.offsets[name] = n
+            n += -(-q.numel() // 4) * 4
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
-        o = 0
-        for q in params:
-            k = q.numel()
+        self.gview = {}
+        for name, q in model.named_parameters():
+            o, k = self.offsets[name], q.numel()
             self.flat_p[o:o + k].copy_(q.data.reshape(-1))
             q.data = self.flat_p[o:o + k].view(q.shape)
-            q.grad = self.flat_g[o:o + k].view(q.shape)
-            o += k
+            self.gview[name] = self.flat_g[o:o + k].view(q.shape)
+            if install_grads:
+                q.grad = self.gview[name]
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.adj = torch.tensor(ADJACENCY, dtype=torch.float32, device=dev)
         self.adj_t = self.adj.t().contiguous()
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)      # read by hupr_adam_step: a schedule acts on captured steps
+        self._lr_uploaded = float(lr)
+        self.gcn_w = [SplitTensor.empty((1, 1024, 1024), dev, True, zero=True) for _ in range(3)]       # W  [q][p]: forward operand
+        self.gcn_wt = [SplitTensor.empty((1, 1024, 1024), dev, True, zero=True) for _ in range(3)]      # W^T: operand of dSt = dYt W
+        self.gcn_relu = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.coop = ops.CoopWorkspaces(dev)       # split-K scratch of this step's launch sequence
+        self._arenas = {}                         # batch size -> ZeroArena
+        self._gcn_bufs = {}                       # batch size -> persistent zero-padded GCN row buffers
         self._dirty = True
+        self._saved = None
+        self._gptr = {id(q): self.gview[name].data_ptr() for name, q in model.named_parameters()}
+        model._train_step = self                  # one TrainStep owns a model's flat parameter storage (HuPRNet._forward_train reuses it)
+
+    def gview_ptr(self, q):
+        return self._gptr.get(id(q), 0)
 
     # ---------------------------------------------------------------------------------------------------------------- packing
     def _pack(self):
-        sd = {k: v for k, v in self.model.named_parameters()}
+        """Operand layouts of every contraction from the flat fp32 parameters — library launches only (hupr_pack_conv_weights,
+        hupr_broadcast_f32), so a captured step re-packs after its own Adam launch without any framework kernel."""
+        sd = {k: v.data for k, v in self.model.named_parameters()}
         for e in self.enc.values():
             e.pack(sd)
         for m in self.levels + self.dblocks:
             m.pack(sd)
         self.head.pack(sd)
         p = "radarDecoder."
-        self.gcn_w = [SplitTensor.from_float(sd[p + "gcn.L%d.weight" % i].detach().float().view(1, 1024, 1024)) for i in (1, 2, 3)]
-        self.gcn_wt = [SplitTensor.from_float(sd[p + "gcn.L%d.weight" % i].detach().float().t().contiguous().view(1, 1024, 1024)) for i in (1, 2, 3)]
-        self.gcn_b = [sd[p + "gcn.L%d.bias" % i].detach().float() for i in (1, 2, 3)]
-        self.mnet = {k: (sd[n + ".temporalConvWx1x1.weight"].detach().float().contiguous(), sd[n + ".temporalConvWx1x1.bias"].detach().float().contiguous())
-                     for k, n in (("ra", "RAchirpNet"), ("re", "REchirpNet"))}
+        for i in range(3):
+            ops.pack_conv_weights(sd[p + "gcn.L%d.weight" % (i + 1)], self.gcn_w[i], 0, self.gcn_wt[i])
+        self.gcn_b = [sd[p + "gcn.L%d.bias" % i] for i in (1, 2, 3)]
+        self.mnet = {k: (sd[n + ".temporalConvWx1x1.weight"], sd[n + ".temporalConvWx1x1.bias"]) for k, n in (("ra", "RAchirpNet"), ("re", "REchirpNet"))}
         self._dirty = False
 
-    # ---------------------------------------------------------------------------------------------------------------- step
-    def forward_backward(self, hori, vert, joints):
+    def _gcn_buffers(self, b):
+        bufs = self._gcn_bufs.get(b)
+        if bufs is None:
+            dev = self.device
+            rows = -(-(b * self.kp) // 128) * 128
+            mk = lambda: SplitTensor.empty((1, 1, 1, rows, 1024), dev, True, zero=True)     # padding rows stay zero: kernels write sample rows only
+            bufs = dict(rows=rows, st=[mk() for _ in range(3)], dy=[mk() for _ in range(2)], bias=[mk() for _ in range(3)])
+            self._gcn_bufs[b] = bufs
+        return bufs
+
+    def set_lr(self, lr):
+        self.hyper["lr"] = float(lr)
+
+    def _sync_lr(self):
+        if self.hyper["lr"] != self._lr_uploaded:       # host-side schedule (Runner.adjustLR) -> device scalar, outside any captured graph
+            self.lr_dev.fill_(float(self.hyper["lr"]))
+            self._lr_uploaded = float(self.hyper["lr"])
+
+    @contextlib.contextmanager
+    def _scope(self, batch, arena=True):
+        a = None
+        if arena:
+            a = self._arenas.get(batch)
+            if a is None:
+                a = self._arenas[batch] = ZeroArena(self.device)
+        with torch.cuda.device(self.device), ops.coop_scope(self.coop), ops.products(self.products), _arena_scope(a):
+            yield
+
+    # ---------------------------------------------------------------------------------------------------------------- forward
+    def _forward(self, hori, vert):
+        """Train-mode forward; returns (heatmap, gcn_heatmap) float32 [B,14,64,64] and keeps what the backward needs in self._saved."""
         if self._dirty:
             self._pack()
         model, nf, g, kp = self.model, self.nf, self.g, self.kp
@@ -459,8 +614,8 @@ class TrainStep(object):
         b = hori.shape[0]
         params = dict(model.named_parameters())
         buffers = dict(model.named_buffers())
-        grads = {}
-        # ---- forward
+        sv = self._saved = _Saved()
+        sv.hori, sv.vert, sv.b = hori, vert, b
         chirp = {}
         for key, x in (("ra", hori), ("re", vert)):
             chirp[key] = ops.mnet_fwd(x.contiguous(), self.mnet[key][0], self.mnet[key][1], _S((b, g, 64, 64, nf), dev))
@@ -475,122 +630,161 @@ class TrainStep(object):
         cat1 = _S((b, 1, 64, 64, 10 * nf), dev)
         ops.resample_linear(o2, 2 * nf, cat1)
         l1.forward(feats["ra"][0], feats["re"][0], cat1)
-        o1 = self.dblocks[5].forward(self.dblocks[4].forward(cat1))
+        sv.o1 = self.dblocks[5].forward(self.dblocks[4].forward(cat1))
         kpad = L.pad64(kp)
         logits = torch.empty((b, 64 * 64, kpad), dtype=torch.float32, device=dev)
-        ops.conv_gemm(o1, L.pad64(nf), self.head.w, kpad, out_f32=logits.view(b, 1, 64, 64, kpad))
-        rows = -(-(b * kp) // 128) * 128
+        ops.conv_gemm(sv.o1, L.pad64(nf), self.head.w, kpad, out_f32=logits.view(b, 1, 64, 64, kpad), lcin=nf, lcout=kp)
+        gb = self._gcn_buffers(b)
+        rows = gb["rows"]
         heat = torch.empty((b, kp, 64, 64), dtype=torch.float32, device=dev)
         gcn = torch.empty_like(heat)
-        st = [_S((1, 1, 1, rows, 1024), dev, zero=True) for _ in range(3)]          # St_0, St_1, St_2 (inputs of the three layers)
-        yt = [_S((1, 1, 1, rows, 1024), dev, zero=True) for _ in range(2)]          # Yt_1, Yt_2 (post-ReLU)
-        bias_rows = []
-        for bias in self.gcn_b:
-            t = torch.zeros(rows, 1024, dtype=torch.float32, device=dev)
-            t[:b * kp] = bias.t().repeat(b, 1)
-            bias_rows.append(SplitTensor.from_float(t.view(1, 1, 1, rows, 1024)))
-        relu = torch.zeros(1024, dtype=torch.float32, device=dev)
+        st = gb["st"]                                                               # St_0, St_1, St_2 (inputs of the three layers)
+        yt = [_S((1, 1, 1, rows, 1024), dev) for _ in range(2)]                     # Yt_1, Yt_2 (post-ReLU)
+        for i in range(3):
+            ops.gcn_bias_rows(self.gcn_b[i], b, gb["bias"][i])                      # bias[q][j] as residual rows [(b, j)][q]
+        relu = self.gcn_relu
         ops.gcn_nodes(logits, self.adj, heat, st[0])
-        ops.conv_gemm(st[0], 1024, self.gcn_w[0], 1024, residual=bias_rows[0], slope=relu, out=yt[0])
+        ops.conv_gemm(st[0], 1024, self.gcn_w[0], 1024, residual=gb["bias"][0], slope=relu, out=yt[0], lrows=b * kp)
         ops.gcn_mix(yt[0], self.adj, st[1], b)
-        ops.conv_gemm(st[1], 1024, self.gcn_w[1], 1024, residual=bias_rows[1], slope=relu, out=yt[1])
+        ops.conv_gemm(st[1], 1024, self.gcn_w[1], 1024, residual=gb["bias"][1], slope=relu, out=yt[1], lrows=b * kp)
         ops.gcn_mix(yt[1], self.adj, st[2], b)
-        y3 = torch.zeros((1, 1, 1, rows, 1024), dtype=torch.float32, device=dev)
-        ops.conv_gemm(st[2], 1024, self.gcn_w[2], 1024, residual=bias_rows[2], out_f32=y3)
+        y3 = torch.empty((1, 1, 1, rows, 1024), dtype=torch.float32, device=dev)
+        ops.conv_gemm(st[2], 1024, self.gcn_w[2], 1024, residual=gb["bias"][2], out_f32=y3, lrows=b * kp)
         ops.gcn_heads(y3.view(rows, 1024), gcn, b)
-        losses, _, _ = ops.heatmap_loss_fwd(heat, gcn, joints)
+        sv.st, sv.yt, sv.rows = st, yt, rows
+        sv.heat, sv.gcn = heat, gcn
         self.last_outputs = (heat, gcn)
-        # ---- backward: loss -> logits (two paths: direct sigmoid head, PRGCN)
-        dlogits = torch.zeros((b, 64 * 64, kpad), dtype=torch.float32, device=dev)
-        dpre = torch.empty((b, kp, 64, 64), dtype=torch.float32, device=dev)
-        ops.heatmap_loss_bwd(heat, gcn, joints, dlogits, dpre)
-        dy3f = torch.zeros((rows, 1024), dtype=torch.float32, device=dev)
+        return heat, gcn
+
+    # ---------------------------------------------------------------------------------------------------------------- backward
+    def _backward(self, dlogits, dpre):
+        """dlogits float32 [B, 4096, kpad] (gradient of the head logits through the direct sigmoid path; the PRGCN path is ADDED to it),
+        dpre float32 [B, 14, 64, 64] (gradient of the pre-sigmoid PRGCN maps) -> every parameter gradient, written into ``self.gview``."""
+        sv = self._saved
+        nf, g, kp = self.nf, self.g, self.kp
+        dev = dlogits.device
+        b, rows, st, yt = sv.b, sv.rows, sv.st, sv.yt
+        kpad = L.pad64(kp)
+        grads = dict(self.gview)
+        gb = self._gcn_buffers(b)
+        relu = self.gcn_relu
+        dy3f = _zeros((rows, 1024), torch.float32, dev)
         ops._call("hupr_gcn_heads_bwd", dpre.data_ptr(), dy3f.data_ptr(), b, ops._C.stream_ptr())
         dyt = _S((1, 1, 1, rows, 1024), dev)
         T.accumulate(dyt, 1024, f=dy3f)
         p = "radarDecoder."
         for layer in (2, 1, 0):
-            # dW[q][p] = sum_rows dYt[row][q] St[row][p]   (both operands transposed to rows-contiguous)
+            # dW[q][p] = sum_rows dYt[row][q] St[row][p]   (both operands transposed to rows-contiguous), written straight into the gradient
             a_t = ops.transpose_split(dyt, 1024, _S((1, 1024, rows), dev))
             s_t = ops.transpose_split(st[layer], 1024, _S((1, 1024, rows), dev))
-            dw = torch.empty((1, 1, 1, 1024, 1024), dtype=torch.float32, device=dev)
-            ops.conv_gemm(SplitTensor(a_t.hi.view(1, 1, 1, 1024, rows), a_t.lo.view(1, 1, 1, 1024, rows)), rows, s_t, 1024, out_f32=dw)
-            grads[p + "gcn.L%d.weight" % (layer + 1)] = dw.view(1024, 1024)
-            db = torch.empty((1024, kp), dtype=torch.float32, device=dev)
-            ops._call("hupr_gcn_bias_grad", dyt.hi.data_ptr(), dyt.lo.data_ptr(), db.data_ptr(), b, ops._C.stream_ptr())
-            grads[p + "gcn.L%d.bias" % (layer + 1)] = db
-            dst = ops.conv_gemm(dyt, 1024, self.gcn_wt[layer], 1024, out=_S((1, 1, 1, rows, 1024), dev))       # dSt = dYt W
+            ops.conv_gemm(SplitTensor(a_t.hi.view(1, 1, 1, 1024, rows), a_t.lo.view(1, 1, 1, 1024, rows)), rows, s_t, 1024,
+                          out_f32=grads[p + "gcn.L%d.weight" % (layer + 1)].view(1, 1, 1, 1024, 1024), lcin=b * kp)
+            ops._call("hupr_gcn_bias_grad", dyt.hi.data_ptr(), dyt.lo.data_ptr(), grads[p + "gcn.L%d.bias" % (layer + 1)].data_ptr(), b,
+                      ops._C.stream_ptr())
+            dst = ops.conv_gemm(dyt, 1024, self.gcn_wt[layer], 1024, out=_S((1, 1, 1, rows, 1024), dev), lrows=b * kp)       # dSt = dYt W
             if layer == 0:
                 ops._call("hupr_gcn_nodes_bwd", dst.hi.data_ptr(), dst.lo.data_ptr(), self.adj.data_ptr(), dlogits.data_ptr(), kpad, b, ops._C.stream_ptr())
             else:
-                dy_prev = _S((1, 1, 1, rows, 1024), dev, zero=True)
+                dy_prev = gb["dy"][layer - 1]
                 ops.gcn_mix(dst, self.adj_t, dy_prev, b)                                                     # dY = dSt A^T (per sample)
                 T.act_bwd(dy_prev, yt[layer - 1], 1024, relu, dy_prev)
                 dyt = dy_prev
         # ---- head conv and decoder
+        l3, l2, l1 = self.levels
         dlog = _S((b, 1, 64, 64, kpad), dev)
         T.accumulate(dlog, kpad, f=dlogits.view(-1, kpad))
-        self.head.wgrad(o1, 0, dlog, 0, grads)
+        self.head.wgrad(sv.o1, 0, dlog, 0, grads)
         d = self.head.dgrad(dlog, _S((b, 1, 64, 64, L.pad64(nf)), dev))
         dcat1 = self.dblocks[4].backward(self.dblocks[5].backward(d, 0, grads), 0, grads)
         dra1, dre1 = l1.backward(dcat1, grads)
-        acc = torch.zeros((b, 1, 32, 32, L.pad64(2 * nf)), dtype=torch.float32, device=dev)
+        acc = _zeros((b, 1, 32, 32, L.pad64(2 * nf)), torch.float32, dev)
         T.resample_linear_bwd((dcat1, 0), 2 * nf, acc)
         do2 = _S((b, 1, 32, 32, L.pad64(2 * nf)), dev)
         T.accumulate(do2, L.pad64(2 * nf), f=acc.view(-1, L.pad64(2 * nf)))
         dcat2 = self.dblocks[2].backward(self.dblocks[3].backward(do2, 0, grads), 0, grads)
         dra2, dre2 = l2.backward(dcat2, grads)
-        acc = torch.zeros((b, 1, 16, 16, 4 * nf), dtype=torch.float32, device=dev)
+        acc = _zeros((b, 1, 16, 16, 4 * nf), torch.float32, dev)
         T.resample_linear_bwd((dcat2, 0), 4 * nf, acc)
         do3 = _S((b, 1, 16, 16, 4 * nf), dev)
         T.accumulate(do3, 4 * nf, f=acc.view(-1, 4 * nf))
         dcat3 = self.dblocks[0].backward(self.dblocks[1].backward(do3, 0, grads), 0, grads)
         dra3, dre3 = l3.backward(dcat3, grads)
         # ---- encoders and chirp nets
-        for key, dfs, x in (("ra", (dra1, dra2, dra3), hori), ("re", (dre1, dre2, dre3), vert)):
+        for key, dfs, x in (("ra", (dra1, dra2, dra3), sv.hori), ("re", (dre1, dre2, dre3), sv.vert)):
             dchirp = self.enc[key].backward(dfs[0], dfs[1], dfs[2], grads)
             dfeat = _S((b, g, 64, 64, nf), dev)
             T.accumulate(dfeat, nf, a=(dchirp, 0))
-            dw = torch.zeros(nf * 4, dtype=torch.float64, device=dev)
-            db = torch.zeros(nf, dtype=torch.float64, device=dev)
+            dwb = _zeros((nf * 4 + nf,), torch.float64, dev)
             ops._call("hupr_mnet_bwd", x.data_ptr(), self.mnet[key][0].data_ptr(), self.mnet[key][1].data_ptr(), dfeat.hi.data_ptr(),
-                      dfeat.lo.data_ptr(), dw.data_ptr(), db.data_ptr(), b * g, ops._C.stream_ptr())
+                      dfeat.lo.data_ptr(), dwb.data_ptr(), dwb[nf * 4:].data_ptr(), b * g, ops._C.stream_ptr())
             net = "RAchirpNet" if key == "ra" else "REchirpNet"
-            grads[net + ".temporalConvWx1x1.weight"] = dw.float().view(nf, 2, 2, 1, 1)
-            grads[net + ".temporalConvWx1x1.bias"] = db.float()
-        # ---- scatter into the flat gradient buffer (views installed as param.grad)
-        for name, q in params.items():
-            g = grads[name]
-            if g.shape != q.shape and g.numel() == q.numel() and not g.is_contiguous():
-                q.grad.view(g.shape).copy_(g)                     # e.g. a conv filter gradient view [c, cin, taps] -> [c, cin, kd, kh, kw]
-            else:
-                q.grad.copy_(g.reshape(q.shape))
+            ops.reduce_f64(dwb, nf * 4, 1, grads[net + ".temporalConvWx1x1.weight"])
+            ops.reduce_f64(dwb[nf * 4:], nf, 1, grads[net + ".temporalConvWx1x1.bias"])
         self.last_grads = grads
+
+    # ---------------------------------------------------------------------------------------------------------------- step
+    def forward_backward(self, hori, vert, joints, loss_weights=(1.0, 1.0)):
+        """One pass of /root/reference/tools/run.py:76-78 (model.train() forward, LossComputer loss, loss.backward()).  ``loss_weights`` =
+        (alpha, beta) of loss = alpha*loss1 + beta*loss2 when TRAINING.lossDecay != -1 (misc/losses.py:36-42), (1, 1) otherwise.
+        Returns the device scalars (loss1 + loss2, loss2)."""
+        b = hori.shape[0]
+        dev = hori.device
+        kpad = L.pad64(self.kp)
+        with self._scope(b):
+            heat, gcn = self._forward(hori, vert)
+            losses, _, _ = ops.heatmap_loss_fwd(heat, gcn, joints)
+            dlogits = _zeros((b, 64 * 64, kpad), torch.float32, dev)
+            dpre = torch.empty((b, self.kp, 64, 64), dtype=torch.float32, device=dev)
+            ops.heatmap_loss_bwd(heat, gcn, joints, dlogits, dpre, weights=loss_weights)
+            self._backward(dlogits, dpre)
+        self.last_losses = losses
         return losses[0], losses[1]
+
+    def forward(self, hori, vert):
+        """Train-mode forward only (the autograd bridge of HuPRNet.forward): (heatmap, gcn_heatmap) float32 [B,14,64,64]."""
+        with self._scope(hori.shape[0], arena=False):
+            return self._forward(hori, vert)
+
+    def backward(self, g_heat, g_gcn):
+        """Backward of the last ``forward`` for caller-supplied output gradients dL/d heatmap, dL/d gcn_heatmap ([B,14,64,64] or None)."""
+        sv = self._saved
+        b, dev = sv.b, sv.heat.device
+        kpad = L.pad64(self.kp)
+        with self._scope(b, arena=False):
+            dlogits = _zeros((b, 64 * 64, kpad), torch.float32, dev)
+            dpre = torch.empty((b, self.kp, 64, 64), dtype=torch.float32, device=dev)
+            gh = None if g_heat is None else g_heat.reshape(b, self.kp, 64, 64).float().contiguous()
+            gg = None if g_gcn is None else g_gcn.reshape(b, self.kp, 64, 64).float().contiguous()
+            ops.heatmap_bwd(sv.heat, sv.gcn, gh, gg, dlogits, dpre)
+            self._backward(dlogits, dpre)
 
     def optimizer_step(self):
         self.step_count += 1
         h = self.hyper
-        self.step_dev.add_(1)          # device-side step counter: the bias corrections stay right under CUDA-graph replay
+        if not torch.cuda.is_current_stream_capturing():
+            self._sync_lr()
+        ops.bump_i32(self.step_dev)        # device-side step counter: the bias corrections stay right under CUDA-graph replay
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, lr=h["lr"], betas=h["betas"], eps=h["eps"],
-                      weight_decay=h["weight_decay"], step_dev=self.step_dev)
+                      weight_decay=h["weight_decay"], step_dev=self.step_dev, lr_dev=self.lr_dev)
         self._dirty = True
         self.model.invalidate()
 
-    def capture(self, hori, vert, joints, with_optimizer=True):
+    def capture(self, hori, vert, joints, with_optimizer=True, loss_weights=(1.0, 1.0)):
         """Capture forward_backward (+ the Adam launch) into one CUDA graph over the caller's STATIC input tensors; returns a
-        ``replay()`` callable whose result is the device tensor pair (loss, loss2).  The step launches ~1 150 kernels, so at small
-        batches the Python/ctypes launch path is the bottleneck; the graph removes it.  (With several ranks capture only
+        ``replay()`` callable whose result is the device tensor pair (loss, loss2).  The step is ~1 000 launches, so at small
+        batches the Python/ctypes launch path is the bottleneck; the graph removes it.  The learning rate and the Adam step count are
+        read from device scalars, so schedules keep working across replays.  (With several ranks capture only
         ``with_optimizer=False`` and run all_reduce_gradients() + optimizer_step() eagerly after each replay.)"""
         joints = joints.to(device=hori.device, dtype=torch.int64).contiguous()
-        for _ in range(2):                       # warm-up: lazy function attributes, allocator high-water mark
-            self.forward_backward(hori, vert, joints)
+        for _ in range(2):                       # warm-up: lazy buffers, the scratch arena's planning pass, allocator high-water mark
+            self.forward_backward(hori, vert, joints, loss_weights)
             if with_optimizer:
                 self.optimizer_step()
         torch.cuda.synchronize()
+        self._dirty = True                       # the operand re-pack is part of the graph: replays see the weights of the latest Adam launch
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.forward_backward(hori, vert, joints)
+            out = self.forward_backward(hori, vert, joints, loss_weights)
             if with_optimizer:
                 self.optimizer_step()
         self._graph = graph
@@ -600,6 +794,7 @@ class TrainStep(object):
         def replay():
             if with_optimizer:
                 self.step_count += 1             # the device-side counter (step_dev) is advanced by the captured graph itself
+                self._sync_lr()
             graph.replay()
             return out
         return replay
@@ -608,3 +803,32 @@ class TrainStep(object):
         """Data-parallel training (SURVEY.md §8 e): ONE sum all-reduce over the flat gradient buffer, then divide by the world size."""
         from .sharding import average_gradients
         average_gradients(self.flat_g)
+
+    # ---------------------------------------------------------------------------------------------------------------- ingest
+    def prefetch(self, hori, vert, joints):
+        """Start the asynchronous upload of the NEXT batch (pinned host tensors) on a copy stream while the current step computes — the
+        training-side counterpart of RadarPoseStream.prefetch.  ``step_prefetched()`` then trains on it."""
+        dev = self.device
+        st = getattr(self, "_ingest", None)
+        if st is None or st["hori"].shape != hori.shape:
+            st = self._ingest = dict(hori=torch.empty(hori.shape, dtype=torch.float32, device=dev),
+                                     vert=torch.empty(vert.shape, dtype=torch.float32, device=dev),
+                                     joints=torch.empty(joints.shape, dtype=torch.int64, device=dev),
+                                     stream=torch.cuda.Stream(device=dev), uploaded=torch.cuda.Event(), consumed=torch.cuda.Event())
+            st["consumed"].record(torch.cuda.current_stream(dev))
+        st["stream"].wait_event(st["consumed"])          # the previous staging contents have been handed to the step
+        with torch.cuda.stream(st["stream"]):
+            st["hori"].copy_(hori, non_blocking=True)
+            st["vert"].copy_(vert, non_blocking=True)
+            st["joints"].copy_(joints, non_blocking=True)
+            st["uploaded"].record(st["stream"])
+
+    def take_prefetched(self, hori, vert, joints):
+        """Move the batch uploaded by the last ``prefetch`` into the step's static input tensors (device-to-device, stream-ordered)."""
+        st = self._ingest
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(st["uploaded"])
+        hori.copy_(st["hori"], non_blocking=True)
+        vert.copy_(st["vert"], non_blocking=True)
+        joints.copy_(st["joints"], non_blocking=True)
+        st["consumed"].record(main)

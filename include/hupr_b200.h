@@ -99,6 +99,9 @@ typedef struct hupr_conv_desc {
                                                                      be shared by launches that may run concurrently (different streams) */
     int no_tma_store;                                             /* 1: keep the thread-per-row global stores even where the shared-memory-staged TMA-store
                                                                      epilogue applies (row tiles: w a multiple of 128, bf16 split output) — for A/B measurements */
+    int nprod;                                                    /* tensor-core products per k-step: 0 = by operands (3 when the lo planes are given, else 1);
+                                                                     1 = hi*hi only although lo planes exist (they are not read): plain bf16 compute with fp32
+                                                                     accumulation, the precision BASELINE.json configs[3] names for training; 3 = require lo planes */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
@@ -131,7 +134,7 @@ int hupr_attention_fwd(const hupr_attn_desc* desc, void* stream);
  * the residual), ADDS  dQ = dS K,  dK = dS^T Q,  dV = P^T dO  to fp32 buffers, where P = exp(Q K^T - lse), dS = P o (dO V^T - rowdot)
  * (autograd of /root/reference/models/layers.py:126-133).  q, k, v, do: bf16 split rows [batch][s][*_ld] with the 64 channels at *_off
  * (v is NOT transposed here); dq, dk, dv: float [batch][s][*_ld] at *_off, zero-filled (or holding earlier contributions) by the caller.
- * s a multiple of 128.  First version: not yet called by the training step. */
+ * s a multiple of 128.  Called by hupr_b200.training.TrainStep for the head-dim-64 level. */
 typedef struct hupr_attn_bwd_desc {
     const void* q_hi; const void* q_lo; int q_ld, q_off;
     const void* k_hi; const void* k_lo; int k_ld, k_off;
@@ -235,9 +238,9 @@ int hupr_heatmap_loss_fwd(const float* heatmap, const float* gcn_heatmap, const 
                           void* workspace, size_t ws_bytes, float* losses, float* targets, float* gt2d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Training building blocks (the complete backward pass is not assembled yet).
+ * Training building blocks (hupr_b200/training.py assembles them into the whole backward pass).
  *
- * hupr_heatmap_loss_bwd: gradient of loss = BCE(heatmap, T) + BCE(gcn_heatmap, T) (mean reduction, lossDecay == -1) with respect to the
+ * hupr_heatmap_loss_bwd: gradient of loss = w1*BCE(heatmap, T) + w2*BCE(gcn_heatmap, T) (mean reduction) with respect to the
  * pre-sigmoid values — what autograd computes for /root/reference/misc/losses.py:23-48 + the sigmoids of models/networks.py:40 and
  * models/gcn_networks.py:64.  d_heat_logits: float channels-last [batch][4096][ld] (first 14 channels written; the layout of the head
  * convolution's output), d_gcn_pre: float [batch][14][64][64].
@@ -331,15 +334,51 @@ typedef struct hupr_wgrad_desc {
     int kd, kh, kw, pd, ph, pw;
     float* dw; int dw_ld;
     int batched; long long dw_batch_stride;
+    int nprod;                               /* 0 / 3: three products per k-step (fp32-equivalent); 1: hi*hi only (the lo planes are not read) */
 } hupr_wgrad_desc;
 int hupr_conv_wgrad(const hupr_wgrad_desc* desc, void* stream);
 
-int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld,
+int hupr_heatmap_loss_bwd(const float* heatmap, const float* gcn_heatmap, const long long* joints, int batch, int ld, float w1, float w2,
                           float* d_heat_logits, float* d_gcn_pre, void* stream);
+/* w1, w2: weights of the two BCE terms, loss = w1*BCE(heatmap, T) + w2*BCE(gcn_heatmap, T): (1, 1) for lossDecay == -1, else the
+ * (alpha, beta) schedule of /root/reference/misc/losses.py:36-42.
+ *
+ * hupr_heatmap_bwd: the same two sigmoid backward steps for CALLER-SUPPLIED output gradients g_heat, g_gcn = dL/d(heatmap),
+ * dL/d(gcn_heatmap) (float [batch][14][64][64], either may be NULL = zero) — what loss.backward() feeds into the model's outputs when the
+ * loss is computed outside the library (/root/reference/tools/run.py:77-78); same output layouts as hupr_heatmap_loss_bwd. */
+int hupr_heatmap_bwd(const float* heatmap, const float* gcn_heatmap, const float* g_heat, const float* g_gcn, int batch, int ld,
+                     float* d_heat_logits, float* d_gcn_pre, void* stream);
 int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, const int* step_dev, void* stream);
+                   float beta2, float eps, float weight_decay, int step, const int* step_dev, const float* lr_dev, void* stream);
 /* step_dev: optional DEVICE int holding the step count; when given it replaces `step`, so a CUDA-graph replay of the launch keeps
- * the bias corrections advancing. */
+ * the bias corrections advancing.  lr_dev: optional DEVICE float holding the learning rate; when given it replaces `lr`, so the
+ * reference's schedule (adjustLR, /root/reference/tools/base.py:66-72) keeps acting on a captured step. */
+
+/* ---------------------------------------------------------------------------------------------
+ * Parameter-layout kernels of the training step (csrc/pack.cu).  The optimiser updates one flat fp32 buffer in torch's layouts
+ * (what /root/reference/tools/base.py:47 optim.Adam sees); the tensor-core kernels read hi/lo bf16 operand layouts.  These entry points
+ * convert inside the captured step, so no framework kernel runs between hupr_adam_step and the next forward.
+ *   hupr_pack_conv_weights  w fp32 [cout][cin][taps] (torch conv layout, taps = kd*kh*kw <= 32) ->
+ *                             fwd  [taps][cout_total][cin_pad] at rows cout_off..   (hupr_conv_desc.w_*; fwd_lo optional)
+ *                             dgrad [taps][cin_pad][cout_total] with the tap order reversed, columns cout_off..  (the flipped/transposed
+ *                             filter of the data-gradient convolution; dgrad_* optional).  Padding cells are never written: zero the
+ *                             buffers once.  cout, cin, cout_off, cin_pad, cout_total must be even.
+ *   hupr_unpack_wgrad       acc fp32 [taps][cin_pad][cout_total] (hupr_conv_wgrad's result) -> dst fp32 [cout][cin][taps], output channels
+ *                             cout_off .. cout_off+cout  (the parameter's .grad in torch layout)
+ *   hupr_reduce_f64         dst[g] = (float) sum_{i<n} src[g*n + i]   (double partial sums of hupr_channel_sums / hupr_mnet_bwd -> fp32 gradients)
+ *   hupr_broadcast_f32      dst[0..n) = *src   (nn.PReLU's single slope -> the per-channel slope array of the conv epilogue)
+ *   hupr_gcn_bias_rows      bias fp32 [1024][14] -> bf16 split rows [(b,j)][1024] = bias[q][j] (zero rows past batch*14): the residual operand
+ *                             of the transposed-layout GCN GEMMs (/root/reference/models/gcn_networks.py:23-29)
+ *   hupr_bump_i32           ++*counter (the device-side Adam step count of hupr_adam_step.step_dev)
+ *   hupr_memset_zero        cudaMemsetAsync(dst, 0, bytes) on `stream` (a memset node under CUDA-graph capture) */
+int hupr_pack_conv_weights(const float* w, int cout, int cin, int taps, void* fwd_hi, void* fwd_lo, int cout_total, int cin_pad, int cout_off,
+                           void* dgrad_hi, void* dgrad_lo, void* stream);
+int hupr_unpack_wgrad(const float* acc, int taps, int cin_pad, int cout_total, int cout_off, float* dst, int cout, int cin, void* stream);
+int hupr_reduce_f64(const double* src, int groups, int n, float* dst, void* stream);
+int hupr_broadcast_f32(const float* src, float* dst, int n, void* stream);
+int hupr_gcn_bias_rows(const float* bias, int batch, int rows, void* rows_hi, void* rows_lo, void* stream);
+int hupr_bump_i32(int* counter, void* stream);
+int hupr_memset_zero(void* dst, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

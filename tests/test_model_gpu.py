@@ -283,7 +283,7 @@ def test_c_abi_edge_cases_zero_sizes_alignment_and_bad_shapes():
     assert lib.hupr_fft_cascade_i16(p + 2, p, 1, s) == -2                                   # HUPR_ERR_ALIGNMENT
     assert lib.hupr_softmax_rows(p, p, p, 4, 4100, s) == -1 and lib.hupr_softmax_rows(p, p, p, 4, 6, s) == -1      # cols > 4096 / not % 4
     assert lib.hupr_heatmap_loss_fwd(p, p, p, 2, p, 8, p, None, None, s) == -5             # HUPR_ERR_WORKSPACE
-    assert lib.hupr_adam_step(p, p, p, p, 16, 1e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None, s) == -1      # step < 1 without a device counter
+    assert lib.hupr_adam_step(p, p, p, p, 16, 1e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None, None, s) == -1      # step < 1 without a device counter
     d = _C.AttnDesc()
     x = SplitTensor.empty((1, 1, 1, 128, 96), "cuda", zero=True)
     d.q_hi = d.k_hi = d.vt_hi = d.o_hi = x.hi.data_ptr()
