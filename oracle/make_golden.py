@@ -198,8 +198,54 @@ def make_cocoeval():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "cocoeval_reference.npz"), **out)
 
 
+TRAIN_CASE = dict(batch=2, seed=1, joints_seed=3)       # the inputs tests/test_training_step_gpu.py feeds the whole-step tests
+GRAD_STRIDE = 499                                        # every 499th element of each flattened gradient is stored
+
+
+def train_case_inputs():
+    import torch
+    from . import model as om
+    sd = om.make_state_dict(TRAIN_CASE["seed"])
+    hori, vert = om.make_vrdae(TRAIN_CASE["batch"], TRAIN_CASE["seed"])
+    joints = torch.randint(0, 256, (TRAIN_CASE["batch"], 14, 2), generator=torch.Generator().manual_seed(TRAIN_CASE["joints_seed"]))
+    return sd, hori, vert, joints
+
+
+def make_train():
+    """One reference training pass (tools/run.py:66,76-78): HuPRNet.train() forward (batch-statistics BatchNorm), LossComputer.computeLoss,
+    loss.backward() — on the oracle's seeded weights / inputs.  Stored: the two losses, for each of the 165 parameters a strided
+    sample + (sum, sum of squares, max |.|) of its gradient, and the running statistics the pass leaves in every BatchNorm."""
+    import torch
+    cls = ref_shim.load_model_classes()
+    LossComputer, _, _ = ref_shim.load_misc()
+    sd, hori, vert, joints = train_case_inputs()
+    net = cls["HuPRNet"](ref_shim.load_cfg())
+    net.load_state_dict(sd)
+    net.train()
+    lc = LossComputer(ref_shim.load_cfg(), torch.device("cpu"))
+    preds = net(hori, vert)
+    loss, loss2, pred2d, gt2d = lc.computeLoss(preds, joints)
+    loss.backward()
+    out = {"loss": np.array(float(loss.detach())), "loss2": np.array(float(loss2.detach())), "pred2d": np.asarray(pred2d), "gt2d": np.asarray(gt2d),
+           "batch": np.array(TRAIN_CASE["batch"]), "seed": np.array(TRAIN_CASE["seed"]), "joints": joints.numpy(),
+           "grad_stride": np.array(GRAD_STRIDE)}
+    names = []
+    for name, q in net.named_parameters():
+        g = q.grad.detach().reshape(-1)
+        names.append(name)
+        out["g/" + name] = g[::GRAD_STRIDE].numpy().copy()
+        out["s/" + name] = tensor_stats(g)
+    for name, buf in net.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            out["b/" + name] = buf.detach().numpy().copy()
+    out["names"] = np.array(names)
+    assert len(names) == 165
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "train_reference.npz"), **out)
+    print("train", float(loss), float(loss2), len(names), "gradients")
+
+
 TARGETS = {"cascade": make_cascade, "dca": make_dca, "model": make_model, "loss": make_loss, "loader": make_loader,
-           "cocoeval": make_cocoeval}
+           "cocoeval": make_cocoeval, "train": make_train}
 
 
 def main(argv):

@@ -215,3 +215,32 @@ def test_tma_store_epilogue_is_bit_identical_to_row_stores(shape):
     ref = torch.where(ref > 0, ref, 0.1 * ref)
     got = outs[1].float()[:, 0, :, :, o_off:o_off + cout].double()
     assert float((got - ref).abs().max()) < 3e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", [
+    (8, 64, 128, 4, 32, 32, (3, 3, 3), (1, 1, 1)),      # halo-reuse kernel, BN = 128
+    (3, 64, 64, 8, 64, 64, (3, 3, 3), (1, 1, 1)),       # halo-reuse kernel, BN = 64
+    (1, 128, 256, 2, 16, 16, (3, 3, 3), (1, 1, 1)),     # generic kernel (small grid)
+    (8, 128, 128, 1, 128, 128, (1, 1, 1), (0, 0, 0)),   # generic kernel, row tiles: TMA-store epilogue
+])
+def test_single_product_mode_on_split_tensors_equals_bf16_operand_reference(shape):
+    """hupr_conv_desc.nprod = 1 (the bf16 training mode): the lo planes exist but only hi*hi is contracted.  Reference = the float64
+    convolution of the bf16-ROUNDED operands, so the comparison isolates the kernel (fp32 accumulation: 2e-5), and the result is written
+    as a full hi/lo pair."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor, conv_gemm
+    n, cin, cout, d, h, w, kernel, pad = shape
+    torch.manual_seed(5)
+    x = torch.randn(n, cin, d, h, w, device="cuda")
+    wt = torch.randn(cout, cin, *kernel, device="cuda") / (cin * kernel[0] * kernel[1] * kernel[2]) ** 0.5
+    A = SplitTensor.from_float(to_cl(x, cin))
+    W = pack_weight(wt, cin, cout)
+    out = SplitTensor.empty((n, d, h, w, cout), "cuda")
+    with ops.products(1):
+        conv_gemm(A, cin, W, cout, kernel=kernel, pad=pad, out=out)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.bfloat16().double(), wt.bfloat16().double(), padding=pad).float()
+    got = out.float().permute(0, 4, 1, 2, 3)
+    assert rel_err(got, ref) < 2e-5
+    full = F.conv3d(x.double(), wt.double(), padding=pad).float()
+    assert 1e-4 < rel_err(got, full) < 3e-2               # and it IS the single-product result, not the 3-product one

@@ -68,3 +68,24 @@ def test_window_indices_equal_clamp_closed_form():
         last = first + loader.DURATION - 1
         expect = [min(max(index - 4 + j, first), last) for j in range(8)]
         assert loader.window_indices(index) == expect
+
+
+def test_training_oracle_matches_reference_train_golden(golden_dir):
+    """oracle.model.training_gradients (train-mode forward + BCE + autograd) against ONE training pass of the unmodified reference
+    (HuPRNet.train(), LossComputer.computeLoss, loss.backward() — tools/run.py:66,76-78), minted by `make_golden train`: losses and
+    every one of the 165 parameter gradients (strided samples + checksums)."""
+    from oracle.make_golden import GRAD_STRIDE, train_case_inputs
+    g = np.load(os.path.join(golden_dir, "train_reference.npz"))
+    assert int(g["grad_stride"]) == GRAD_STRIDE
+    sd, hori, vert, joints = train_case_inputs()
+    assert np.array_equal(joints.numpy(), g["joints"])
+    total, loss2, grads = om.training_gradients(sd, hori, vert, joints.numpy())
+    assert abs(total - float(g["loss"])) < 2e-6 and abs(loss2 - float(g["loss2"])) < 2e-6
+    names = [str(n) for n in g["names"]]
+    assert len(names) == 165 and sorted(names) == sorted(grads)
+    for name in names:
+        got = grads[name].reshape(-1)
+        ref_stats = g["s/" + name]
+        scale = max(float(ref_stats[2]), 1e-30)
+        assert float(np.abs(got[::GRAD_STRIDE].numpy() - g["g/" + name]).max()) <= 1e-5 * scale + 1e-9, name
+        np.testing.assert_allclose(tensor_stats(got)[1:], ref_stats[1:], rtol=1e-4, err_msg=name)

@@ -94,3 +94,24 @@ def test_matmul_tn_batched_matches_float64(shape):
     ref = torch.matmul(a.double().transpose(1, 2), bm.double()[:, :, off:off + c])
     err = float(((out.double() - 0.25) - ref).abs().max() / ref.abs().max())
     assert err < 3e-5, err
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[5]])
+def test_wgrad_single_product_mode_equals_bf16_operand_reference(shape):
+    """hupr_wgrad_desc.nprod = 1 (bf16 training mode): only the hi planes are contracted; reference = float64 autograd on the
+    bf16-rounded operands."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    n, cin, cout, d, h, w, kernel, pad = shape
+    torch.manual_seed(23)
+    x = torch.randn(n, cin, d, h, w, device="cuda")
+    dy = torch.randn(n, cout, d + 2 * pad[0] - kernel[0] + 1, h, w, device="cuda")
+    wt = torch.zeros(cout, cin, *kernel, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.bfloat16().double(), wt, padding=pad).backward(dy.bfloat16().double())
+    X = SplitTensor.from_float(x.permute(0, 2, 3, 4, 1).contiguous())
+    DY = SplitTensor.from_float(dy.permute(0, 2, 3, 4, 1).contiguous())
+    out = ops.conv_wgrad_direct(X, 0, cin, DY, 0, cout, kernel, pad, nprod=1)
+    torch.cuda.synchronize()
+    got = out.permute(2, 1, 0).reshape(cout, cin, *kernel).double()
+    err = float((got - wt.grad).abs().max() / wt.grad.abs().max())
+    assert err < 3e-5, err
