@@ -92,6 +92,7 @@ SIGNATURES = {
     "hupr_version": (ctypes.c_int, []),
     "hupr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "hupr_launch_count": (ctypes.c_longlong, []),
+    "hupr_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
     "hupr_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), ctypes.c_void_p]),

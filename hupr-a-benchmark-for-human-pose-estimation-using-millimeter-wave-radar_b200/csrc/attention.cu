@@ -115,6 +115,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t tmem_O = tmem_base + Cfg::kTmemO;
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
 
     if (warp == 0) {
         // ================= TMA producer: K ring and V ring are independent (K_j is free as soon as Q K_j^T retires) =================
@@ -383,7 +385,7 @@ static int launch_attention(const hupr_attn_desc* d, cudaStream_t stream) {
     p.s = d->s;
     p.lse = d->lse;
     const dim3 grid(d->s / AT_BM, d->batch);
-    attention_kernel<D, BKV><<<grid, AT_THREADS, AT_SMEM, stream>>>(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p);
+    launch_k(attention_kernel<D, BKV>, grid, dim3(AT_THREADS), (size_t)AT_SMEM, stream, q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

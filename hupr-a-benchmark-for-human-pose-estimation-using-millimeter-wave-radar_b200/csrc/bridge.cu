@@ -44,6 +44,8 @@ __device__ __forceinline__ void reduce_by_quad(float (&v)[4], float* scratch /* 
 // passes 2 and 3 hit L2.  Thread t owns float4 index t + 512*k, i.e. a fixed elevation pair 2*(t&3), 2*(t&3)+1.
 __global__ void __launch_bounds__(kNormThreads)
 window_normalize_kernel(const float4* __restrict__ cube, const int* __restrict__ slot_fs, float* __restrict__ vrdae) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float scratch[(kNormThreads / 32) * 16];
     const int c = blockIdx.x;                       // kept Doppler row 0..7 -> cube row 4 + c (dataset.py:145)
     const int slot = blockIdx.y;
@@ -89,6 +91,8 @@ window_normalize_kernel(const float4* __restrict__ cube, const int* __restrict__
 __global__ void __launch_bounds__(256)
 mnet_kernel(const float* __restrict__ vrdae, const float* __restrict__ weight, const float* __restrict__ bias,
             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int n_slots) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float sW[32 * 4 + 32];
     if (threadIdx.x < 160) sW[threadIdx.x] = threadIdx.x < 128 ? __ldg(weight + threadIdx.x) : __ldg(bias + threadIdx.x - 128);
     __syncthreads();
@@ -131,6 +135,8 @@ mnet_kernel(const float* __restrict__ vrdae, const float* __restrict__ weight, c
 // Plane statistics: one CTA per (frame-sensor, kept Doppler row) -> mean and 1/std (unbiased) of the 16 (re|im, elevation) planes.
 __global__ void __launch_bounds__(kNormThreads)
 plane_stats_kernel(const float4* __restrict__ cube, float* __restrict__ stats /* [n_fs][8][2 mean|rstd][4 quad][4] */) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float scratch[(kNormThreads / 32) * 16];
     const int c = blockIdx.x, fs = blockIdx.y;
     const float4* plane = cube + ((size_t)fs * 16 + 4 + c) * kPlaneF4;
@@ -168,6 +174,8 @@ __global__ void __launch_bounds__(256)
 frame_features_kernel(const float4* __restrict__ cube, const float* __restrict__ stats, const float* __restrict__ weight,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                       int fs0, int n_fs) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float sW[32 * 4 + 32];
     __shared__ float sStat[8 * 32];
     if (threadIdx.x < 160) sW[threadIdx.x] = threadIdx.x < 128 ? __ldg(weight + threadIdx.x) : __ldg(bias + threadIdx.x - 128);
@@ -223,6 +231,8 @@ struct ResampleParams {
 __global__ void __launch_bounds__(256)
 resample_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, const ResampleParams p) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     const size_t total = (size_t)p.n * p.dout * p.ho * p.wo * p.c8;
     for (size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (size_t)gridDim.x * 256) {
         size_t t = gid;
@@ -265,6 +275,8 @@ resample_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __
 // One CTA (256 threads) per row; cols in {256, 512, ..., 4096} (multiple of 4, <= 4096).
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo, int cols) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float red[8];
     const size_t row = blockIdx.x;
     const float4* src = reinterpret_cast<const float4*>(logits + row * cols);
@@ -323,6 +335,8 @@ softmax_rows_kernel(const float* __restrict__ logits, __nv_bfloat16* __restrict_
 // in [n][s][in_ld] (channels in_off .. in_off + c) -> out [n][c][s]; 32x32 tiles, block (32, 8).
 __global__ void __launch_bounds__(256)
 transpose_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int s, int c, int in_ld, int in_off) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ uint16_t tile[32][34];
     const int n = blockIdx.z;
     const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -360,7 +374,7 @@ extern "C" int hupr_window_normalize(const void* cube, const int32_t* slot_fs, i
     if (((uintptr_t)cube | (uintptr_t)vrdae) & 15) return HUPR_ERR_ALIGNMENT;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
-    window_normalize_kernel<<<dim3(8, n_slots), kNormThreads, 0, (cudaStream_t)stream>>>(
+    launch_k(window_normalize_kernel, dim3(dim3(8, n_slots)), dim3(kNormThreads), (size_t)(0), (cudaStream_t)stream, 
         static_cast<const float4*>(cube), slot_fs, vrdae);
     return launch_status();
 }
@@ -377,7 +391,7 @@ extern "C" int hupr_plane_stats(const void* cube, int n_frame_sensors, void* wor
     if (((uintptr_t)cube | (uintptr_t)workspace) & 15) return HUPR_ERR_ALIGNMENT;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
-    plane_stats_kernel<<<dim3(8, n_frame_sensors), kNormThreads, 0, (cudaStream_t)stream>>>(static_cast<const float4*>(cube),
+    launch_k(plane_stats_kernel, dim3(dim3(8, n_frame_sensors)), dim3(kNormThreads), (size_t)(0), (cudaStream_t)stream, static_cast<const float4*>(cube),
                                                                                           static_cast<float*>(workspace));
     return launch_status();
 }
@@ -390,7 +404,7 @@ extern "C" int hupr_frame_features(const void* cube, const void* stats, int firs
     if (((uintptr_t)cube | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) return HUPR_ERR_ALIGNMENT;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
-    frame_features_kernel<<<n_frame_sensors * (kPlaneCells / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(frame_features_kernel, dim3(n_frame_sensors * (kPlaneCells / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         static_cast<const float4*>(cube), static_cast<const float*>(stats), weight, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
         first_frame_sensor, n_frame_sensors);
     return launch_status();
@@ -405,7 +419,7 @@ extern "C" int hupr_mnet_fwd(const float* vrdae, const float* weight, const floa
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
     const size_t total = (size_t)n_slots * kPlaneCells;
-    mnet_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(mnet_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         vrdae, weight, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, n_slots);
     return launch_status();
 }
@@ -428,7 +442,7 @@ extern "C" int hupr_resample_linear(const void* in_hi, const void* in_lo, int n,
     const size_t total = (size_t)n * dout * ho * wo * p.c8;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    resample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+    launch_k(resample_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
                                                                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, p);
     return launch_status();
 }
@@ -440,7 +454,7 @@ extern "C" int hupr_softmax_rows(const float* logits, void* p_hi, void* p_lo, lo
     if (((uintptr_t)logits | (uintptr_t)p_hi | (uintptr_t)p_lo) & 15) return HUPR_ERR_ALIGNMENT;
     int rc = check_sm100();
     if (rc != HUPR_OK) return rc;
-    softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo, cols);
+    launch_k(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), (size_t)(0), (cudaStream_t)stream, logits, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo, cols);
     return launch_status();
 }
 
@@ -455,8 +469,8 @@ extern "C" int hupr_transpose_split(const void* in_hi, const void* in_lo, int n,
         !(((uintptr_t)in_hi | (uintptr_t)in_lo) & 15) && !(((uintptr_t)out_hi | (uintptr_t)out_lo) & 3))
         return fast_transpose_dense(in_hi, in_lo, n, s, c, in_ld, in_ch_off, out_hi, out_lo, (cudaStream_t)stream);      // transpose.cu
     const dim3 grid(s / 32, c / 32, n), block(32, 8);
-    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_hi, (uint16_t*)out_hi, s, c, in_ld, in_ch_off);
-    if (in_lo) transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
+    launch_k(transpose_kernel, dim3(grid), dim3(block), (size_t)(0), (cudaStream_t)stream, (const uint16_t*)in_hi, (uint16_t*)out_hi, s, c, in_ld, in_ch_off);
+    if (in_lo) launch_k(transpose_kernel, dim3(grid), dim3(block), (size_t)(0), (cudaStream_t)stream, (const uint16_t*)in_lo, (uint16_t*)out_lo, s, c, in_ld, in_ch_off);
     return launch_status(in_lo ? 2 : 1);
 }
 

@@ -1,5 +1,6 @@
 // Miscellaneous C-ABI entry points (version, error strings).
 #include <atomic>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -7,6 +8,18 @@ static std::atomic<long long> g_launches{0};
 
 namespace hupr {
 void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("HUPR_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 int device_index() {
     int dev = -1;
@@ -45,7 +58,14 @@ int device_sm_count() {
 
 extern "C" long long hupr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int hupr_version(void) { return 100; }
+extern "C" int hupr_version(void) { return 200; }
+
+namespace hupr { void set_pdl(int on); }
+extern "C" int hupr_set_pdl(int on) {
+    const int prev = hupr::pdl_enabled() ? 1 : 0;
+    hupr::set_pdl(on);
+    return prev;
+}
 
 extern "C" const char* hupr_error_string(int code) {
     switch (code) {

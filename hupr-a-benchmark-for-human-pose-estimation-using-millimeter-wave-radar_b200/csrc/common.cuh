@@ -22,6 +22,33 @@ constexpr int kMaxDevices = 64;
 int device_index();            // current CUDA device ordinal, or -1
 int device_check_sm100();      // HUPR_OK on an sm_100 device, HUPR_ERR_ARCH otherwise (HUPR_ERR_CUDA if the query fails)
 int device_sm_count();         // multiprocessor count of the current device (0 if the query fails)
+// Programmatic dependent launch (PDL).  Kernels of the latency-bound inference chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (launch_k below, when pdl_enabled()): the next kernel of the stream may start —
+// block scheduling, barrier init, TMEM allocation, tensor-map prefetch — while its predecessor is still running.  Contract for every
+// kernel launched through launch_k: all threads execute pdl_wait() before the first access to global memory (it returns once the
+// predecessor grid has completed and its writes are visible), then pdl_launch_dependents() so the successor's prologue overlaps this
+// kernel's body.  Both instructions are no-ops in a kernel launched without the attribute.
+bool pdl_enabled();            // capi.cu: HUPR_PDL environment switch / hupr_set_pdl()
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError() at the call site
+}
+#endif
 // Opt-in dynamic shared memory for `func` on the current device, once per (kernel, device): `flags` is a per-kernel static array.
 template <typename F>
 static inline int ensure_smem_optin(F func, int bytes, bool (&flags)[kMaxDevices]) {

@@ -101,6 +101,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
 
     // item -> (k slice, column tile, sample, depth slice, h block, w block); consecutive items share the weight tile
     auto decode = [&](int item, int& kb_begin, int& kb_end, int& n0, int& n, int& od, int& h0, int& w0) {
@@ -416,7 +418,7 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     const long long items = (long long)pp.m_tiles * pp.n_tiles * pp.k_split;
     if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
     dim3 grid((unsigned)(items < num_sms ? items : num_sms), 1, 1);
-    conv_gemm_kernel<BN, NPROD, TSTORE><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, pp);
+    launch_k(conv_gemm_kernel<BN, NPROD, TSTORE>, grid, dim3(kConvThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, pp);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
-template <int BN>
+template <int BN, int NPROD>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p,
@@ -65,7 +65,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
-    const bool three = g.nprod == 3;
+    constexpr bool three = NPROD == 3;      // compile-time: the single-thread MMA issue loop carries no runtime branches
     const int total_tiles = g.m_tiles * g.n_tiles;
 
     if (threadIdx.x == 0) {
@@ -88,6 +88,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
 
     // tile -> (weight column tile, sample, depth slice, h block); tiles that run concurrently share the weight tile
     auto decode = [&](int tile, int& n0, int& n, int& od, int& h0) {
@@ -235,12 +237,12 @@ static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int 
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-template <int BN>
+template <int BN, int NPROD>
 static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
     static bool configured[kMaxDevices] = {};
     const int smem_max = 232448;
-    if (int crc = ensure_smem_optin(conv_halo_kernel<BN>, smem_max, configured)) return crc;
+    if (int crc = ensure_smem_optin(conv_halo_kernel<BN, NPROD>, smem_max, configured)) return crc;
     const int smem = g.stages * g.stage_bytes + 1024 + 256;
     if (smem > smem_max) return HUPR_ERR_BAD_ARG;
     const int num_sms = device_sm_count();
@@ -250,7 +252,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     gg.n_tiles = p.cout / BN;
     const int total = gg.m_tiles * gg.n_tiles;
     dim3 grid(total < num_sms ? total : num_sms, 1, 1);
-    conv_halo_kernel<BN><<<grid, kHaloThreads, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p, gg);
+    launch_k(conv_halo_kernel<BN, NPROD>, grid, dim3(kHaloThreads), (size_t)smem, stream, a_hi, a_lo, b_hi, b_lo, p, gg);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
@@ -300,8 +302,11 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     if ((rc = encode_halo_act_map(&a_lo, three ? d->a_lo : d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
     if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
-    return bn == 128 ? launch_halo<128>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
-                     : launch_halo<64>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
+    if (three)
+        return bn == 128 ? launch_halo<128, 3>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
+                         : launch_halo<64, 3>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
+    return bn == 128 ? launch_halo<128, 1>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
+                     : launch_halo<64, 1>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
 }
 
 }  // namespace hupr

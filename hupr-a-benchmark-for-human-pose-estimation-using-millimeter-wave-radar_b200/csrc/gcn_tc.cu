@@ -21,6 +21,8 @@ __device__ __forceinline__ float gsigmoid(float x) { return 1.0f / (1.0f + expf(
 __global__ void __launch_bounds__(256)
 gcn_nodes_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ adj, float* __restrict__ heatmap,
                  __nv_bfloat16* __restrict__ s_hi, __nv_bfloat16* __restrict__ s_lo, int batch) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float sA[kGJ * kGJ];
     if (threadIdx.x < kGJ * kGJ) sA[threadIdx.x] = __ldg(adj + threadIdx.x);
     __syncthreads();
@@ -64,6 +66,8 @@ gcn_nodes_kernel(const float* __restrict__ logits, int ld, const float* __restri
 __global__ void __launch_bounds__(256)
 gcn_mix_kernel(const uint32_t* __restrict__ y_hi, const uint32_t* __restrict__ y_lo, const float* __restrict__ adj,
                uint32_t* __restrict__ s_hi, uint32_t* __restrict__ s_lo, int batch) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float sA[kGJ * kGJ];
     if (threadIdx.x < kGJ * kGJ) sA[threadIdx.x] = __ldg(adj + threadIdx.x);
     __syncthreads();
@@ -96,6 +100,8 @@ gcn_mix_kernel(const uint32_t* __restrict__ y_hi, const uint32_t* __restrict__ y
 
 __global__ void __launch_bounds__(256)
 gcn_heads_kernel(const float* __restrict__ y, int y_ld, float* __restrict__ gcn_heatmap, int batch) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     const int gid = blockIdx.x * 256 + threadIdx.x;
     if (gid >= batch * kGJ * 4096) return;
     const int pos = gid & 4095, bj = gid >> 12;
@@ -124,7 +130,7 @@ extern "C" int hupr_gcn_nodes(const float* logits, int ld, const float* adj, flo
     if (!logits || !adj || !heatmap || !s_hi || !s_lo || ld < kGJ) return HUPR_ERR_BAD_ARG;
     int rc = gcn_check_sm100();
     if (rc != HUPR_OK) return rc;
-    gcn_nodes_kernel<<<(batch * 4096 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(logits, ld, adj, heatmap, (__nv_bfloat16*)s_hi,
+    launch_k(gcn_nodes_kernel, dim3((batch * 4096 + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, logits, ld, adj, heatmap, (__nv_bfloat16*)s_hi,
                                                                                    (__nv_bfloat16*)s_lo, batch);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
@@ -137,7 +143,7 @@ extern "C" int hupr_gcn_mix(const void* y_hi, const void* y_lo, const float* adj
     if (((uintptr_t)y_hi | (uintptr_t)y_lo | (uintptr_t)s_hi | (uintptr_t)s_lo) & 3) return HUPR_ERR_ALIGNMENT;
     int rc = gcn_check_sm100();
     if (rc != HUPR_OK) return rc;
-    gcn_mix_kernel<<<(batch * (kGNodes / 2) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    launch_k(gcn_mix_kernel, dim3((batch * (kGNodes / 2) + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         (const uint32_t*)y_hi, (const uint32_t*)y_lo, adj, (uint32_t*)s_hi, (uint32_t*)s_lo, batch);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
@@ -149,7 +155,7 @@ extern "C" int hupr_gcn_heads(const float* y, int y_ld, float* gcn_heatmap, int 
     if (!y || !gcn_heatmap || y_ld < kGNodes) return HUPR_ERR_BAD_ARG;
     int rc = gcn_check_sm100();
     if (rc != HUPR_OK) return rc;
-    gcn_heads_kernel<<<(batch * kGJ * 4096 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, y_ld, gcn_heatmap, batch);
+    launch_k(gcn_heads_kernel, dim3((batch * kGJ * 4096 + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, y, y_ld, gcn_heatmap, batch);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

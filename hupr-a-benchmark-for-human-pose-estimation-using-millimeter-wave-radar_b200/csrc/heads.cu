@@ -149,6 +149,8 @@ gcn_post_kernel(const float* __restrict__ y, int ncol, float* __restrict__ gcn_h
 // ---- argmax over each 64x64 map (first maximum wins, like numpy.argmax) --------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_kernel(const float* __restrict__ maps, float* __restrict__ preds, float* __restrict__ maxvals) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ float sv[8];
     __shared__ int si[8];
     const float* m = maps + (size_t)blockIdx.x * 4096;
@@ -309,7 +311,7 @@ extern "C" int hupr_keypoints_argmax(const float* maps, int n_maps, float* preds
     if (!maps || !preds) return HUPR_ERR_BAD_ARG;
     int rc = heads_check_sm100();
     if (rc != HUPR_OK) return rc;
-    argmax_kernel<<<n_maps, 256, 0, (cudaStream_t)stream>>>(maps, preds, maxvals);
+    launch_k(argmax_kernel, dim3(n_maps), dim3(256), (size_t)(0), (cudaStream_t)stream, maps, preds, maxvals);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

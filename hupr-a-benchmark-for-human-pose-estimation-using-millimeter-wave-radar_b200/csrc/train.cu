@@ -57,16 +57,15 @@ channel_sums_kernel(TView a, TView b, TView m, const float* __restrict__ mean, c
         for (int i = 0; i < 8; ++i) { mu[i] = __ldg(mean + cg * 8 + i); rs[i] = __ldg(rstd + cg * 8 + i); }
     }
     if (lane < lanes) {
-        for (long long pos = (long long)blockIdx.x * lanes + lane; pos < positions; pos += (long long)gridDim.x * lanes) {
-            float x[8], y[8], k[8];
-            tv_load8(a, (size_t)pos, cg * 8, x);
+        // two positions per iteration: all loads of both are issued before the (double-precision) accumulation chain consumes them
+        const long long stride = (long long)gridDim.x * lanes;
+        long long pos = (long long)blockIdx.x * lanes + lane;
+        auto accumulate = [&](float (&x)[8], float (&y)[8], float (&k)[8]) {
             if (MODE == SUMS_STATS) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { acc1[i] += x[i]; acc2[i] += (double)x[i] * x[i]; }
             } else if (MODE == SUMS_BN_BWD) {       // a = g, b = z, m = activation output (mask), may be absent
-                tv_load8(b, (size_t)pos, cg * 8, y);
                 if (m.hi) {
-                    tv_load8(m, (size_t)pos, cg * 8, k);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) x[i] = k[i] > 0.f ? x[i] : 0.f;
                 }
@@ -74,13 +73,29 @@ channel_sums_kernel(TView a, TView b, TView m, const float* __restrict__ mean, c
                 for (int i = 0; i < 8; ++i) { acc1[i] += x[i]; acc2[i] += (double)x[i] * ((y[i] - mu[i]) * rs[i]); }
             } else {                                 // PRELU: a = g, b = pre-activation s (may be absent -> only sum g)
                 if (b.hi) {
-                    tv_load8(b, (size_t)pos, cg * 8, y);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc1[i] += y[i] > 0.f ? 0.0 : (double)x[i] * y[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc2[i] += x[i];
             }
+        };
+        auto load = [&](long long q, float (&x)[8], float (&y)[8], float (&k)[8]) {
+            tv_load8(a, (size_t)q, cg * 8, x);
+            if (MODE != SUMS_STATS && b.hi) tv_load8(b, (size_t)q, cg * 8, y);
+            if (MODE == SUMS_BN_BWD && m.hi) tv_load8(m, (size_t)q, cg * 8, k);
+        };
+        for (; pos + stride < positions; pos += 2 * stride) {
+            float x0[8], y0[8], k0[8], x1[8], y1[8], k1[8];
+            load(pos, x0, y0, k0);
+            load(pos + stride, x1, y1, k1);
+            accumulate(x0, y0, k0);
+            accumulate(x1, y1, k1);
+        }
+        if (pos < positions) {
+            float x0[8], y0[8], k0[8];
+            load(pos, x0, y0, k0);
+            accumulate(x0, y0, k0);
         }
     }
     double* r1 = sred;
@@ -390,7 +405,7 @@ extern "C" int hupr_channel_sums(int mode, const hupr_tensor_view* a, const hupr
     const int lanes = 256 / groups;
     const size_t smem = (size_t)2 * lanes * c * sizeof(double);
     long long blocks = (positions + lanes - 1) / lanes;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 6) blocks = 148 * 6;
     cudaStream_t s = (cudaStream_t)stream;
     const TView va = mk_view(a), vb = mk_view(b && b->hi ? b : nullptr), vm = mk_view(mask && mask->hi ? mask : nullptr);
     if (mode == SUMS_STATS) channel_sums_kernel<SUMS_STATS><<<(unsigned)blocks, 256, smem, s>>>(va, vb, vm, mean, rstd, positions, c, s1, s2);

@@ -21,6 +21,8 @@ struct TileTransposeParams {
 __global__ void __launch_bounds__(256)
 tile_transpose_kernel(const uint16_t* __restrict__ src_hi, const uint16_t* __restrict__ src_lo, uint16_t* __restrict__ dst_hi,
                       uint16_t* __restrict__ dst_lo, const TileTransposeParams p) {
+    pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
+    pdl_launch_dependents();     // the successor may start its prologue now; it waits the same way before touching memory
     __shared__ __align__(16) uint16_t tile[2][64][66];             // [plane][channel][position], pitch 66 keeps 4-byte reads conflict free
     const long long pos0 = (long long)blockIdx.x * 64;
     const int c0 = blockIdx.y * 64;
@@ -88,7 +90,7 @@ int fast_transpose_dense(const void* in_hi, const void* in_lo, int n, int s, int
     TileTransposeParams p = {};
     p.ld = in_ld; p.ch_off = in_ch_off; p.dense = 1; p.s = s; p.c_total = c; p.n_copies = 1; p.shift0 = 0; p.copy_stride = 0; p.ppad = 0;
     const dim3 grid((unsigned)((long long)n * s / 64), c / 64);
-    tile_transpose_kernel<<<grid, 256, 0, stream>>>((const uint16_t*)in_hi, (const uint16_t*)in_lo, (uint16_t*)out_hi, (uint16_t*)out_lo, p);
+    launch_k(tile_transpose_kernel, dim3(grid), dim3(256), (size_t)(0), stream, (const uint16_t*)in_hi, (const uint16_t*)in_lo, (uint16_t*)out_hi, (uint16_t*)out_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
@@ -103,7 +105,7 @@ int fast_to_kmajor(const void* src_hi, const void* src_lo, int n, int d, int h, 
     p.d = d; p.h = h; p.w = w; p.dp = dp; p.hp = hp; p.wp = wp; p.pd = pd; p.ph = ph; p.pw = pw;
     p.n_copies = n_copies; p.shift0 = shift0; p.copy_stride = copy_stride; p.ppad = ppad;
     const dim3 grid((unsigned)((long long)n * d * h * w / 64), c / 64);
-    tile_transpose_kernel<<<grid, 256, 0, stream>>>((const uint16_t*)src_hi, (const uint16_t*)src_lo, (uint16_t*)dst_hi, (uint16_t*)dst_lo, p);
+    launch_k(tile_transpose_kernel, dim3(grid), dim3(256), (size_t)(0), stream, (const uint16_t*)src_hi, (const uint16_t*)src_lo, (uint16_t*)dst_hi, (uint16_t*)dst_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }

@@ -253,6 +253,8 @@ class HuPRNet(nn.Module):
     def _forward_train(self, hori, vert):
         """networks.py:35-41 under ``model.train()`` (tools/run.py:66,76): batch-statistics BatchNorm, outputs connected to autograd."""
         from ..training import TrainStep
+        if next(self.parameters()).device.type != "cuda" or not hori.is_cuda:
+            raise RuntimeError("hupr_b200.HuPRNet runs on a B200 only: move the module and its inputs to a CUDA device (no CPU fallback)")
         if not self.split:
             raise RuntimeError("train-mode forward needs the hi/lo (split=True) model")
         step = self._train_step

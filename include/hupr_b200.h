@@ -33,6 +33,12 @@ int hupr_version(void);
 /* Number of kernels this library has launched in the calling process (all entry points, all streams). */
 long long hupr_launch_count(void);
 
+/* Programmatic dependent launch for the latency-bound inference chain (convolutions, attention, bridge / GCN / argmax kernels): when on
+ * (default; environment HUPR_PDL=0 turns it off) those kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+ * wait with griddepcontrol.wait before their first global access, so a kernel's launch and prologue overlap its predecessor's tail (also
+ * as programmatic edges inside captured CUDA graphs).  Returns the previous setting. */
+int hupr_set_pdl(int on);
+
 /* Human-readable text for an error code (static storage). */
 const char* hupr_error_string(int code);
 

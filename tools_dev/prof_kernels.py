@@ -36,6 +36,31 @@ if which in ("wgrad", "all"):
         dy = SplitTensor.from_float(torch.randn(b, d, h, w, cout, device="cuda"))
         out = torch.zeros((27, cin, cout), device="cuda")
         ops.conv_wgrad_direct(x, 0, cin, dy, 0, cout, (3, 3, 3), (1, 1, 1), out=out)
+if which in ("conv128_1", "conv64_1"):
+    # single-product (bf16 training mode) 3x3x3 convolutions through the halo kernel
+    cout = 128 if which == "conv128_1" else 64
+    x = SplitTensor.from_float(torch.randn(b, 8, 64, 64, 64, device="cuda"))
+    w = SplitTensor.from_float(torch.randn(27, cout, 64, device="cuda") * 0.02)
+    out = SplitTensor.empty((b, 8, 64, 64, cout), "cuda")
+    with ops.products(1):
+        for _ in range(3):
+            ops.conv_gemm(x, 64, w, cout, kernel=(3, 3, 3), pad=(1, 1, 1), out=out)
+if which in ("wgrad_1",):
+    with ops.products(1):
+        for cin, cout, d, h, w in ((64, 64, 8, 64, 64), (64, 128, 8, 64, 64), (128, 256, 4, 32, 32)):
+            x = SplitTensor.from_float(torch.randn(b, d, h, w, cin, device="cuda"))
+            dy = SplitTensor.from_float(torch.randn(b, d, h, w, cout, device="cuda"))
+            out = torch.zeros((27, cin, cout), device="cuda")
+            ops.conv_wgrad_direct(x, 0, cin, dy, 0, cout, (3, 3, 3), (1, 1, 1), out=out)
+if which in ("attnbwd_fused",):
+    s_, c = 4096, 64
+    mk = lambda: SplitTensor.from_float(torch.randn(b, 1, 1, s_, 4 * c, device="cuda") * 0.3)
+    pq, v, do = mk(), mk(), mk()
+    lse = torch.full((b, s_), 9.0, device="cuda")
+    rowdot = torch.zeros((b, s_), device="cuda")
+    dq = torch.zeros((b, s_, 4 * c), device="cuda")
+    for _ in range(2):
+        ops.attention_bwd(pq, c, pq, 0, v, 0, do, 0, lse, rowdot, dq, c, dq, 0, dq, 2 * c)
 if which in ("attnbwd",):
     # the [S, S]-output GEMMs of the attention backward at level 1: P = exp(Q K^T - lse) and dS = P * (dO V^T - rowdot)
     s_, c = 4096, 64
