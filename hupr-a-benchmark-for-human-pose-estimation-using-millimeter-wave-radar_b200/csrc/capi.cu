@@ -13,8 +13,10 @@ static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
     int v = g_pdl.load(std::memory_order_relaxed);
     if (v < 0) {
+        // default off: measured on B200 (profiles/r02_bench_*pdl*.json) it gains 0.7 % on the batch-1 forward (1.539 -> 1.528 ms) and costs
+        // 0.6 % on the batch-32 stream (12.27 -> 12.35 ms); the Python side turns it on for small-batch forwards (ops.pdl)
         const char* e = getenv("HUPR_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;
         g_pdl.store(v, std::memory_order_relaxed);
     }
     return v != 0;
@@ -63,7 +65,7 @@ extern "C" int hupr_version(void) { return 200; }
 namespace hupr { void set_pdl(int on); }
 extern "C" int hupr_set_pdl(int on) {
     const int prev = hupr::pdl_enabled() ? 1 : 0;
-    hupr::set_pdl(on);
+    if (on >= 0) hupr::set_pdl(on);      // negative: query only
     return prev;
 }
 

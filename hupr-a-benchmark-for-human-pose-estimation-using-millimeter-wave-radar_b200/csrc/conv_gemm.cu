@@ -128,12 +128,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 int kb_begin, kb_end, n0, n, od, h0, w0;
                 decode(item, kb_begin, kb_end, n0, n, od, h0, w0);
+                // k-block -> (tap, channel block) -> (kd, kh, kw): decoded once per item, then walked with carries (the divisions cost more
+                // than a single-product stage's worth of tensor cycles)
+                int tap = kb_begin / p.cin_blocks, cb = kb_begin - tap * p.cin_blocks;
+                int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % Cfg::kStages;
                     const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-                    const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
                     uint8_t* st = smem + s * Cfg::kStageBytes;
                     mbar_expect_tx(&full[s], Cfg::kStageBytes);
                     const int ac = p.a_ch_off + cb * BK, aw = w0 + tkw - p.pw, ah = h0 + tkh - p.ph, ad = od + tkd - p.pd;
@@ -143,6 +145,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (NPROD == 3) {
                         tma_load_5d(st + Cfg::kABytes, &tmA_lo, &full[s], ac, aw, ah, ad, n);
                         tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB_lo, &full[s], cb * BK + p.w_k_off, n0, b2);
+                    }
+                    if (++cb == p.cin_blocks) {
+                        cb = 0;
+                        ++tap;
+                        if (++tkw == p.kw) {
+                            tkw = 0;
+                            if (++tkh == p.kh) { tkh = 0; ++tkd; }
+                        }
                     }
                 }
             }

@@ -11,7 +11,12 @@
 //   * k-blocks are 32 channels (64-byte rows, SWIZZLE_64B) so that a stage (halo box + 3 weight tiles, hi and lo planes)
 //     stays under 96 KiB and two to three stages fit;
 //   * the kernel is persistent (one CTA per SM walks the tiles) with two accumulator sets in TMEM, so the epilogue of one tile
-//     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next.
+//     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next;
+//   * cout = 64 tiles (BN = 64, three products) are bound by the tensor core's shared-memory operand reads: an M = 128, N = 64, K = 16
+//     MMA reads 4 KB of A and 2 KB of B per 32 cycles = 192 B/cycle against a 128 B/cycle port (ncu: 34 % tensor-active).  There the
+//     weight tiles of a tap are stored as one 128-row B operand [w_hi | w_lo], so a_hi meets both in ONE N = 128 MMA (columns 0..63 =
+//     hi*hi, 64..127 = hi*lo) and a_lo * w_hi is a second, N = 64 MMA into columns 0..63: the A planes are read twice instead of three
+//     times per k-step (14 KB instead of 18 KB per 96 tensor cycles); the epilogue adds the two column halves.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
 #include <stdlib.h>
 
@@ -66,6 +71,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
     constexpr bool three = NPROD == 3;      // compile-time: the single-thread MMA issue loop carries no runtime branches
+    constexpr bool ncat = (BN == 64 && NPROD == 3);         // [w_hi | w_lo] as one N = 128 operand (header comment)
+    constexpr int ACC = ncat ? 128 : BN;                    // TMEM columns of one accumulator
+    constexpr int TMEM_COLS = 4 * ACC;                      // two sets x two accumulators
     const int total_tiles = g.m_tiles * g.n_tiles;
 
     if (threadIdx.x == 0) {
@@ -81,7 +89,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(4 * BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -103,16 +111,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int it = 0;
+            int it = 0, sidx = 0;
+            uint32_t sph = 0;                              // stage ring position / phase, advanced without divisions
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int n0, n, od, h0;
                 decode(tile, n0, n, od, h0);
+                int cb = 0, tkw = 0, tkd = 0;                 // gi = (tkd * kw + tkw) * cin_blocks + cb, walked with carries (no divisions per stage)
                 for (int gi = 0; gi < groups; ++gi, ++it) {
-                    const int s = it % g.stages;
-                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    const int cb = gi % p.cin_blocks;
-                    const int tkw = (gi / p.cin_blocks) % p.kw, tkd = gi / (p.cin_blocks * p.kw);
+                    const int s = sidx;
+                    mbar_wait(&empty[s], sph ^ 1u);
                     uint8_t* st = smem + s * g.stage_bytes;
                     mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
                     const int ac = p.a_ch_off + cb * HK;
@@ -122,9 +129,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                     for (int tkh = 0; tkh < 3; ++tkh) {
                         const int tap = (tkd * 3 + tkh) * p.kw + tkw;
-                        tma_load_3d(sb + tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
-                        if (three) tma_load_3d(sb + (3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                        // B tiles of a stage: [hi0 hi1 hi2 lo0 lo1 lo2], or [hi0 lo0 hi1 lo1 hi2 lo2] when hi|lo form one N = 128 operand
+                        tma_load_3d(sb + (ncat ? 2 * tkh : tkh) * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
+                        if (three) tma_load_3d(sb + (ncat ? 2 * tkh + 1 : 3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
                     }
+                    if (++cb == p.cin_blocks) {
+                        cb = 0;
+                        if (++tkw == p.kw) { tkw = 0; ++tkd; }
+                    }
+                    if (++sidx == g.stages) { sidx = 0; sph ^= 1u; }
                 }
             }
         }
@@ -132,34 +145,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int it = 0, lt = 0;
+            const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 128
+            int it = 0, lt = 0, sidx = 0;
+            uint32_t sph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
                 const int as = lt & 1;
                 mbar_wait(&accum_empty[as], (uint32_t)(((lt >> 1) & 1) ^ 1));     // the epilogue drained this accumulator set
                 tc_fence_after();
-                const uint32_t tset = tmem_base + (uint32_t)(as * 2 * BN);
+                const uint32_t tset = tmem_base + (uint32_t)(as * 2 * ACC);
                 for (int gi = 0; gi < groups; ++gi, ++it) {
-                    const int s = it % g.stages;
-                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-                    mbar_wait(&full[s], ph);
+                    const int s = sidx;
+                    mbar_wait(&full[s], sph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * g.stage_bytes);
                     const uint32_t sb = st + (three ? 2 : 1) * g.a_plane_bytes;
 #pragma unroll
                     for (int tkh = 0; tkh < 3; ++tkh) {
-                        const uint64_t db_hi = make_smem_desc_sw64(sb + tkh * g.b_tile_bytes);
-                        const uint64_t db_lo = make_smem_desc_sw64(sb + (3 + tkh) * g.b_tile_bytes);
+                        const uint64_t db_hi = make_smem_desc_sw64(sb + (ncat ? 2 * tkh : tkh) * g.b_tile_bytes);
+                        const uint64_t db_lo = make_smem_desc_sw64(sb + (ncat ? 2 * tkh + 1 : 3 + tkh) * g.b_tile_bytes);
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
                             const uint64_t da_hi = make_smem_desc_sw64(st + aoff);
                             const uint64_t da_lo = make_smem_desc_sw64(st + g.a_plane_bytes + aoff);
-                            const uint32_t tacc = tset + (uint32_t)(a * BN);
+                            const uint32_t tacc = tset + (uint32_t)(a * ACC);
 #pragma unroll
                             for (int k = 0; k < HK / 16; ++k) {
                                 const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
                                 const uint32_t acc_flag = (gi | tkh | k) != 0;
-                                if (three) {
+                                if (ncat) {
+                                    umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc_cat, acc_flag);      // a_hi x [w_hi | w_lo] -> columns 0..127
+                                    umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, 1u);                // a_lo x w_hi -> columns 0..63
+                                } else if (three) {
                                     umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
                                     umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
                                     umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
@@ -170,6 +187,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         }
                     }
                     tc_commit(&empty[s]);
+                    if (++sidx == g.stages) { sidx = 0; sph ^= 1u; }
                 }
                 tc_commit(&accum_full[as]);
             }
@@ -185,7 +203,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int as = lt & 1;
             mbar_wait(&accum_full[as], (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
-            const uint32_t tset = tmem_base + (uint32_t)(as * 2 * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t tset = tmem_base + (uint32_t)(as * 2 * ACC) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int a = 0; a < 2; ++a) {
                 const int ow = row % p.bw, oh = h0 + a * (p.bh / 2) + row / p.bw;
@@ -193,7 +211,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t acc[32];
-                    tmem_ld32(tset + (uint32_t)(a * BN + c * 32), acc);
+                    if (ncat) {                            // hi*hi + lo*hi (columns c) + hi*lo (columns 64 + c)
+                        uint32_t cross[32];
+                        tmem_ld32_nowait(tset + (uint32_t)(a * ACC + c * 32), acc);
+                        tmem_ld32_nowait(tset + (uint32_t)(a * ACC + 64 + c * 32), cross);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(cross[j]));
+                    } else {
+                        tmem_ld32(tset + (uint32_t)(a * BN + c * 32), acc);
+                    }
                     if (a == 1 && c == BN / 32 - 1) {      // last TMEM read of this set: hand it back before the stores
                         tc_fence_before();
                         mbar_arrive(&accum_empty[as]);
@@ -206,7 +233,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 

@@ -32,15 +32,17 @@ constexpr int WG_KB = 64;                 // positions per K block
 constexpr int WG_ATOM = WG_KB * 128;      // bytes of one atom plane: 64 positions x 64 bf16 channels
 constexpr int WG_THREADS = 192;
 
-template <int BN>
+template <int BN, int NPROD>
 struct WgCfg {
+    static constexpr int kPlanes = NPROD == 3 ? 2 : 1;           // single-product mode stages the hi planes only: twice the stages in flight
     static constexpr int kYAtoms = BN / 64;
-    static constexpr int kYBytes = 2 * kYAtoms * WG_ATOM;        // hi atoms | lo atoms
-    static constexpr int kABytes = 4 * WG_ATOM;                  // hi atom 0, hi atom 1, lo atom 0, lo atom 1
+    static constexpr int kYBytes = kPlanes * kYAtoms * WG_ATOM;  // hi atoms | lo atoms
+    static constexpr int kABytes = kPlanes * 2 * WG_ATOM;        // hi atom 0, hi atom 1 | lo atom 0, lo atom 1
     static constexpr int kSlots = 512 / BN;                      // accumulator slots of [128 lanes x BN columns]
-    static constexpr int kStages = (224 * 1024 - 2 * kYBytes) / kABytes;
-    static constexpr int kSmemBytes = 2 * kYBytes + kStages * kABytes + 1024 /*align*/ + 256 /*barriers*/;
-    static_assert(kStages >= 2 && kStages <= 8, "wgrad smem plan");
+    static constexpr int kStagesFit = (224 * 1024 - 2 * kYBytes) / kABytes;
+    static constexpr int kStages = kStagesFit > 12 ? 12 : kStagesFit;
+    static constexpr int kSmemBytes = 2 * kYBytes + kStages * kABytes + 1024 /*align*/ + 256 /*barriers*/ + 256 /*atom table*/;
+    static_assert(kStages >= 2 && 2 * kStages + 6 <= 32, "wgrad smem plan (32 barrier slots)");
 };
 
 struct WgParams {
@@ -71,16 +73,17 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+template <int BN, int NPROD>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
              const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo, const WgParams p) {
-    using Cfg = WgCfg<BN>;
+    using Cfg = WgCfg<BN, NPROD>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sm_y = smem;                                   // 2 buffers of kYBytes
     uint8_t* sm_a = smem + 2 * Cfg::kYBytes;                // kStages stages of kABytes
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_a + Cfg::kStages * Cfg::kABytes);
+    int4* atom_tab = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2 * kSlots] (channel, dw, dh, dd) of the CTA's atoms
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + Cfg::kStages;
     uint64_t* y_full = bars + 2 * Cfg::kStages;             // [2]
@@ -89,7 +92,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool three = p.nprod == 3;
+    constexpr bool three = NPROD == 3;
 
     // work item: (sample [batched mode], split-K slice, column tile of cout, group of accumulator slots)
     int item = blockIdx.x;
@@ -121,16 +124,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            // The CTA's atoms (filter tap, 64-channel block) do not depend on the K block: decode them once (the integer divisions of
+            // the decode were ~250 cycles per stage against 128..384 tensor cycles of work per stage) ...
+            for (int j = 0; j < 2 * nslots; ++j) {
+                int atom = slot0 * 2 + j;
+                if (atom >= p.atoms) atom = p.atoms - 1;      // odd atom count: lanes 64..127 of the last slot repeat a real atom (ignored)
+                const int tap = atom / p.cin_blocks, cb = atom - tap * p.cin_blocks;
+                const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+                atom_tab[j] = make_int4(p.x_ch_off + cb * 64, tkw - p.pw, tkh - p.ph, tkd - p.pd);
+            }
+            // ... and walk the K blocks (w tile fastest, then h tile, depth, sample) with carry counters instead of divisions
+            int tw, th, od, nn;
+            {
+                int t = kb_begin;
+                tw = t % p.tiles_w; t /= p.tiles_w;
+                th = t % p.tiles_h; t /= p.tiles_h;
+                od = t % p.d_out;
+                nn = t / p.d_out;
+            }
             int it = 0;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
-                int t = kb;
-                const int w0 = (t % p.tiles_w) * p.bw; t /= p.tiles_w;
-                const int h0 = (t % p.tiles_h) * p.bh; t /= p.tiles_h;
-                const int od = t % p.d_out;
-                const int n = sample + t / p.d_out;
+                const int w0 = tw * p.bw, h0 = th * p.bh, n = sample + nn;
                 const int i = kb - kb_begin, yb = i & 1;
                 mbar_wait(&y_empty[yb], (uint32_t)(((i >> 1) & 1) ^ 1));
-                mbar_expect_tx(&y_full[yb], three ? Cfg::kYBytes : Cfg::kYBytes / 2);
+                mbar_expect_tx(&y_full[yb], Cfg::kYBytes);
                 uint8_t* ys = sm_y + yb * Cfg::kYBytes;
 #pragma unroll
                 for (int j = 0; j < Cfg::kYAtoms; ++j) {
@@ -140,17 +157,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
                 for (int sl = 0; sl < nslots; ++sl, ++it) {
                     const int s = it % Cfg::kStages;
                     mbar_wait(&a_empty[s], (uint32_t)(((it / Cfg::kStages) & 1) ^ 1));
-                    mbar_expect_tx(&a_full[s], three ? Cfg::kABytes : Cfg::kABytes / 2);
+                    mbar_expect_tx(&a_full[s], Cfg::kABytes);
                     uint8_t* as = sm_a + s * Cfg::kABytes;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        int atom = (slot0 + sl) * 2 + half;
-                        if (atom >= p.atoms) atom = p.atoms - 1;      // odd atom count: lanes 64..127 of the last slot repeat a real atom (ignored)
-                        const int tap = atom / p.cin_blocks, cb = atom - tap * p.cin_blocks;
-                        const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
-                        const int xc = p.x_ch_off + cb * 64, xw = w0 + tkw - p.pw, xh = h0 + tkh - p.ph, xd = od + tkd - p.pd;
-                        tma_load_5d(as + half * WG_ATOM, &tmX_hi, &a_full[s], xc, xw, xh, xd, n);
-                        if (three) tma_load_5d(as + (2 + half) * WG_ATOM, &tmX_lo, &a_full[s], xc, xw, xh, xd, n);
+                        const int4 at = atom_tab[2 * sl + half];
+                        tma_load_5d(as + half * WG_ATOM, &tmX_hi, &a_full[s], at.x, w0 + at.y, h0 + at.z, od + at.w, n);
+                        if (three) tma_load_5d(as + (2 + half) * WG_ATOM, &tmX_lo, &a_full[s], at.x, w0 + at.y, h0 + at.z, od + at.w, n);
+                    }
+                }
+                if (++tw == p.tiles_w) {
+                    tw = 0;
+                    if (++th == p.tiles_h) {
+                        th = 0;
+                        if (++od == p.d_out) { od = 0; ++nn; }
                     }
                 }
             }
@@ -238,12 +258,12 @@ static int encode_pos_map(CUtensorMap* map, const void* base, int c, int w, int 
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-template <int BN>
+template <int BN, int NPROD>
 static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi, const CUtensorMap& y_lo, WgParams p,
                         int cout, int problems, int num_sms, cudaStream_t stream) {
-    using Cfg = WgCfg<BN>;
+    using Cfg = WgCfg<BN, NPROD>;
     static bool configured[kMaxDevices] = {};
-    if (int crc = ensure_smem_optin(wgrad_kernel<BN>, Cfg::kSmemBytes, configured)) return crc;
+    if (int crc = ensure_smem_optin(wgrad_kernel<BN, NPROD>, Cfg::kSmemBytes, configured)) return crc;
     p.groups = (p.slots + Cfg::kSlots - 1) / Cfg::kSlots;
     p.n_tiles = cout / BN;
     const long long tiles = (long long)p.groups * p.n_tiles * problems;
@@ -254,7 +274,7 @@ static int launch_wgrad(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const 
     p.k_split = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
     const long long items = tiles * p.k_split;
     if (items > 2147483647LL) return HUPR_ERR_BAD_ARG;
-    wgrad_kernel<BN><<<(unsigned)items, WG_THREADS, Cfg::kSmemBytes, stream>>>(x_hi, x_lo, y_hi, y_lo, p);
+    wgrad_kernel<BN, NPROD><<<(unsigned)items, WG_THREADS, Cfg::kSmemBytes, stream>>>(x_hi, x_lo, y_hi, y_lo, p);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
@@ -308,7 +328,12 @@ extern "C" int hupr_conv_wgrad(const hupr_wgrad_desc* d, void* stream) {
     if ((rc = encode_pos_map(&y_hi, d->dy_hi, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
     if ((rc = encode_pos_map(&y_lo, three ? d->dy_lo : d->dy_hi, d->cy, d->w, d->h, d_out, d->n, bw, bh)) != HUPR_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (d->cout % 256 == 0) return launch_wgrad<256>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
-    if (d->cout % 128 == 0) return launch_wgrad<128>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
-    return launch_wgrad<64>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    if (three) {
+        if (d->cout % 256 == 0) return launch_wgrad<256, 3>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+        if (d->cout % 128 == 0) return launch_wgrad<128, 3>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+        return launch_wgrad<64, 3>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    }
+    if (d->cout % 256 == 0) return launch_wgrad<256, 1>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    if (d->cout % 128 == 0) return launch_wgrad<128, 1>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
+    return launch_wgrad<64, 1>(x_hi, x_lo, y_hi, y_lo, p, d->cout, problems, num_sms, s);
 }

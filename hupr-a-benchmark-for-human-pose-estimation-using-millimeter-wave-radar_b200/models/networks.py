@@ -229,7 +229,7 @@ class HuPRNet(nn.Module):
         plan's output buffers — valid until the next forward)."""
         batch = chirp_ra.hi.shape[0]
         pk, plan = self._plan(batch)
-        with ops.coop_scope(plan["coop"]):
+        with ops.coop_scope(plan["coop"]), ops.pdl(batch <= 4 or ops._C.lib().hupr_set_pdl(-1) == 1):
             return self._forward_features(pk, plan, batch, chirp_ra, chirp_re)
 
     def _forward_features(self, pk, plan, batch, chirp_ra, chirp_re):

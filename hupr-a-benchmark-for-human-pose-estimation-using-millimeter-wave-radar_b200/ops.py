@@ -248,6 +248,17 @@ def attention_bwd(q, q_off, k, k_off, v, v_off, do, do_off, lse, rowdot, dq, dq_
         _C.check(_C.lib().hupr_attention_bwd(desc, _C.stream_ptr()), "hupr_attention_bwd")
 
 
+@contextlib.contextmanager
+def pdl(on=True):
+    """Launches in the block use programmatic dependent launch (hupr_set_pdl): a kernel's launch + prologue overlap its predecessor's
+    tail.  Worth it only in the latency regime (small-batch forwards); the setting is restored on exit."""
+    prev = _C.lib().hupr_set_pdl(1 if on else 0)
+    try:
+        yield
+    finally:
+        _C.lib().hupr_set_pdl(prev)
+
+
 def launch_count():
     """Kernels launched by libhupr_b200.so in this process so far (hupr_launch_count)."""
     return int(_C.lib().hupr_launch_count())

@@ -34,9 +34,9 @@ int hupr_version(void);
 long long hupr_launch_count(void);
 
 /* Programmatic dependent launch for the latency-bound inference chain (convolutions, attention, bridge / GCN / argmax kernels): when on
- * (default; environment HUPR_PDL=0 turns it off) those kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+ * (default off; environment HUPR_PDL=1 turns it on) those kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization and
  * wait with griddepcontrol.wait before their first global access, so a kernel's launch and prologue overlap its predecessor's tail (also
- * as programmatic edges inside captured CUDA graphs).  Returns the previous setting. */
+ * as programmatic edges inside captured CUDA graphs).  Returns the previous setting; a negative argument only queries. */
 int hupr_set_pdl(int on);
 
 /* Human-readable text for an error code (static storage). */
