@@ -409,10 +409,14 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     if (!TSTORE && p.coop_ws && pp.k_split == 1) {     // small grid, long contraction: cooperative split-K with an ordered in-kernel reduction
         const long long tiles = (long long)pp.m_tiles * pp.n_tiles;
         const int total_kb = p.kd * p.kh * p.kw * p.cin_blocks;
-        if (tiles * 2 <= num_sms && total_kb >= 24) {     // long contractions only: a slice must outweigh the park / re-read of its tile
+        if (tiles * 2 <= num_sms && total_kb >= 8) {
+            // up to 8 slices, as many as fill the GPU once; a slice keeps >= 4 k-blocks (>= 2 when the grid is tiny: batch-1 level-3
+            // layers and the PRGCN GEMMs stream 4-28 MB of weights through 4-16 tiles, where the serial k-loop of a tile — not the
+            // 64 KB park / re-read of its partial sums — is the latency; batch-1 launch list: profiles/r02_b1_launches.csv)
             int ks = (int)(num_sms / tiles);
-            if (ks > total_kb / 8) ks = total_kb / 8;
-            if (ks > 4) ks = 4;
+            const int min_kb = tiles <= 16 ? 2 : 4;
+            if (ks > total_kb / min_kb) ks = total_kb / min_kb;
+            if (ks > 8) ks = 8;
             const size_t per_slice = (size_t)tiles * BM * BN * sizeof(float);
             const size_t avail = p.coop_ws_bytes > 4096 ? p.coop_ws_bytes - 4096 : 0;
             if ((size_t)ks * per_slice > avail) ks = (int)(avail / per_slice);

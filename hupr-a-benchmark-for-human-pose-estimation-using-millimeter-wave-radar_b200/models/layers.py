@@ -49,12 +49,12 @@ def bn_affine(sd, prefix):
 
 class Block(object):
     """Packed residual block: conv1 || downsample, then conv2 (+ residual, activation)."""
-    __slots__ = ("w1", "scale1", "shift1", "slope1", "w2", "scale2", "shift2", "slope2", "cin", "cmid", "taps", "pad")
+    __slots__ = ("w1", "scale1", "shift1", "slope1", "w2", "scale2", "shift2", "slope2", "cin", "cmid", "taps", "pad", "lc")      # lc: un-padded width
 
 
 def pack_block3d(sd, prefix, cin, cout, split):
     b = Block()
-    b.cin, b.cmid, b.taps, b.pad = pad64(cin), cout, (3, 3, 3), (1, 1, 1)
+    b.cin, b.cmid, b.taps, b.pad, b.lc = pad64(cin), cout, (3, 3, 3), (1, 1, 1), cout
     b.w1 = pack_conv([sd[prefix + ".main.0.weight"], sd[prefix + ".downsample.0.weight"]], b.cin, [cout, cout], split)
     s1, h1 = bn_affine(sd, prefix + ".main.1")
     sd_, hd = bn_affine(sd, prefix + ".downsample.1")
@@ -69,7 +69,7 @@ def pack_block3d(sd, prefix, cin, cout, split):
 def pack_block2d(sd, prefix, cin, cout, split):
     b = Block()
     cp = pad64(cout)
-    b.cin, b.cmid, b.taps, b.pad = cin, cp, (1, 3, 3), (0, 1, 1)
+    b.cin, b.cmid, b.taps, b.pad, b.lc = cin, cp, (1, 3, 3), (0, 1, 1), cout
     w_main = sd[prefix + ".main.0.weight"].unsqueeze(2)
     w_ds = sd[prefix + ".downsample.0.weight"].unsqueeze(2)
     b.w1 = pack_conv([w_main, w_ds], cin, [cp, cp], split)
@@ -85,9 +85,9 @@ def run_block(x, blk, tmp, out, o_ch_off=0):
     """x -> out[..., o_ch_off : o_ch_off + cmid];  tmp is a ``[..., 2*cmid]`` scratch tensor."""
     c = blk.cmid
     ops.conv_gemm(x, blk.cin, blk.w1, 2 * c, kernel=blk.taps, pad=blk.pad, scale=blk.scale1, shift=blk.shift1,
-                  slope=blk.slope1, out=tmp)
+                  slope=blk.slope1, out=tmp, lcout=2 * blk.lc)
     ops.conv_gemm(tmp, c, blk.w2, c, kernel=blk.taps, pad=blk.pad, scale=blk.scale2, shift=blk.shift2, slope=blk.slope2,
-                  residual=tmp, r_ch_off=c, out=out, o_ch_off=o_ch_off)
+                  residual=tmp, r_ch_off=c, out=out, o_ch_off=o_ch_off, lcin=blk.lc, lcout=blk.lc)
     return out
 
 
@@ -151,7 +151,7 @@ PROJ_VERT = ("phi_cross_vert", "theta_cross_vert", "phi_self_vert", "theta_self_
 class DecoderWeights(object):
     def __init__(self, sd, nf, keypoints, split):
         p = "radarDecoder."
-        self.nf = nf
+        self.nf, self.keypoints = nf, keypoints
         self.proj_hori, self.proj_vert = [], []
         for level, c in enumerate((8 * nf, 4 * nf, 2 * nf)):
             for names, dst in ((PROJ_HORI, self.proj_hori), (PROJ_VERT, self.proj_vert)):
@@ -182,8 +182,10 @@ class DecoderBuffers(object):
                                     vt_ra=mk(b, c, s), vt_re=mk(b, c, s),
                                     cat=mk(b, 1, hw, hw, prev + 4 * c)))
         smax = 64 * 64 if not split else 16 * 16      # levels 1 and 2 run fused when split; scratch covers the unfused level(s)
-        self.logits = torch.empty(b * smax * smax, dtype=torch.float32, device=dev)
-        self.probs = mk(b * smax * smax)
+        self._scratch_elems, self._split, self._dev = b * smax * smax, split, dev
+        self._scratch = {}                             # index -> (fp32 logits, split probabilities) of one unfused attention
+        self._att_streams = None
+        self.attention_scratch(0)
         self.t3a, self.o3a = mk(b, 1, 16, 16, 16 * nf), mk(b, 1, 16, 16, 8 * nf)
         self.t3b, self.o3b = mk(b, 1, 16, 16, 8 * nf), mk(b, 1, 16, 16, 4 * nf)
         self.t2a, self.o2a = mk(b, 1, 32, 32, 8 * nf), mk(b, 1, 32, 32, 4 * nf)
@@ -200,6 +202,21 @@ class DecoderBuffers(object):
         self.heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
         self.gcn_heatmap = torch.empty((b, keypoints, 64, 64), dtype=torch.float32, device=dev)
 
+    def attention_scratch(self, index):
+        """(fp32 logits, split probabilities) scratch of unfused attention number ``index`` of a level."""
+        pair = self._scratch.get(index)
+        if pair is None:
+            pair = (torch.empty(self._scratch_elems, dtype=torch.float32, device=self._dev),
+                    SplitTensor.empty((self._scratch_elems,), self._dev, self._split))
+            self._scratch[index] = pair
+        return pair
+
+    def attention_streams(self, device):
+        """Three side streams on which attentions 1..3 of a level run next to attention 0 (small batches)."""
+        if self._att_streams is None:
+            self._att_streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        return self._att_streams
+
 
 def _view(t, shape):
     n = 1
@@ -208,25 +225,29 @@ def _view(t, shape):
     return SplitTensor(t.hi[:n].view(shape), None if t.lo is None else t.lo[:n].view(shape))
 
 
-def run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, out, o_off, residual):
+def run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, out, o_off, residual, scratch=0):
     """layers.py:126-133 with Q = q_src[..., q_off:+C], K = k_src[..., k_off:+C], V = v:
-    logits[n, m] = <Q[n], K[m]>;  P = softmax over keys m;  out[n] = sum_m P[n, m] V[m]  (+ V[n] for the cross branches)."""
+    logits[n, m] = <Q[n], K[m]>;  P = softmax over keys m;  out[n] = sum_m P[n, m] V[m]  (+ V[n] for the cross branches).
+    ``scratch``: which logits / probabilities scratch pair the unfused path uses (attentions running concurrently need their own)."""
     b = v.hi.shape[0]
     c, s = lv["c"], lv["s"]
     if c in (64, 128) and v.lo is not None:      # fused flash-style kernel (levels 1 and 2: 99.7 % of the attention FLOPs)
         ops.attention_fwd(q_src, q_off, k_src, k_off, vt, c, out, o_off, residual=v if residual else None)
         return
-    logits = bf.logits[:b * s * s].view(b, 1, 1, s, s)
-    probs = _view(bf.probs, (b, 1, 1, s, s))
+    lg, pb = bf.attention_scratch(scratch)
+    logits = lg[:b * s * s].view(b, 1, 1, s, s)
+    probs = _view(pb, (b, 1, 1, s, s))
     ops.conv_gemm(q_src, c, SplitTensor(k_src.hi.view(b, s, 4 * c), None if k_src.lo is None else k_src.lo.view(b, s, 4 * c)), s,
                   a_ch_off=q_off, w_batched=True, w_ld=4 * c, w_ch_off=k_off, out_f32=logits)
     ops.softmax_rows(logits, probs)
     ops.conv_gemm(probs, s, vt, c, w_batched=True, residual=v if residual else None, out=out, o_ch_off=o_off)
 
 
-def run_attention_level(bf, lv, w_hori, w_vert, ra, re):
+def run_attention_level(bf, lv, w_hori, w_vert, ra, re, concurrent=False):
     """One scale of the cross/self attention (layers.py:138-149): fills cat[..., prev : prev + 4C] with
-    (ra_cross, ra_self, re_cross, re_self)."""
+    (ra_cross, ra_self, re_cross, re_self).  ``concurrent`` (small batches): the four attentions are independent and each fills only
+    batch * S / 128 CTAs (32 of 148 SMs at batch 1, level 1), so they run as four parallel branches (fork / join on side streams, parallel
+    branches of the captured graph) instead of back to back."""
     c, prev = lv["c"], lv["prev"]
     b, hw = ra.hi.shape[0], lv["hw"]
     ra_s = SplitTensor(ra.hi.view(b, 1, 1, lv["s"], c), None if ra.lo is None else ra.lo.view(b, 1, 1, lv["s"], c))
@@ -238,34 +259,48 @@ def run_attention_level(bf, lv, w_hori, w_vert, ra, re):
     cat = lv["cat"]
     cat_s = SplitTensor(cat.hi.view(b, 1, 1, lv["s"], prev + 4 * c), None if cat.lo is None else cat.lo.view(b, 1, 1, lv["s"], prev + 4 * c))
     pra, pre = lv["proj_ra"], lv["proj_re"]
-    # ra_cross: k = phi_c_hori(ra), q = theta_c_vert(re), v = ra, + ra
-    run_attention(bf, lv, pre, c, pra, 0, ra_s, lv["vt_ra"], cat_s, prev, True)
-    # ra_self : k = phi_s_hori(ra), q = theta_s_hori(ra), v = ra
-    run_attention(bf, lv, pra, 3 * c, pra, 2 * c, ra_s, lv["vt_ra"], cat_s, prev + c, False)
-    # re_cross: k = phi_c_vert(re), q = theta_c_hori(ra), v = re, + re
-    run_attention(bf, lv, pra, c, pre, 0, re_s, lv["vt_re"], cat_s, prev + 2 * c, True)
-    # re_self : k = phi_s_vert(re), q = theta_s_vert(re), v = re
-    run_attention(bf, lv, pre, 3 * c, pre, 2 * c, re_s, lv["vt_re"], cat_s, prev + 3 * c, False)
+    jobs = [
+        (pre, c, pra, 0, ra_s, lv["vt_ra"], prev, True),                 # ra_cross: k = phi_c_hori(ra), q = theta_c_vert(re), v = ra, + ra
+        (pra, 3 * c, pra, 2 * c, ra_s, lv["vt_ra"], prev + c, False),    # ra_self : k = phi_s_hori(ra), q = theta_s_hori(ra), v = ra
+        (pra, c, pre, 0, re_s, lv["vt_re"], prev + 2 * c, True),         # re_cross: k = phi_c_vert(re), q = theta_c_hori(ra), v = re, + re
+        (pre, 3 * c, pre, 2 * c, re_s, lv["vt_re"], prev + 3 * c, False),   # re_self : k = phi_s_vert(re), q = theta_s_vert(re), v = re
+    ]
+    if not concurrent:
+        for q_src, q_off, k_src, k_off, v, vt, o_off, res in jobs:
+            run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, cat_s, o_off, res)
+        return cat
+    main = torch.cuda.current_stream()
+    sides = bf.attention_streams(ra.hi.device)
+    for side in sides:
+        side.wait_stream(main)                                           # fork: projections and transposes are done on the main stream
+    for i, (q_src, q_off, k_src, k_off, v, vt, o_off, res) in enumerate(jobs):
+        if i == 0:
+            run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, cat_s, o_off, res, scratch=0)
+        else:
+            with torch.cuda.stream(sides[i - 1]), ops.coop_slot(("attention", i)):
+                run_attention(bf, lv, q_src, q_off, k_src, k_off, v, vt, cat_s, o_off, res, scratch=i)
+    for side in sides:
+        main.wait_stream(side)                                           # join
     return cat
 
 
-def run_decoder(w, bf, feats_ra, feats_re, adj):
+def run_decoder(w, bf, feats_ra, feats_re, adj, concurrent=False):
     """feats_* = (f1, f2, f3).  Returns (heatmap, gcn_heatmap) float32 ``[B, 14, 64, 64]``."""
     nf = w.nf
     l3, l2, l1 = bf.levels
-    cat3 = run_attention_level(bf, l3, w.proj_hori[0], w.proj_vert[0], feats_ra[2], feats_re[2])
+    cat3 = run_attention_level(bf, l3, w.proj_hori[0], w.proj_vert[0], feats_ra[2], feats_re[2], concurrent)
     run_block(cat3, w.blocks[0], bf.t3a, bf.o3a)
     run_block(bf.o3a, w.blocks[1], bf.t3b, bf.o3b)
     ops.resample_linear(bf.o3b, 4 * nf, l2["cat"])
-    cat2 = run_attention_level(bf, l2, w.proj_hori[1], w.proj_vert[1], feats_ra[1], feats_re[1])
+    cat2 = run_attention_level(bf, l2, w.proj_hori[1], w.proj_vert[1], feats_ra[1], feats_re[1], concurrent)
     run_block(cat2, w.blocks[2], bf.t2a, bf.o2a)
     run_block(bf.o2a, w.blocks[3], bf.t2b, bf.o2b)
     ops.resample_linear(bf.o2b, 2 * nf, l1["cat"])
-    cat1 = run_attention_level(bf, l1, w.proj_hori[2], w.proj_vert[2], feats_ra[0], feats_re[0])
+    cat1 = run_attention_level(bf, l1, w.proj_hori[2], w.proj_vert[2], feats_ra[0], feats_re[0], concurrent)
     run_block(cat1, w.blocks[4], bf.t1a, bf.o1a)
     run_block(bf.o1a, w.blocks[5], bf.t1b, bf.o1b)
     b = bf.o1b.hi.shape[0]
-    ops.conv_gemm(bf.o1b, pad64(nf), w.head, bf.logits_out.shape[-1], out_f32=bf.logits_out.view(b, 1, 64, 64, -1))
+    ops.conv_gemm(bf.o1b, pad64(nf), w.head, bf.logits_out.shape[-1], out_f32=bf.logits_out.view(b, 1, 64, 64, -1), lcin=nf, lcout=w.keypoints)
     if w.gcn_w_tc is None:
         ops.prgcn_fwd(bf.logits_out, w.gcn_w, w.gcn_b, adj, bf.gcn_ws, bf.heatmap, bf.gcn_heatmap)
         return bf.heatmap, bf.gcn_heatmap
@@ -278,10 +313,11 @@ def run_decoder(w, bf, feats_ra, feats_re, adj):
         bf.gcn_bias_rows = rows
     st_a, st_b = bf.gcn_st
     ops.gcn_nodes(bf.logits_out, adj, bf.heatmap, st_a)
-    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[0], 1024, residual=bf.gcn_bias_rows[0], slope=w.gcn_relu, out=st_b)
+    lr = b * w.keypoints                 # GEMM rows that carry data (the rest is tile padding)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[0], 1024, residual=bf.gcn_bias_rows[0], slope=w.gcn_relu, out=st_b, lrows=lr)
     ops.gcn_mix(st_b, adj, st_a, b)
-    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[1], 1024, residual=bf.gcn_bias_rows[1], slope=w.gcn_relu, out=st_b)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[1], 1024, residual=bf.gcn_bias_rows[1], slope=w.gcn_relu, out=st_b, lrows=lr)
     ops.gcn_mix(st_b, adj, st_a, b)
-    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[2], 1024, residual=bf.gcn_bias_rows[2], out_f32=bf.gcn_y3)
+    ops.conv_gemm(st_a, 1024, w.gcn_w_tc[2], 1024, residual=bf.gcn_bias_rows[2], out_f32=bf.gcn_y3, lrows=lr)
     ops.gcn_heads(bf.gcn_y3.view(bf.gcn_rows, 1024), bf.gcn_heatmap, b)
     return bf.heatmap, bf.gcn_heatmap

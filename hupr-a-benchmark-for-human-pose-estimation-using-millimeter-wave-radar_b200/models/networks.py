@@ -233,7 +233,8 @@ class HuPRNet(nn.Module):
             return self._forward_features(pk, plan, batch, chirp_ra, chirp_re)
 
     def _forward_features(self, pk, plan, batch, chirp_ra, chirp_re):
-        if batch <= 4 and ops._PROFILE is None:
+        small = batch <= 4 and ops._PROFILE is None
+        if small:
             # small batches leave most SMs idle inside one encoder (level 2/3 convolutions launch 16-64 CTAs): run the two
             # independent sensor branches on two streams (fork/join with events, captured into the CUDA graph as parallel branches)
             main = torch.cuda.current_stream()
@@ -248,7 +249,7 @@ class HuPRNet(nn.Module):
         else:
             feats_ra = L.run_encoder(chirp_ra, pk["RAradarEncoder"], plan["enc_ra"])
             feats_re = L.run_encoder(chirp_re, pk["REradarEncoder"], plan["enc_re"])
-        return L.run_decoder(pk["decoder"], plan["dec"], feats_ra, feats_re, pk["adj"])
+        return L.run_decoder(pk["decoder"], plan["dec"], feats_ra, feats_re, pk["adj"], concurrent=small)
 
     def _forward_train(self, hori, vert):
         """networks.py:35-41 under ``model.train()`` (tools/run.py:66,76): batch-statistics BatchNorm, outputs connected to autograd."""

@@ -71,7 +71,7 @@ class SplitTensor(object):
         return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
 
 
-COOP_WS_BYTES = 16 << 20
+COOP_WS_BYTES = 40 << 20
 _COOP_DEFAULT = os.environ.get("HUPR_NO_COOP", "") == ""      # A/B switch for measurements
 
 
