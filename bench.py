@@ -309,8 +309,9 @@ def train_probe(dev, world, gen, steps, products):
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(steps):
-        losses.append(one(True))
+        loss = one(True)
         torch.cuda.current_stream().synchronize()
+        losses.append(float(loss))                # the graph's loss tensor is static: read it before the next replay overwrites it
         ar_ms.append(ev[1].elapsed_time(ev[2]))
     ev[3].record()
     torch.cuda.synchronize()
@@ -326,7 +327,7 @@ def train_probe(dev, world, gen, steps, products):
             "samples_per_gpu": b, "global_batch": b * world, "steps": steps, "ms_per_step": ms, "allreduce_ms": ar,
             "allreduce_bytes": trainer.flat_g.numel() * 4, "samples_per_s": b * world / (ms * 1e-3),
             "products_per_k_step": products, "replicas_identical": bool(torch.equal(lo, hi)),
-            "loss_first_last": [float(losses[0]), float(losses[-1])]}
+            "loss_first_last": [losses[0], losses[-1]]}
 
 
 def run_cascade_sweep(args, dev, world, rank, local_rank, peaks, gen, sync_all):

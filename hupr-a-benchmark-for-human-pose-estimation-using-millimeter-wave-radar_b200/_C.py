@@ -78,6 +78,16 @@ class WgradDesc(ctypes.Structure):
     ]
 
 
+class PackJob(ctypes.Structure):
+    """Mirror of ``hupr_pack_job``."""
+    _fields_ = [
+        ("w", ctypes.c_void_p), ("a_hi", ctypes.c_void_p), ("a_lo", ctypes.c_void_p), ("b_hi", ctypes.c_void_p), ("b_lo", ctypes.c_void_p),
+        ("cout", ctypes.c_int), ("cin", ctypes.c_int), ("taps", ctypes.c_int),
+        ("cout_total", ctypes.c_int), ("cin_pad", ctypes.c_int), ("cout_off", ctypes.c_int),
+        ("blocks_x", ctypes.c_int), ("block_begin", ctypes.c_int),
+    ]
+
+
 class TensorView(ctypes.Structure):
     """Mirror of ``hupr_tensor_view``."""
     _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("ld", ctypes.c_int), ("ch_off", ctypes.c_int)]
@@ -137,6 +147,8 @@ SIGNATURES = {
     "hupr_heatmap_loss_fwd": (ctypes.c_int, [_P, _P, _P, _I, _P, ctypes.c_size_t, _P, _P, _P, _P]),
     "hupr_pack_conv_weights": (ctypes.c_int, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "hupr_unpack_wgrad": (ctypes.c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "hupr_pack_conv_weights_multi": (ctypes.c_int, [_P, _P, _I, _I, _P]),
+    "hupr_unpack_wgrad_multi": (ctypes.c_int, [_P, _P, _I, _I, _P]),
     "hupr_reduce_f64": (ctypes.c_int, [_P, _I, _I, _P, _P]),
     "hupr_broadcast_f32": (ctypes.c_int, [_P, _P, _I, _P]),
     "hupr_gcn_bias_rows": (ctypes.c_int, [_P, _I, _I, _P, _P, _P]),

@@ -19,13 +19,25 @@ namespace hupr {
 
 constexpr int PK_T = 16;     // channels per tile side
 
+// Job table of the batched entry points (hupr_pack_conv_weights_multi / hupr_unpack_wgrad_multi): the ~85 parameter tensors of the model
+// are (un)packed by ONE launch each; `block_job[b]` names the job of CTA b and `block_begin` its first CTA.
+struct PackJob {                 // mirrors hupr_pack_job (include/hupr_b200.h)
+    const float* w;              // pack: fp32 source [cout][cin][taps]; unpack: fp32 accumulator [taps][cin_pad][cout_total]
+    void* a_hi; void* a_lo;      // pack: forward operand planes; unpack: a_hi = fp32 destination [cout][cin][taps], a_lo unused
+    void* b_hi; void* b_lo;      // pack: data-gradient operand planes (may be null); unpack: unused
+    int cout, cin, taps;
+    int cout_total, cin_pad, cout_off;
+    int blocks_x;                // ceil(cout / 16)
+    int block_begin;             // first CTA of this job in the batched grid
+};
+
 // One CTA: a [16 cout] x [16 cin] x [taps] brick.  Source rows (ci, tap) of one cout are contiguous, so the load is coalesced; both
 // stores write 32-byte segments (16 bf16 along cin for the forward layout, 16 bf16 along cout for the data-gradient layout).
-__global__ void __launch_bounds__(256)
-pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
-                 int cout_total, int cin_pad, int cout_off, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+__device__ __forceinline__ void
+pack_conv_brick(const float* __restrict__ w, int cout, int cin, int taps, __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
+                int cout_total, int cin_pad, int cout_off, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int bx, int by) {
     extern __shared__ float brick[];                      // [16 co][16 ci][taps]
-    const int co0 = blockIdx.x * PK_T, ci0 = blockIdx.y * PK_T;
+    const int co0 = bx * PK_T, ci0 = by * PK_T;
     const int row = PK_T * taps;                          // floats of one cout row of the brick
     for (int i = threadIdx.x; i < PK_T * row; i += 256) {
         const int co_l = i / row, rem = i - co_l * row;
@@ -60,11 +72,18 @@ pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, __nv_
     }
 }
 
-// acc fp32 [taps][cin_pad][cout_total] -> dst fp32 [cout][cin][taps] for the output channels [cout_off, cout_off + cout).
 __global__ void __launch_bounds__(256)
-unpack_wgrad_kernel(const float* __restrict__ acc, int taps, int cin_pad, int cout_total, int cout_off, float* __restrict__ dst, int cout, int cin) {
+pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
+                 int cout_total, int cin_pad, int cout_off, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+    pack_conv_brick(w, cout, cin, taps, f_hi, f_lo, cout_total, cin_pad, cout_off, d_hi, d_lo, blockIdx.x, blockIdx.y);
+}
+
+// acc fp32 [taps][cin_pad][cout_total] -> dst fp32 [cout][cin][taps] for the output channels [cout_off, cout_off + cout).
+__device__ __forceinline__ void
+unpack_wgrad_brick(const float* __restrict__ acc, int taps, int cin_pad, int cout_total, int cout_off, float* __restrict__ dst, int cout, int cin,
+                   int bx, int by) {
     extern __shared__ float brick[];                      // [16 co][16 ci][taps]
-    const int co0 = blockIdx.x * PK_T, ci0 = blockIdx.y * PK_T;
+    const int co0 = bx * PK_T, ci0 = by * PK_T;
     for (int i = threadIdx.x; i < taps * PK_T * PK_T; i += 256) {
         const int co_l = i % PK_T, ci_l = (i / PK_T) % PK_T, t = i / (PK_T * PK_T);
         float v = 0.f;
@@ -78,6 +97,26 @@ unpack_wgrad_kernel(const float* __restrict__ acc, int taps, int cin_pad, int co
         const int ci_l = rem / taps;
         if (co0 + co_l < cout && ci0 + ci_l < cin) dst[((size_t)(co0 + co_l) * cin + ci0) * taps + rem] = brick[i];
     }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_wgrad_kernel(const float* __restrict__ acc, int taps, int cin_pad, int cout_total, int cout_off, float* __restrict__ dst, int cout, int cin) {
+    unpack_wgrad_brick(acc, taps, cin_pad, cout_total, cout_off, dst, cout, cin, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(256)
+pack_conv_multi_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ block_job) {
+    const PackJob j = jobs[__ldg(block_job + blockIdx.x)];
+    const int local = blockIdx.x - j.block_begin;
+    pack_conv_brick(j.w, j.cout, j.cin, j.taps, (__nv_bfloat16*)j.a_hi, (__nv_bfloat16*)j.a_lo, j.cout_total, j.cin_pad, j.cout_off,
+                    (__nv_bfloat16*)j.b_hi, (__nv_bfloat16*)j.b_lo, local % j.blocks_x, local / j.blocks_x);
+}
+
+__global__ void __launch_bounds__(256)
+unpack_wgrad_multi_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ block_job) {
+    const PackJob j = jobs[__ldg(block_job + blockIdx.x)];
+    const int local = blockIdx.x - j.block_begin;
+    unpack_wgrad_brick(j.w, j.taps, j.cin_pad, j.cout_total, j.cout_off, (float*)j.a_hi, j.cout, j.cin, local % j.blocks_x, local / j.blocks_x);
 }
 
 __global__ void __launch_bounds__(128)
@@ -147,6 +186,31 @@ extern "C" int hupr_unpack_wgrad(const float* acc, int taps, int cin_pad, int co
     const dim3 grid((cout + PK_T - 1) / PK_T, (cin + PK_T - 1) / PK_T);
     const size_t smem = (size_t)PK_T * PK_T * taps * sizeof(float);
     unpack_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(acc, taps, cin_pad, cout_total, cout_off, dst, cout, cin);
+    return pack_status();
+}
+
+// Batched forms: jobs / block_job are DEVICE arrays built once by the caller (hupr_pack_job: include/hupr_b200.h); every job must satisfy
+// the single-job entry point's constraints (validated by the caller when the table is built: hupr_b200/training.py).
+extern "C" int hupr_pack_conv_weights_multi(const hupr_pack_job* jobs, const int* block_job, int total_blocks, int max_taps, void* stream) {
+    using namespace hupr;
+    static_assert(sizeof(PackJob) == sizeof(hupr_pack_job), "PackJob mirrors hupr_pack_job");
+    if (total_blocks < 0 || max_taps <= 0 || max_taps > 32) return HUPR_ERR_BAD_ARG;
+    if (total_blocks == 0) return HUPR_OK;
+    if (!jobs || !block_job) return HUPR_ERR_BAD_ARG;
+    if (int rc = device_check_sm100()) return rc;
+    const size_t smem = (size_t)PK_T * PK_T * max_taps * sizeof(float);
+    pack_conv_multi_kernel<<<total_blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const PackJob*>(jobs), block_job);
+    return pack_status();
+}
+
+extern "C" int hupr_unpack_wgrad_multi(const hupr_pack_job* jobs, const int* block_job, int total_blocks, int max_taps, void* stream) {
+    using namespace hupr;
+    if (total_blocks < 0 || max_taps <= 0 || max_taps > 32) return HUPR_ERR_BAD_ARG;
+    if (total_blocks == 0) return HUPR_OK;
+    if (!jobs || !block_job) return HUPR_ERR_BAD_ARG;
+    if (int rc = device_check_sm100()) return rc;
+    const size_t smem = (size_t)PK_T * PK_T * max_taps * sizeof(float);
+    unpack_wgrad_multi_kernel<<<total_blocks, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const PackJob*>(jobs), block_job);
     return pack_status();
 }
 

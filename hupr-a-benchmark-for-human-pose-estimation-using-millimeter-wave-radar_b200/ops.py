@@ -480,6 +480,41 @@ def unpack_wgrad(acc, cout_off, dst):
         _call("hupr_unpack_wgrad", _p(acc), taps, cin_pad, cout_total, cout_off, _p(dst), cout, cin, _C.stream_ptr())
 
 
+class PackTable(object):
+    """Device-resident job table of the batched (un)pack launches (hupr_pack_conv_weights_multi / hupr_unpack_wgrad_multi): built once
+    from ``(w, a_hi, a_lo, b_hi, b_lo, cout, cin, taps, cout_total, cin_pad, cout_off)`` tuples of raw pointers / sizes."""
+
+    def __init__(self, jobs, device):
+        import ctypes
+        import numpy as np
+        arr = (_C.PackJob * max(len(jobs), 1))()
+        block_job, begin, self.max_taps = [], 0, 1
+        for i, (w, a_hi, a_lo, b_hi, b_lo, cout, cin, taps, cout_total, cin_pad, cout_off) in enumerate(jobs):
+            if cout % 2 or cin % 2 or cout_off % 2 or cin_pad % 2 or cout_total % 2 or not 0 < taps <= 32 or cout_off + cout > cout_total or cin > cin_pad:
+                raise ValueError("PackTable: job %d violates the layout constraints of hupr_pack_conv_weights" % i)
+            bx, by = -(-cout // 16), -(-cin // 16)
+            j = arr[i]
+            j.w, j.a_hi, j.a_lo, j.b_hi, j.b_lo = w, a_hi, a_lo, b_hi, b_lo
+            j.cout, j.cin, j.taps, j.cout_total, j.cin_pad, j.cout_off = cout, cin, taps, cout_total, cin_pad, cout_off
+            j.blocks_x, j.block_begin = bx, begin
+            block_job.extend([i] * (bx * by))
+            begin += bx * by
+            self.max_taps = max(self.max_taps, taps)
+        self.key = tuple(jobs)
+        self.total_blocks = begin
+        raw = np.frombuffer(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr)), dtype=np.uint8).copy()
+        self.jobs = torch.from_numpy(raw).to(device)
+        self.block_job = torch.tensor(block_job if block_job else [0], dtype=torch.int32, device=device)
+
+    def pack(self):
+        with torch.cuda.device(self.jobs.device):
+            _call("hupr_pack_conv_weights_multi", _p(self.jobs), _p(self.block_job), self.total_blocks, self.max_taps, _C.stream_ptr())
+
+    def unpack(self):
+        with torch.cuda.device(self.jobs.device):
+            _call("hupr_unpack_wgrad_multi", _p(self.jobs), _p(self.block_job), self.total_blocks, self.max_taps, _C.stream_ptr())
+
+
 def reduce_f64(src, groups, n, dst):
     """dst[g] = float(sum_i src[g*n + i]) — hupr_reduce_f64 (float64 partial sums -> float32 gradient storage)."""
     with torch.cuda.device(src.device):

@@ -106,6 +106,10 @@ def _rows(t):
     return SplitTensor(t.hi.view(n, 1, 1, s, c), t.lo.view(n, 1, 1, s, c))
 
 
+_UNPACK_JOBS = "__unpack_jobs__"      # key under which TrainStep collects the (accumulator, gradient) pairs of its batched unpack launch
+_KEEP_ALIVE = "__keep_alive__"
+
+
 def _grad_out(grads, name, shape, dev):
     """Destination of a parameter gradient: the pre-installed tensor of ``grads`` (TrainStep: a view of the flat gradient buffer) or a
     fresh float32 tensor stored under ``name`` (block-level use with a plain dict)."""
@@ -132,18 +136,40 @@ class ConvOp(object):
     def pack(self, sd):
         """sd: name -> float32 parameter (torch layout).  Rebuilds the forward [taps, cout, cin_pad] and data-gradient
         [flipped taps, cin_pad, cout] hi/lo operands in place (hupr_pack_conv_weights; the zero padding is written once, here)."""
+        ws = self._bind(sd)
+        o = 0
+        for w, cp in zip(ws, self.cout_pads):
+            ops.pack_conv_weights(w, self.w, o, self.wd)
+            o += cp
+        self._bind_bias(sd)
+
+    def _bind(self, sd):
+        """Allocate the (zero-padded) operand buffers on first use and record the parameter shapes; returns the fp32 sources."""
         ws = [sd[n].detach() for n in self.names]
         dev = ws[0].device
         if self.w is None or self.w.hi.device != dev:
             self.w = SplitTensor.empty((self.taps, self.cout, self.cin_pad), dev, True, zero=True)
             self.wd = SplitTensor.empty((self.taps, self.cin_pad, self.cout), dev, True, zero=True)
-        o = 0
-        for n, w, cp in zip(self.names, ws, self.cout_pads):
+        out = []
+        for n, w in zip(self.names, ws):
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
             self.shapes[n] = tuple(w.shape)
-            ops.pack_conv_weights(w, self.w, o, self.wd)
+            out.append(w)
+        return out
+
+    def pack_jobs(self, sd):
+        """Job tuples of this convolution for the batched pack launch (ops.PackTable); the sources must be the LIVE fp32 parameters."""
+        ws = self._bind(sd)
+        self._bind_bias(sd)
+        jobs, o = [], 0
+        for w, cp in zip(ws, self.cout_pads):
+            jobs.append((w.data_ptr(), self.w.hi.data_ptr(), self.w.lo.data_ptr(), self.wd.hi.data_ptr(), self.wd.lo.data_ptr(),
+                         w.shape[0], w.shape[1], self.taps, self.cout, self.cin_pad, o))
             o += cp
+        return jobs
+
+    def _bind_bias(self, sd):
         b = sd[self.bias_name].detach() if self.bias_name else None
         self.bias = b if b is None or (b.dtype == torch.float32 and b.is_contiguous()) else b.float().contiguous()
         if self.bias_name:
@@ -166,8 +192,14 @@ class ConvOp(object):
         acc = _zeros((self.taps, self.cin_pad, self.cout), torch.float32, dev)
         ops.conv_wgrad_direct(x, x_off, self.cin_pad, dy, dy_off, self.cout, self.kernel, self.pad, out=acc, lcin=self.cin, lcout=self.lcout)
         o = 0
+        deferred = grads.get(_UNPACK_JOBS)           # TrainStep: one batched unpack launch at the end of the backward pass
         for name, cp in zip(self.names, self.cout_pads):
-            ops.unpack_wgrad(acc, o, _grad_out(grads, name, self.shapes[name], dev))
+            dst = _grad_out(grads, name, self.shapes[name], dev)
+            if deferred is not None:
+                deferred.append((acc.data_ptr(), dst.data_ptr(), 0, 0, 0, dst.shape[0], dst.shape[1], self.taps, self.cout, self.cin_pad, o))
+                grads[_KEEP_ALIVE].append(acc)       # an individually allocated accumulator must outlive the deferred launch
+            else:
+                ops.unpack_wgrad(acc, o, dst)
             o += cp
         if self.bias_name:
             sums = _zeros((2, self.cout), torch.float64, dev)
@@ -275,6 +307,9 @@ class Block2D(object):
     def pack(self, sd):
         self.conv1.pack(sd)
         self.conv2.pack(sd)
+        self.pack_slopes(sd)
+
+    def pack_slopes(self, sd):
         s1, s2 = sd[self.prefix + ".main.1.weight"].detach(), sd[self.prefix + ".relu.weight"].detach()
         dev = s1.device
         if self.a1 is None or self.a1.device != dev:
@@ -553,25 +588,47 @@ class TrainStep(object):
         self._gcn_bufs = {}                       # batch size -> persistent zero-padded GCN row buffers
         self._dirty = True
         self._saved = None
+        self._pack_table = None                   # batched pack launch (built on the first _pack)
+        self._unpack_tables = {}                  # batch size -> (job key, ops.PackTable) of the batched gradient unpack
         self._gptr = {id(q): self.gview[name].data_ptr() for name, q in model.named_parameters()}
         model._train_step = self                  # one TrainStep owns a model's flat parameter storage (HuPRNet._forward_train reuses it)
 
     def gview_ptr(self, q):
         return self._gptr.get(id(q), 0)
 
+    def _conv_ops(self):
+        ops_ = []
+        for e in self.enc.values():
+            ops_.append(e.conv0)
+            for blk in e.blocks:
+                ops_ += [blk.conv1, blk.conv2]
+            ops_ += e.merges
+        for lvl in self.levels:
+            ops_ += [lvl.proj_h, lvl.proj_v]
+        for blk in self.dblocks:
+            ops_ += [blk.conv1, blk.conv2]
+        return ops_ + [self.head]
+
     # ---------------------------------------------------------------------------------------------------------------- packing
     def _pack(self):
         """Operand layouts of every contraction from the flat fp32 parameters — library launches only (hupr_pack_conv_weights,
         hupr_broadcast_f32), so a captured step re-packs after its own Adam launch without any framework kernel."""
         sd = {k: v.data for k, v in self.model.named_parameters()}
-        for e in self.enc.values():
-            e.pack(sd)
-        for m in self.levels + self.dblocks:
-            m.pack(sd)
-        self.head.pack(sd)
         p = "radarDecoder."
-        for i in range(3):
-            ops.pack_conv_weights(sd[p + "gcn.L%d.weight" % (i + 1)], self.gcn_w[i], 0, self.gcn_wt[i])
+        if self._pack_table is None:
+            # ONE launch re-packs all 84 convolution filters and the three GCN matrices (hupr_pack_conv_weights_multi): the table holds raw
+            # pointers into the flat parameter buffer and the persistent operand buffers, both fixed for the life of this object
+            jobs = []
+            for conv in self._conv_ops():
+                jobs += conv.pack_jobs(sd)
+            for i in range(3):
+                w = sd[p + "gcn.L%d.weight" % (i + 1)]
+                jobs.append((w.data_ptr(), self.gcn_w[i].hi.data_ptr(), self.gcn_w[i].lo.data_ptr(), self.gcn_wt[i].hi.data_ptr(),
+                             self.gcn_wt[i].lo.data_ptr(), 1024, 1024, 1, 1024, 1024, 0))
+            self._pack_table = ops.PackTable(jobs, self.device)
+        self._pack_table.pack()
+        for blk in self.dblocks:
+            blk.pack_slopes(sd)
         self.gcn_b = [sd[p + "gcn.L%d.bias" % i] for i in (1, 2, 3)]
         self.mnet = {k: (sd[n + ".temporalConvWx1x1.weight"], sd[n + ".temporalConvWx1x1.bias"]) for k, n in (("ra", "RAchirpNet"), ("re", "REchirpNet"))}
         self._dirty = False
@@ -666,6 +723,7 @@ class TrainStep(object):
         b, rows, st, yt = sv.b, sv.rows, sv.st, sv.yt
         kpad = L.pad64(kp)
         grads = dict(self.gview)
+        grads[_UNPACK_JOBS], grads[_KEEP_ALIVE] = [], []
         gb = self._gcn_buffers(b)
         relu = self.gcn_relu
         dy3f = _zeros((rows, 1024), torch.float32, dev)
@@ -720,6 +778,16 @@ class TrainStep(object):
             net = "RAchirpNet" if key == "ra" else "REchirpNet"
             ops.reduce_f64(dwb, nf * 4, 1, grads[net + ".temporalConvWx1x1.weight"])
             ops.reduce_f64(dwb[nf * 4:], nf, 1, grads[net + ".temporalConvWx1x1.bias"])
+        # ---- every filter gradient from its [taps, cin_pad, cout] accumulator into the torch-layout flat buffer: ONE launch.  The table is
+        # rebuilt only when an accumulator moved (the planning pass of the scratch arena); it is static by the time a graph is captured.
+        jobs = tuple(grads.pop(_UNPACK_JOBS))
+        cached = self._unpack_tables.get(b)
+        if cached is None or cached.key != jobs:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("hupr_b200.training: gradient accumulators moved during CUDA-graph capture (run the warm-up passes first)")
+            cached = self._unpack_tables[b] = ops.PackTable(jobs, self.device)
+        cached.unpack()
+        grads.pop(_KEEP_ALIVE)
         self.last_grads = grads
 
     # ---------------------------------------------------------------------------------------------------------------- step

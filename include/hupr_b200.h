@@ -380,6 +380,20 @@ int hupr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int hupr_pack_conv_weights(const float* w, int cout, int cin, int taps, void* fwd_hi, void* fwd_lo, int cout_total, int cin_pad, int cout_off,
                            void* dgrad_hi, void* dgrad_lo, void* stream);
 int hupr_unpack_wgrad(const float* acc, int taps, int cin_pad, int cout_total, int cout_off, float* dst, int cout, int cin, void* stream);
+/* Batched forms: ONE launch (un)packs every parameter tensor of the model.  `jobs` and `block_job` are DEVICE arrays built once by the
+ * caller: jobs[j] describes tensor j with the arguments of the single-tensor entry points; the grid has sum_j blocks_x * ceil(cin/16)
+ * CTAs, block_job[b] = the job of CTA b, jobs[j].block_begin = its first CTA.  max_taps = the largest `taps` of the table. */
+typedef struct hupr_pack_job {
+    const float* w;              /* pack: fp32 source [cout][cin][taps];  unpack: fp32 accumulator [taps][cin_pad][cout_total] */
+    void* a_hi; void* a_lo;      /* pack: forward operand planes;         unpack: a_hi = fp32 destination [cout][cin][taps] */
+    void* b_hi; void* b_lo;      /* pack: data-gradient operand planes (may be NULL);  unpack: unused */
+    int cout, cin, taps;
+    int cout_total, cin_pad, cout_off;
+    int blocks_x;                /* ceil(cout / 16) */
+    int block_begin;
+} hupr_pack_job;
+int hupr_pack_conv_weights_multi(const hupr_pack_job* jobs, const int* block_job, int total_blocks, int max_taps, void* stream);
+int hupr_unpack_wgrad_multi(const hupr_pack_job* jobs, const int* block_job, int total_blocks, int max_taps, void* stream);
 int hupr_reduce_f64(const double* src, int groups, int n, float* dst, void* stream);
 int hupr_broadcast_f32(const float* src, float* dst, int n, void* stream);
 int hupr_gcn_bias_rows(const float* bias, int batch, int rows, void* rows_hi, void* rows_lo, void* stream);

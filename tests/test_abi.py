@@ -59,7 +59,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     if gcc is None:
         pytest.skip("no C compiler")
     mirrors = {"hupr_conv_desc": _C.ConvDesc, "hupr_attn_desc": _C.AttnDesc, "hupr_attn_bwd_desc": _C.AttnBwdDesc,
-               "hupr_wgrad_desc": _C.WgradDesc, "hupr_tensor_view": _C.TensorView}
+               "hupr_wgrad_desc": _C.WgradDesc, "hupr_tensor_view": _C.TensorView, "hupr_pack_job": _C.PackJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hupr_b200.h"', 'int main(void) {']
     for cname, cls in mirrors.items():
         lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
