@@ -32,6 +32,7 @@ class ConvDesc(ctypes.Structure):
         ("ws", ctypes.c_void_p), ("ws_bytes", ctypes.c_size_t),
         ("no_tma_store", ctypes.c_int),
         ("nprod", ctypes.c_int),
+        ("stats", ctypes.c_void_p), ("stats_ld", ctypes.c_int),
     ]
 
 

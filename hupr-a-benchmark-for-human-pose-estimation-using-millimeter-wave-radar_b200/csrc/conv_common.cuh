@@ -35,7 +35,53 @@ struct ConvParams {
     int coop;
     size_t coop_ws_bytes;
     int n_fastest;                 // work-item order: column tile fastest (wide outputs) instead of row tile fastest
+    double* stats;                 // optional per-output-channel sums of the epilogue values: stats[ch] += sum v, stats[stats_ld + ch] += sum v^2
+    int stats_ld;                  // (train-mode BatchNorm batch statistics fused into the producing convolution, layers.py:45-53)
 };
+
+// Column sums over a warp: every lane holds 32 values (one row of a 32-row x 32-column block); after five exchange rounds
+// (recursive halving, 31 shuffles) lane j holds the sum of column j over the 32 rows.
+__device__ __forceinline__ float warp_column_sums32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// Fused BatchNorm statistics: `wstat` = one warp's running column sums in shared memory, [sum v | sum v^2] x `width` columns; lane j owns
+// columns j, j + 32, ...  stat_add folds a 32-row x 32-column block in (31 + 31 shuffles), stat_flush adds the totals to global memory.
+__device__ __forceinline__ void stat_add(float* wstat32, int width, const float (&v)[32], int lane) {
+    float a[32], b[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { a[j] = v[j]; b[j] = v[j] * v[j]; }
+    const float s1 = warp_column_sums32(a, lane), s2 = warp_column_sums32(b, lane);
+    wstat32[lane] += s1;
+    wstat32[width + lane] += s2;
+}
+// Direct form (generic kernel: few tiles per CTA, column tile changes from item to item): the block's column sums go straight to global memory.
+__device__ __forceinline__ void stat_add_global(const ConvParams& p, const float (&v)[32], int ch0, int lane) {
+    float a[32], b[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { a[j] = v[j]; b[j] = v[j] * v[j]; }
+    const float s1 = warp_column_sums32(a, lane), s2 = warp_column_sums32(b, lane);
+    atomicAdd(p.stats + ch0 + lane, (double)s1);
+    atomicAdd(p.stats + p.stats_ld + ch0 + lane, (double)s2);
+}
+__device__ __forceinline__ void stat_flush(const ConvParams& p, float* wstat, int width, int ch0, int lane) {
+    for (int j = lane; j < width; j += 32) {
+        atomicAdd(p.stats + ch0 + j, (double)wstat[j]);
+        atomicAdd(p.stats + p.stats_ld + ch0 + j, (double)wstat[width + j]);
+        wstat[j] = 0.f;
+        wstat[width + j] = 0.f;
+    }
+}
 
 // acc: 32 consecutive accumulator columns (channels ch0 .. ch0+31) of output position `pos` -> epilogue values v (everything but the stores).
 // rv = row_vec[pos] (loaded by the caller ahead of time; ignored unless row_mode).
@@ -100,9 +146,8 @@ __device__ __forceinline__ void conv_epilogue_values(const ConvParams& p, const 
     }
 }
 
-__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float rv) {
-    float v[32];
-    conv_epilogue_values(p, acc, pos, ch0, v, rv);
+// Stores of 32 epilogue values of one row (fp32 and/or hi/lo bf16; split-K partial sums are added atomically).
+__device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, const float (&v)[32], size_t pos, int ch0) {
     if (p.atomic) {     // split-K partial sum (no scale / shift / residual / activation on this path)
         float* dst = p.o_f32 + pos * p.o_f32_ld + ch0;
 #pragma unroll
@@ -127,6 +172,29 @@ __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint3
             for (int g = 0; g < 4; ++g) dl[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
         }
     }
+}
+
+__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float rv) {
+    float v[32];
+    conv_epilogue_values(p, acc, pos, ch0, v, rv);
+    conv_epilogue_store(p, v, pos, ch0);
+}
+
+// Same, also folding the row's values into the running column sums of its chunk (fused BatchNorm statistics; warp-uniform branch).
+__device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float rv, float* wstat32,
+                                                int width, int lane) {
+    float v[32];
+    conv_epilogue_values(p, acc, pos, ch0, v, rv);
+    conv_epilogue_store(p, v, pos, ch0);
+    if (p.stats) stat_add(wstat32, width, v, lane);
+}
+
+// Same with the direct global-memory form of the statistics.
+__device__ __forceinline__ void conv_epilogue32_stats(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0, float rv, int lane) {
+    float v[32];
+    conv_epilogue_values(p, acc, pos, ch0, v, rv);
+    conv_epilogue_store(p, v, pos, ch0);
+    if (p.stats) stat_add_global(p, v, ch0, lane);
 }
 
 __device__ __forceinline__ void conv_epilogue32(const ConvParams& p, const uint32_t (&acc)[32], size_t pos, int ch0) {

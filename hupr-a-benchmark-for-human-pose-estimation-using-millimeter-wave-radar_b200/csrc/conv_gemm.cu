@@ -237,6 +237,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const uint32_t (&acc)[32] = accs[k];
                     float v[32];
                     conv_epilogue_values(p, acc, pos, n0 + c * 32, v, rv);
+                    if (p.stats) stat_add_global(p, v, n0 + c * 32, lane);
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
@@ -321,7 +322,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         uint32_t acc[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
-                        conv_epilogue32(p, acc, pos, n0 + c * 32, rv);
+                        conv_epilogue32_stats(p, acc, pos, n0 + c * 32, rv, lane);
                     }
                     if (lane == 0) p.coop_counters[(tile * 4 + q) * 2 + half] = 0;
                 }
@@ -335,7 +336,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tc_fence_before();
             mbar_arrive(&accum_empty[as]);
 #pragma unroll
-            for (int k = 0; k < BN / 64; ++k) conv_epilogue32(p, accs[k], pos, n0 + (c_begin + k) * 32, rv);
+            for (int k = 0; k < BN / 64; ++k) conv_epilogue32_stats(p, accs[k], pos, n0 + (c_begin + k) * 32, rv, lane);
         }
         if (TSTORE && warp == 2 && lane == 0) tma_store_wait_all();      // the CTA's last stores are complete before its smem goes away
     }
@@ -482,6 +483,8 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     p.o_f32 = d->o_f32; p.o_f32_ld = d->o_f32_ld;
     p.w_k_off = d->w_k_off;
     p.row_vec = d->row_vec; p.row_mode = d->row_vec ? d->row_mode : 0;
+    p.stats = d->stats; p.stats_ld = d->stats_ld;
+    if (d->stats && (d->stats_ld < d->cout || d->k_split > 1 || ((uintptr_t)d->stats & 7))) return HUPR_ERR_BAD_ARG;
     p.coop_ws = static_cast<float*>(d->ws); p.coop_ws_bytes = d->ws ? d->ws_bytes : 0; p.coop_counters = nullptr; p.coop = 0;
     if (d->ws && ((uintptr_t)d->ws & 15)) return HUPR_ERR_ALIGNMENT;
     if (p.row_mode < 0 || p.row_mode > 2 || (p.row_mode && (d->scale || d->shift || d->slope || !d->o_hi)) || (p.row_mode == 2 && !d->r_hi)) return HUPR_ERR_BAD_ARG;

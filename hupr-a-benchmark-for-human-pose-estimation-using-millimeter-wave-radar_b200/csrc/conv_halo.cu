@@ -28,6 +28,7 @@ namespace hupr {
 constexpr int HK = 32;             // channels per k-block (64-byte swizzled rows)
 constexpr int HM = 256;            // output positions per CTA
 constexpr int kHaloThreads = 192;
+constexpr int kHaloStatBytes = 4 * 2 * 128 * 4;      // per-warp running column sums of the fused BatchNorm statistics
 
 struct HaloGeom {
     int halo_rows;                 // (bh + 2) * bw
@@ -66,6 +67,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint64_t* accum_full = bars + 8;     // [2]
     uint64_t* accum_empty = bars + 10;   // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s_stat = reinterpret_cast<float*>(bars + 32);      // [4 epilogue warps][2][BN] running column sums (fused BatchNorm statistics)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -197,9 +199,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int lt = 0;
+        // fused BatchNorm statistics: this warp's running column sums (sum v, sum v^2 of channel n0 + col over all rows it has seen) live
+        // in shared memory, lane j owning columns j, j + 32, ...; a CTA's tiles come in non-decreasing n0 order, so the sums are flushed
+        // (double atomics) when n0 changes and at the end
+        float* wstat = s_stat + q * 2 * BN;
+        if (p.stats) {
+            for (int j = lane; j < 2 * BN; j += 32) wstat[j] = 0.f;
+        }
+        int st_n0 = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             int n0, n, od, h0;
             decode(tile, n0, n, od, h0);
+            if (p.stats && n0 != st_n0) {
+                if (st_n0 >= 0) stat_flush(p, wstat, BN, st_n0, lane);
+                st_n0 = n0;
+            }
             const int as = lt & 1;
             mbar_wait(&accum_full[as], (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
@@ -225,10 +239,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         tc_fence_before();
                         mbar_arrive(&accum_empty[as]);
                     }
-                    conv_epilogue32(p, acc, pos, n0 + c * 32);
+                    conv_epilogue32(p, acc, pos, n0 + c * 32, p.row_mode ? __ldg(p.row_vec + pos) : 0.f, wstat + c * 32, BN, lane);
                 }
             }
         }
+        if (p.stats && st_n0 >= 0) stat_flush(p, wstat, BN, st_n0, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -270,7 +285,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     static bool configured[kMaxDevices] = {};
     const int smem_max = 232448;
     if (int crc = ensure_smem_optin(conv_halo_kernel<BN, NPROD>, smem_max, configured)) return crc;
-    const int smem = g.stages * g.stage_bytes + 1024 + 256;
+    const int smem = g.stages * g.stage_bytes + 1024 + 256 + kHaloStatBytes;
     if (smem > smem_max) return HUPR_ERR_BAD_ARG;
     const int num_sms = device_sm_count();
     if (num_sms <= 0) return HUPR_ERR_CUDA;
@@ -312,7 +327,7 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     g.b_tile_bytes = bn * 64;
     g.nprod = three ? 3 : 1;
     g.stage_bytes = (three ? 2 : 1) * (g.a_plane_bytes + 3 * g.b_tile_bytes);
-    g.stages = (232448 - 1024 - 256) / g.stage_bytes;
+    g.stages = (232448 - 1024 - 256 - kHaloStatBytes) / g.stage_bytes;
     if (g.stages > 4) g.stages = 4;
     if (g.stages < 2) return 1;
     g.tap_stride_bytes = bw * 64;

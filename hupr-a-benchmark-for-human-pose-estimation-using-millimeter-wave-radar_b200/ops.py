@@ -159,7 +159,7 @@ def products(n):
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
               out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True, tma_store=True,
-              nprod=None, lcin=None, lcout=None, lrows=None):
+              nprod=None, lcin=None, lcout=None, lrows=None, stats=None):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -184,6 +184,10 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     if not tma_store or os.environ.get("HUPR_NO_TMA_STORE"):
         desc.no_tma_store = 1
     desc.nprod = _NPROD if nprod is None else nprod
+    if stats is not None:            # float64 [2, >= cout]: sum v and sum v^2 per output channel are ADDED (fused BatchNorm batch statistics)
+        if stats.dtype != torch.float64 or stats.dim() != 2 or stats.shape[0] != 2 or stats.stride(1) != 1:
+            raise TypeError("conv_gemm: stats must be a float64 [2, C] tensor")
+        desc.stats, desc.stats_ld = stats.data_ptr(), stats.stride(0)
     if k_split <= 1 and coop and _COOP_DEFAULT:     # small grids split their contraction cooperatively (deterministic ordered reduction)
         ws = coop_workspace(a.hi.device)
         desc.ws, desc.ws_bytes = ws.data_ptr(), ws.numel()

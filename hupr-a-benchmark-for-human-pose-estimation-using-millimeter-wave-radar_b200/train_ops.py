@@ -59,9 +59,9 @@ def accumulate(out, c, a=None, b=None, f=None, f_off=0):
 def bn_finalize(sums, count, gamma, beta, eps, momentum, running_mean=None, running_var=None, num_batches_tracked=None):
     """sums: float64 [2, c] (sum z, sum z^2) -> float32 [4, c] rows (mean, rstd, scale, shift); running statistics updated in place
     (hupr_bn_finalize: one launch for the whole per-channel bookkeeping of a train-mode BatchNorm)."""
-    c = sums.shape[1]
-    out = torch.empty((4, c), dtype=torch.float32, device=sums.device)
-    with torch.cuda.device(sums.device):
+    c = sums[0].shape[-1]
+    out = torch.empty((4, c), dtype=torch.float32, device=sums[0].device)
+    with torch.cuda.device(sums[0].device):
         _call("hupr_bn_finalize", _p(sums[0]), _p(sums[1]), int(count), _p(gamma), _p(beta), float(eps), float(momentum), _p(out[0]), _p(out[1]),
               _p(out[2]), _p(out[3]), _p(running_mean), _p(running_var), _p(num_batches_tracked), c, _C.stream_ptr())
     return out

@@ -32,6 +32,7 @@ from .ops import SplitTensor
 
 EPS = 1e-5
 MOMENTUM = 0.1
+FUSED_BN_STATS = os.environ.get("HUPR_FUSED_BN_STATS", "1") != "0"      # A/B switch: 0 = separate hupr_channel_sums passes
 
 
 # ------------------------------------------------------------------------------------------------------------------ scratch memory
@@ -211,17 +212,20 @@ class BNOp(object):
     def __init__(self, prefix, c):
         self.prefix, self.c = prefix, c
 
-    def forward_stats(self, z, z_off, params, buffers, count):
-        """Batch statistics of z[..., z_off:z_off+c]; updates running stats; returns (scale, shift) for the affine kernel."""
+    def forward_stats(self, z, z_off, params, buffers, count, sums=None):
+        """Batch statistics of z[..., z_off:z_off+c]; updates running stats; returns (scale, shift) for the affine kernel.
+        ``sums``: float64 [2, c] (sum z, sum z^2) already accumulated by the producing convolution's epilogue (hupr_conv_desc.stats);
+        None = one hupr_channel_sums pass over z."""
         dev = z.hi.device
-        sums = _zeros((2, self.c), torch.float64, dev)
-        T.channel_sums(T.SUMS_STATS, (z, z_off), self.c, sums[0], sums[1])
+        if sums is None:
+            sums = _zeros((2, self.c), torch.float64, dev)
+            T.channel_sums(T.SUMS_STATS, (z, z_off), self.c, sums[0], sums[1])
         gamma, beta = params[self.prefix + ".weight"].detach(), params[self.prefix + ".bias"].detach()
         rm, rv = buffers[self.prefix + ".running_mean"], buffers[self.prefix + ".running_var"]
         nbt = buffers[self.prefix + ".num_batches_tracked"]
         ok = all(t.dtype == torch.float32 and t.is_contiguous() for t in (gamma, beta, rm, rv)) and nbt.dtype == torch.int64
         if ok:      # one launch: mean, rstd, fused affine, running statistics (hupr_bn_finalize)
-            st = T.bn_finalize(sums, count, gamma, beta, EPS, MOMENTUM, rm, rv, nbt)
+            st = T.bn_finalize((sums[0], sums[1]), count, gamma, beta, EPS, MOMENTUM, rm, rv, nbt)
             self.mean, self.rstd, self.scale, self.shift = st[0], st[1], st[2], st[3]
             return self.scale, self.shift
         s1, s2 = sums[0], sums[1]          # parameters / buffers kept in another dtype (tests drive float64 state): same algebra in torch
@@ -267,13 +271,16 @@ class Block3D(object):
         if self.relu is None or self.relu.device != dev:
             self.relu = torch.zeros(c, dtype=torch.float32, device=dev)
         self.x = x
-        self.zc = self.conv1.forward(x, _S(shape + (2 * c,), dev))
-        s1, h1 = self.bn1.forward_stats(self.zc, 0, params, buffers, count)
-        sd_, hd = self.bnd.forward_stats(self.zc, c, params, buffers, count)
+        # the batch statistics of the three BatchNorms ride in the epilogues of the convolutions that produce their inputs
+        st1 = _zeros((2, 2 * c), torch.float64, dev) if FUSED_BN_STATS else None
+        self.zc = self.conv1.forward(x, _S(shape + (2 * c,), dev), stats=st1)
+        s1, h1 = self.bn1.forward_stats(self.zc, 0, params, buffers, count, sums=None if st1 is None else st1[:, :c])
+        sd_, hd = self.bnd.forward_stats(self.zc, c, params, buffers, count, sums=None if st1 is None else st1[:, c:])
         self.t = _S(shape + (c,), dev)
         T.affine_act((self.zc, 0), c, self.t, scale1=s1, shift1=h1, slope=self.relu)
-        self.z2 = self.conv2.forward(self.t, _S(shape + (c,), dev))
-        s2, h2 = self.bn2.forward_stats(self.z2, 0, params, buffers, count)
+        st2 = _zeros((2, c), torch.float64, dev) if FUSED_BN_STATS else None
+        self.z2 = self.conv2.forward(self.t, _S(shape + (c,), dev), stats=st2)
+        s2, h2 = self.bn2.forward_stats(self.z2, 0, params, buffers, count, sums=st2)
         self.out = _S(shape + (c,), dev)
         T.affine_act(self.z2, c, self.out, scale1=s2, shift1=h2, r=(self.zc, c), scale2=sd_, shift2=hd, slope=self.relu)
         self.count = count

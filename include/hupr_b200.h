@@ -108,6 +108,10 @@ typedef struct hupr_conv_desc {
     int nprod;                                                    /* tensor-core products per k-step: 0 = by operands (3 when the lo planes are given, else 1);
                                                                      1 = hi*hi only although lo planes exist (they are not read): plain bf16 compute with fp32
                                                                      accumulation, the precision BASELINE.json configs[3] names for training; 3 = require lo planes */
+    double* stats; int stats_ld;                                  /* optional: per-output-channel sums of the epilogue values over all positions, ADDED to
+                                                                     stats[co] (sum v) and stats[stats_ld + co] (sum v^2); zero-filled by the caller.  Fuses the
+                                                                     batch statistics of a train-mode nn.BatchNorm3d (/root/reference/models/layers.py:45-53)
+                                                                     into the convolution that produces its input */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);

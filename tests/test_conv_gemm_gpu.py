@@ -244,3 +244,38 @@ def test_single_product_mode_on_split_tensors_equals_bf16_operand_reference(shap
     assert rel_err(got, ref) < 2e-5
     full = F.conv3d(x.double(), wt.double(), padding=pad).float()
     assert 1e-4 < rel_err(got, full) < 3e-2               # and it IS the single-product result, not the 3-product one
+
+
+@pytest.mark.parametrize("shape,products", [
+    ((8, 64, 128, 4, 32, 32, (3, 3, 3), (1, 1, 1)), 3),      # halo-reuse kernel, BN = 128
+    ((3, 64, 64, 8, 64, 64, (3, 3, 3), (1, 1, 1)), 3),       # halo-reuse kernel, BN = 64 ([w_hi | w_lo] operand, two accumulator halves)
+    ((32, 128, 256, 2, 16, 16, (3, 3, 3), (1, 1, 1)), 1),    # halo-reuse kernel, two column tiles per CTA walk, single product
+    ((1, 128, 256, 2, 16, 16, (3, 3, 3), (1, 1, 1)), 3),     # generic kernel, cooperative split-K (the last-arriving slice reduces)
+    ((2, 64, 64, 8, 64, 64, (8, 1, 1), (0, 0, 0)), 3),       # generic kernel, plain epilogue
+    ((8, 128, 128, 1, 128, 128, (1, 1, 1), (0, 0, 0)), 3),   # generic kernel, TMA-store epilogue
+])
+def test_fused_channel_statistics_match_a_pass_over_the_output(shape, products):
+    """hupr_conv_desc.stats: per-output-channel sum v and sum v^2 accumulated in the convolution's epilogue (train-mode BatchNorm batch
+    statistics, /root/reference/models/layers.py:45-53) against sums over the stored output; 2e-5 relative (fp32 partial sums per warp /
+    CTA, float64 across CTAs)."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor, conv_gemm
+    n, cin, cout, d, h, w, kernel, pad = shape
+    torch.manual_seed(9)
+    x = torch.randn(n, cin, d, h, w, device="cuda") + 0.3
+    wt = torch.randn(cout, cin, *kernel, device="cuda") / (cin * kernel[0] * kernel[1] * kernel[2]) ** 0.5
+    A = SplitTensor.from_float(to_cl(x, cin))
+    W = pack_weight(wt, cin, cout)
+    d_out = d + 2 * pad[0] - kernel[0] + 1
+    out = SplitTensor.empty((n, d_out, h, w, cout), "cuda")
+    stats = torch.zeros((2, cout + 64), dtype=torch.float64, device="cuda")      # wider than cout: stats_ld is a stride
+    stats[:, cout:] = 5.0
+    with ops.products(products):
+        conv_gemm(A, cin, W, cout, kernel=kernel, pad=pad, out=out, stats=stats)
+        conv_gemm(A, cin, W, cout, kernel=kernel, pad=pad, out=out, stats=stats)      # sums are ADDED: a second launch doubles them
+    torch.cuda.synchronize()
+    y = out.float().double().reshape(-1, cout)
+    ref1, ref2 = 2 * y.sum(0), 2 * (y * y).sum(0)
+    assert float((stats[0, :cout] - ref1).abs().max() / ref1.abs().max()) < 2e-5
+    assert float((stats[1, :cout] - ref2).abs().max() / ref2.abs().max()) < 2e-5
+    assert bool((stats[:, cout:] == 5.0).all())
