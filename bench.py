@@ -391,6 +391,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="e2e: poses (windows) per GPU per step (default 32); train: samples per GPU (default 32 = the per-GPU shard of configs[3])")
     ap.add_argument("--frames-per-step", type=int, default=1024, help="cascade: radar frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ingest", default="adc", choices=["adc", "vrdae"],
+                    help="train e2e leg: host buffers hold raw int16 ADC words (cascade + standardisation on the device, default) or float32 VRDAE maps")
     ap.add_argument("--no-train-probe", action="store_true", help="multi-rank e2e runs: skip the data-parallel training probe record")
     ap.add_argument("--single-bf16", action="store_true", help="one bf16 product per k-step instead of the fp32-equivalent 3-product split")
     args = ap.parse_args()
@@ -484,17 +486,28 @@ def main():
                 trainer.optimizer_step()
             return out
 
-        trainer.prefetch(h_h, h_v, h_j)
+        if args.ingest == "adc":
+            # compact ingest: raw int16 DCA1000 words of each sample's 8-frame window (12.6 MB per sample); FFT cascade + standardisation on the device
+            h_ah = torch.randint(-2048, 2048, (units, 8, FRAME_WORDS), dtype=torch.int16).pin_memory()
+            h_av = torch.randint(-2048, 2048, (units, 8, FRAME_WORDS), dtype=torch.int16).pin_memory()
+            upload = lambda: trainer.prefetch_adc(h_ah, h_av, h_j)
+            take = lambda: trainer.take_prefetched_adc(hori, vert, joints)
+            h2d = 2 * h_ah.numel() * 2 + h_j.numel() * 8
+        else:
+            upload = lambda: trainer.prefetch(h_h, h_v, h_j)
+            take = lambda: trainer.take_prefetched(hori, vert, joints)
+            h2d = 2 * h_h.numel() * 4 + h_j.numel() * 8
+        upload()
 
         def e2e_step():
             # public ingest API: the upload of the NEXT batch (copy stream, pinned host tensors) overlaps this step's compute; every step
             # still moves its own inputs host->device and its two loss scalars device->host inside the timed region
-            trainer.take_prefetched(hori, vert, joints)
-            trainer.prefetch(h_h, h_v, h_j)
+            take()
+            upload()
             l, l2 = step()
             h_loss[0:1].copy_(l.reshape(1), non_blocking=True)
             h_loss[1:2].copy_(l2.reshape(1), non_blocking=True)
-        e2e_units, h2d, d2h = units, 2 * h_h.numel() * 4 + h_j.numel() * 8, 8
+        e2e_units, d2h = units, 8
         profile_step = lambda: trainer.forward_backward(hori, vert, joints)
         l2_note = "per-step working set (saved activations + gradients, tens of GB) exceeds the 126 MB L2"
         dtype = ("bf16 tensor-core products, fp32 accumulate, in every convolution / data-gradient / weight-gradient launch (attention and "
@@ -615,7 +628,12 @@ def main():
         conv = fam["conv_gemm"]
         achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        # DRAM traffic of the family's dominant kernel from its ncu --set full capture (profiles/r01_halo128_persist_metrics.csv: ONE
+        # conv_halo_kernel<128,3> launch, 64 -> 128 channels, batch 32): 269.7 MB read + 484.2 MB written against 269.3 MB of input + weights
+        # and 536.9 MB of output — no DRAM re-reads: the 27-tap operand re-reads are served by L2 (part of the output is still in L2 at exit)
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": 269696256.0 + 484221184.0, "traffic_algorithmic_bytes": 269317120.0 + 536870912.0,
+                    "traffic_of": "one conv_halo_kernel<128,3> launch (64->128 channels, 3x3x3, batch 32), ncu dram__bytes_read.sum + dram__bytes_write.sum",
                     "kernel": "hupr::conv_gemm_kernel (all %d launches of one step; FLOPs = 2 x MACs of the fp32 contraction — the "
                               "tensor pipe executes %dx that)" % (conv["launch_calls"], 1 if args.single_bf16 else 3),
                     "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "algorithmic_flops_per_step": conv["flops"],
@@ -657,7 +675,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic (seeded random int16 ADC words; random-init weights of the reference architecture)",
-            "config": {"workload": WORKLOADS[args.workload], "units_per_gpu_per_step": units, "l2": l2_note,
+            "config": {"workload": WORKLOADS[args.workload] + ((" [e2e ingest: %s]" % args.ingest) if args.workload == "train" else ""),
+                       "units_per_gpu_per_step": units, "l2": l2_note,
                        "parallelism": ("data parallel: samples sharded across ranks, one NCCL sum all-reduce over the flat fp32 gradient buffer per step"
                                        if args.workload == "train" else "frames sharded across ranks, no collective")},
             "roofline": roofline, "cpu_baseline": cpu,

@@ -898,6 +898,43 @@ class TrainStep(object):
             st["joints"].copy_(joints, non_blocking=True)
             st["uploaded"].record(st["stream"])
 
+    def prefetch_adc(self, adc_hori, adc_vert, joints):
+        """Compact ingest: upload the NEXT batch as raw DCA1000 words — int16 ``[B, 8, FRAME_WORDS]`` per sensor (the eight frames of each
+        sample's window; pinned host tensors), 12.6 MB per sample instead of the 32 MiB of float32 VRDAE maps — on the copy stream.
+        ``take_prefetched_adc`` then runs the FFT cascade and the window standardisation on the device (what
+        preprocessing/process_iwr1843.py:106-173 and datasets/dataset.py:139-150 do on the host in the reference)."""
+        from .preprocessing.process_iwr1843 import FRAME_WORDS
+        dev = self.device
+        b, g = adc_hori.shape[0], adc_hori.shape[1]
+        st = getattr(self, "_ingest_adc", None)
+        if st is None or st["adc"].shape[1] != b * g:
+            st = self._ingest_adc = dict(adc=torch.empty((2, b * g, FRAME_WORDS), dtype=torch.int16, device=dev),
+                                         cubes=torch.empty((2 * b * g, 16, 64, 64, 8), dtype=torch.complex64, device=dev),
+                                         slots=[torch.arange(b * g, dtype=torch.int32, device=dev),
+                                                torch.arange(b * g, 2 * b * g, dtype=torch.int32, device=dev)],
+                                         joints=torch.empty(joints.shape, dtype=torch.int64, device=dev),
+                                         stream=torch.cuda.Stream(device=dev), uploaded=torch.cuda.Event(), consumed=torch.cuda.Event())
+            st["consumed"].record(torch.cuda.current_stream(dev))
+        st["stream"].wait_event(st["consumed"])
+        with torch.cuda.stream(st["stream"]):
+            st["adc"][0].copy_(adc_hori.view(b * g, FRAME_WORDS), non_blocking=True)
+            st["adc"][1].copy_(adc_vert.view(b * g, FRAME_WORDS), non_blocking=True)
+            st["joints"].copy_(joints, non_blocking=True)
+            st["uploaded"].record(st["stream"])
+
+    def take_prefetched_adc(self, hori, vert, joints):
+        """FFT cascade + window standardisation of the batch uploaded by ``prefetch_adc`` into the step's static VRDAE input tensors."""
+        from .preprocessing.process_iwr1843 import FRAME_WORDS, cascade_i16
+        st = self._ingest_adc
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(st["uploaded"])
+        n = st["adc"].shape[1]
+        cascade_i16(st["adc"].view(2 * n, FRAME_WORDS), st["cubes"])
+        joints.copy_(st["joints"], non_blocking=True)
+        st["consumed"].record(main)                       # the staging words are consumed; the cubes are this stream's own scratch
+        ops.window_normalize(st["cubes"], st["slots"][0], hori.view(n, 8, 2, 64, 64, 8))
+        ops.window_normalize(st["cubes"], st["slots"][1], vert.view(n, 8, 2, 64, 64, 8))
+
     def take_prefetched(self, hori, vert, joints):
         """Move the batch uploaded by the last ``prefetch`` into the step's static input tensors (device-to-device, stream-ordered)."""
         st = self._ingest

@@ -102,5 +102,9 @@ def test_two_rank_nccl_training_gradients_equal_oracle_shard_mean(tmp_path):
             continue                                   # 1-element PReLU slopes: cancellation-dominated sums (checked in absolute terms on one GPU)
         assert l2 < 0.06 and cos > 0.998, (name, l2, cos)          # a handful of activation-mask flips at most (test_training_step_gpu.py)
     assert sorted(e for e, _, _ in errs)[len(errs) // 2] < 5e-3
-    tail = [e for e, _, n in errs if "gcn.L3" in n or "decoderLayer1.2" in n]       # no ReLU / PReLU / max-pool kink between these and the loss
-    assert len(tail) == 3 and max(tail) < 2e-4, tail
+    # no ReLU / PReLU / max-pool kink lies between the last GCN layer and the loss (the head convolution does see the GCN's ReLU masks:
+    # its output gradient is the direct sigmoid path PLUS the path through the three GCN layers — measured 3.4e-4 with one flip)
+    tail = [e for e, _, n in errs if "gcn.L3" in n]
+    assert len(tail) == 2 and max(tail) < 2e-4, tail
+    head = [e for e, _, n in errs if "decoderLayer1.2" in n]
+    assert len(head) == 1 and head[0] < 2e-3, head

@@ -90,3 +90,37 @@ def test_loader_items_identical_from_cube_and_plane_caches(tmp_path):
     for a, b in zip(*items):
         assert torch.equal(a["VRDAEmap_hori"], b["VRDAEmap_hori"]) and torch.equal(a["VRDAEmap_vert"], b["VRDAEmap_vert"])
         assert a["imageId"] == b["imageId"]
+
+
+def test_training_adc_ingest_equals_oracle_cascade_and_loader():
+    """TrainStep.prefetch_adc / take_prefetched_adc: pinned int16 DCA1000 words of a sample's 8-frame window -> copy stream -> FFT cascade ->
+    window standardisation -> the step's float32 VRDAE inputs.  Against the oracle chain (complex128 cascade restatement + fp64 Normalize,
+    process_iwr1843.py:106-173 + datasets/base.py:13-24) on the signal chirp slots; slot 4 is the Doppler-0 round-off plane (unit variance
+    by construction, checked as such)."""
+    import numpy as np
+    import torch
+    from hupr_b200.models import HuPRNet
+    from hupr_b200.training import TrainStep
+    from oracle import cascade, loader
+    from oracle import model as om
+    from tests.test_model_gpu import make_cfg
+    net = HuPRNet(make_cfg())
+    net.load_state_dict(om.make_state_dict(0))
+    step = TrainStep(net.cuda().train())
+    frames = {s: [cascade.synth_frame(f, s) for f in range(8)] for s in (0, 1)}
+    words = {s: torch.from_numpy(np.stack([cascade.complex_to_dca1000(f) for f in frames[s]])[None]).pin_memory() for s in (0, 1)}
+    joints = torch.randint(0, 256, (1, 14, 2)).pin_memory()
+    hori = torch.empty((1, 8, 8, 2, 64, 64, 8), device="cuda")
+    vert = torch.empty_like(hori)
+    jd = torch.empty((1, 14, 2), dtype=torch.int64, device="cuda")
+    step.prefetch_adc(words[0], words[1], joints)
+    step.take_prefetched_adc(hori, vert, jd)
+    torch.cuda.synchronize()
+    assert torch.equal(jd.cpu(), joints)
+    signal = [c for c in range(8) if c != 4]
+    for s, got in ((0, hori), (1, vert)):
+        ref = loader.vrdae_from_cubes([cascade.generate_heatmap(f) for f in frames[s]])
+        g = got[0].cpu().numpy()
+        assert float(np.abs(g[:, signal] - ref[:, signal]).max()) < 2e-3
+        noise = g[:, 4]
+        assert np.isfinite(noise).all() and abs(float(noise.std()) - 1.0) < 0.05
