@@ -167,6 +167,13 @@ class HuPRNet(nn.Module):
         self._train_step = None      # parameter storage was replaced: a TrainStep's flat views are stale
         return out
 
+    def __getstate__(self):
+        """Pickling / deepcopy keep parameters and buffers only: packed operands, launch plans and the training step hold device scratch,
+        streams and raw-pointer tables that belong to this process."""
+        state = self.__dict__.copy()
+        state["_packed"], state["_plans"], state["_train_step"] = None, {}, None
+        return state
+
     def invalidate(self):
         """Drop the packed (kernel-format) weights and cached launch plans; call after mutating parameters in place."""
         self._packed = None

@@ -66,8 +66,10 @@ class ZeroArena(object):
             self.sizes.append(aligned)
             return ops.zeros(tuple(shape), dtype, self.device)
         if self.cursor >= len(self.sizes) or self.sizes[self.cursor] != aligned:
+            cursor = self.cursor
+            self.buf, self.sizes = None, []          # forget the plan: the next pass plans again instead of failing forever
             raise RuntimeError("hupr_b200.training: the step's scratch request sequence changed between passes (request %d: %d bytes)"
-                               % (self.cursor, aligned))
+                               % (cursor, aligned))
         t = self.buf[self.offset:self.offset + n].view(dtype).view(tuple(shape))
         self.cursor += 1
         self.offset += aligned
@@ -621,6 +623,10 @@ class TrainStep(object):
         """Operand layouts of every contraction from the flat fp32 parameters — library launches only (hupr_pack_conv_weights,
         hupr_broadcast_f32), so a captured step re-packs after its own Adam launch without any framework kernel."""
         sd = {k: v.data for k, v in self.model.named_parameters()}
+        for name in ("RAchirpNet.temporalConvWx1x1.weight", "radarDecoder.gcn.L3.bias"):      # first and a late parameter of the flat buffer
+            if sd[name].data_ptr() != self.flat_p.data_ptr() + 4 * self.offsets[name]:
+                raise RuntimeError("hupr_b200.training: the model's parameter storage was replaced after this TrainStep was built "
+                                   "(model.to() / .float() / load into new tensors): build a new TrainStep")
         p = "radarDecoder."
         if self._pack_table is None:
             # ONE launch re-packs all 84 convolution filters and the three GCN matrices (hupr_pack_conv_weights_multi): the table holds raw
