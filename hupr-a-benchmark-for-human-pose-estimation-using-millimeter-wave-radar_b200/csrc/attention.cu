@@ -120,7 +120,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer: K ring and V ring are independent (K_j is free as soon as Q K_j^T retires) =================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, 2 * Cfg::kQPlane);
 #pragma unroll
             for (int a = 0; a < D / 64; ++a) {
@@ -150,7 +150,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread): Q K^T runs two key blocks ahead of P V =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
             const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
             const uint32_t sQ = smem_u32(smem + Cfg::kSmQ), sP = smem_u32(smem + Cfg::kSmP);

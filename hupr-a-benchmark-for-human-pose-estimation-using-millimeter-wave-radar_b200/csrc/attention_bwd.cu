@@ -116,7 +116,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_co
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 4 * AB_PLANE);
             tma_load_3d(smem + AB_SM_K, &tmK_hi, kv_full, p.k_off, k0, b);
             tma_load_3d(smem + AB_SM_K + AB_PLANE, &tmK_lo, kv_full, p.k_off, k0, b);
@@ -136,7 +136,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_co
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (elect_one()) {
             // D = f32, A = B = bf16; N, M = 128.  bit 15: A MN-major, bit 16: B MN-major
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_ts = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AB_D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -348,7 +348,7 @@ attention_bwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ_hi, const __grid
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 4 * AB_PLANE);
             tma_load_3d(smem + AB_SM_K, &tmK_hi, kv_full, p.k_off, k0, b);
             tma_load_3d(smem + AB_SM_K + AB_PLANE, &tmK_lo, kv_full, p.k_off, k0, b);
@@ -370,7 +370,7 @@ attention_bwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ_hi, const __grid
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (elect_one()) {
             // D = f32, A = B = bf16, M = 128.  bit 15: A MN-major, bit 16: B MN-major
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A2_BQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_ts = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AB_D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -123,7 +123,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 int kb_begin, kb_end, n0, n, od, h0, w0;
@@ -159,7 +159,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int it = 0, li = 0;

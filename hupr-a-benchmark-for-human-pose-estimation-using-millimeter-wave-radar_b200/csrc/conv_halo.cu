@@ -112,7 +112,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0, sidx = 0;
             uint32_t sph = 0;                              // stage ring position / phase, advanced without divisions
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -145,7 +145,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 128
             int it = 0, lt = 0, sidx = 0;

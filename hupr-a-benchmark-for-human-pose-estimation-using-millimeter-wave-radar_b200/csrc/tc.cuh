@@ -8,6 +8,22 @@
 namespace hupr {
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
+// One elected lane of a CONVERGED warp (elect.sync).  The single-thread roles (TMA producer, tcgen05.mma issuer) are entered through
+// `if (elect_one())` rather than `if (lane == 0)`: tcgen05.mma / cp.async.bulk.tensor / tcgen05.commit are uniform-datapath instructions,
+// and under a plain lane test the compiler wraps EVERY one of them in a warp-serialisation loop (PLOP3 / ELECT / BRA.U.ANY — 737 such
+// loops in the round-1 library), which made the 32-cycle N = 64 MMAs issue-bound (~100 cycles per issue).  With the election it emits
+// the instruction directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(

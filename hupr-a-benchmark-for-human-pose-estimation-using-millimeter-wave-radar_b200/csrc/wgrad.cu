@@ -123,7 +123,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             // The CTA's atoms (filter tap, 64-channel block) do not depend on the K block: decode them once (the integer divisions of
             // the decode were ~250 cycles per stage against 128..384 tensor cycles of work per stage) ...
             for (int j = 0; j < 2 * nslots; ++j) {
@@ -177,7 +177,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (elect_one()) {
             // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
