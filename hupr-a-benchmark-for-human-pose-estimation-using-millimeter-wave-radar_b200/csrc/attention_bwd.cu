@@ -450,14 +450,24 @@ attention_bwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ_hi, const __grid
         const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
         const float kLog2e = 1.4426950408889634f;
         const uint32_t xr = (uint32_t)(row & 7);
+        // dQ of a pair (lanes = its 128 query rows) -> global: this warp adds 32 of the 64 channels of its 32 rows
+        auto dq_epilogue = [&](int pair) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + A2_T_DQ + (uint32_t)(half * 32) + lane_sel, acc);
+            float* dst = p.dq + ((size_t)b * p.s + (size_t)pair * 128 + row) * p.dq_ld + p.dq_off + half * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                ab_red_add_v4(dst + 4 * g, __uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]), __uint_as_float(acc[4 * g + 2]),
+                              __uint_as_float(acc[4 * g + 3]));
+            tc_fence_before();
+        };
         for (int s = 0; s < nsub; ++s) {
             const int bf = s & 1;
             const uint32_t par = (uint32_t)((s >> 1) & 1);
             mbar_wait(&qd_full[bf], par);                                   // lse_s / rowdot_s are in shared memory
             mbar_wait(&s_full[bf], par);
             tc_fence_after();
-            const float* v_lse = s_vec + bf * 2 * A2_BQ + half * 32;
-            const float* v_rd = v_lse + A2_BQ;
+            const uint32_t v_lse = smem_u32(s_vec + bf * 2 * A2_BQ + half * 32), v_rd = v_lse + A2_BQ * 4;
             const uint32_t ts = tmem_base + A2_T_S + (uint32_t)(bf * A2_BQ + half * 32) + lane_sel;
             const uint32_t td = tmem_base + A2_T_DP + (uint32_t)(bf * A2_BQ + half * 32) + lane_sel;
             // dS^T tile of the pair: atom (s & 1) = this sub-block's 64 queries, [128 key rows][128 B], hi planes then lo planes
@@ -469,15 +479,25 @@ attention_bwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ_hi, const __grid
             tmem_ld_wait();
             uint32_t ph[16], pl[16], sh[16], sl[16];                        // packed bf16 pairs: 32 queries -> 16 columns per plane
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float la = v_lse[2 * j] * kLog2e, lb = v_lse[2 * j + 1] * kLog2e;
-                float pa, pb;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pa) : "f"(fmaf(__uint_as_float(sv[2 * j]), kLog2e, -la)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pb) : "f"(fmaf(__uint_as_float(sv[2 * j + 1]), kLog2e, -lb)));
-                const float da = pa * (__uint_as_float(dv[2 * j]) - v_rd[2 * j]);
-                const float db = pb * (__uint_as_float(dv[2 * j + 1]) - v_rd[2 * j + 1]);
-                split2(pa, pb, ph[j], pl[j]);
-                split2(da, db, sh[j], sl[j]);
+            for (int j4 = 0; j4 < 8; ++j4) {                                // four queries per step: one 16-byte read of lse and of rowdot
+                const float4 l4 = lds_f4(v_lse + j4 * 16), r4 = lds_f4(v_rd + j4 * 16);
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+                float pv[4], dsv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(sv[4 * j4 + e]), kLog2e, -ls[e] * kLog2e)));
+                    dsv[e] = pv[e] * (__uint_as_float(dv[4 * j4 + e]) - rs[e]);
+                }
+                split2(pv[0], pv[1], ph[2 * j4], pl[2 * j4]);
+                split2(pv[2], pv[3], ph[2 * j4 + 1], pl[2 * j4 + 1]);
+                split2(dsv[0], dsv[1], sh[2 * j4], sl[2 * j4]);
+                split2(dsv[2], dsv[3], sh[2 * j4 + 1], sl[2 * j4 + 1]);
+            }
+            // The dS^T atoms of the previous pair are read by its dQ MMA: its completion (dq_full) is awaited only HERE, after this
+            // sub-block's loads and arithmetic, so that MMA runs while the element-wise work of the next sub-block is under way.
+            if (s >= 2 && !(s & 1)) {
+                mbar_wait(dq_full, (uint32_t)(((s >> 1) - 1) & 1));
+                tc_fence_after();
             }
             // dS^T -> shared memory (MN-major A operand of dQ = dS K): 32 queries = 4 chunks of 16 B per plane, 128B-swizzled by key row
 #pragma unroll
@@ -489,27 +509,17 @@ attention_bwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ_hi, const __grid
                              "r"(sl[4 * g + 3]) : "memory");
             }
             // P^T and dS^T packed, in place over the chunk's own S^T / dP^T columns: hi at [0, 16), lo at [16, 32) of the chunk
-            tmem_st16(ts, ph);
-            tmem_st16(ts + 16, pl);
-            tmem_st16(td, sh);
-            tmem_st16(td + 16, sl);
+            tmem_st32_halves_nowait(ts, ph, pl);
+            tmem_st32_halves_nowait(td, sh, sl);
+            tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&p_full[bf]);
-            if (s & 1) {
-                // dQ of the pair (lanes = its 128 query rows) -> global: this warp adds 32 of the 64 channels of its 32 rows
-                mbar_wait(dq_full, (uint32_t)((s >> 1) & 1));
-                tc_fence_after();
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + A2_T_DQ + (uint32_t)(half * 32) + lane_sel, acc);
-                float* dst = p.dq + ((size_t)b * p.s + (size_t)(s >> 1) * 128 + row) * p.dq_ld + p.dq_off + half * 32;
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    ab_red_add_v4(dst + 4 * g, __uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]), __uint_as_float(acc[4 * g + 2]),
-                                  __uint_as_float(acc[4 * g + 3]));
-                tc_fence_before();
-            }
+            if (s >= 2 && !(s & 1)) dq_epilogue((s >> 1) - 1);              // the previous pair's dQ (its MMA completed: awaited above)
         }
+        mbar_wait(dq_full, (uint32_t)(((nsub >> 1) - 1) & 1));              // last pair
+        tc_fence_after();
+        dq_epilogue((nsub >> 1) - 1);
         // dV_j, dK_j (lanes = key rows) -> global: every MMA has retired once the last pair's dq_full completed (waited above)
         {
             uint32_t acc[32];

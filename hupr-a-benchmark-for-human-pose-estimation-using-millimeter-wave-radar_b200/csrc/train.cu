@@ -36,6 +36,27 @@ __device__ __forceinline__ void tv_store8(const TViewOut& t, size_t pos, int ch,
     store8(t.hi + o, t.lo ? t.lo + o : nullptr, v);
 }
 
+// Raw (undecoded) 8-channel load: both planes are requested back to back with no control flow in between, so a caller can put the loads
+// of several tensors / positions in flight before the first conversion (tv_load8's `if (lo)` splits the basic block and the compiler
+// then keeps one load pair in flight per thread: channel_sums measured 0.40 of the HBM peak that way, ncu r02_chsums).
+struct Raw8 { uint4 h, l; };
+__device__ __forceinline__ Raw8 tv_raw8(const TView& t, size_t pos, int ch) {
+    const size_t o = pos * t.ld + t.off + ch;
+    Raw8 r;
+    r.h = __ldg(reinterpret_cast<const uint4*>(t.hi + o));
+    r.l = __ldg(reinterpret_cast<const uint4*>((t.lo ? t.lo : t.hi) + o));      // single-plane tensors: a harmless second read of hi, masked below
+    if (!t.lo) r.l = make_uint4(0u, 0u, 0u, 0u);
+    return r;
+}
+__device__ __forceinline__ void raw_decode8(const Raw8& r, float (&v)[8]) {
+    const uint32_t hw[4] = {r.h.x, r.h.y, r.h.z, r.h.w}, lw[4] = {r.l.x, r.l.y, r.l.z, r.l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = bf16_lo_f(hw[i]) + bf16_lo_f(lw[i]);
+        v[2 * i + 1] = bf16_hi_f(hw[i]) + bf16_hi_f(lw[i]);
+    }
+}
+
 enum { SUMS_STATS = 0, SUMS_BN_BWD = 1, SUMS_PRELU = 2 };
 
 // grid.x CTAs of 256 threads; thread = (channel group of 8, position lane); each CTA walks a strided range of positions and
@@ -80,21 +101,26 @@ channel_sums_kernel(TView a, TView b, TView m, const float* __restrict__ mean, c
                 for (int i = 0; i < 8; ++i) acc2[i] += x[i];
             }
         };
-        auto load = [&](long long q, float (&x)[8], float (&y)[8], float (&k)[8]) {
-            tv_load8(a, (size_t)q, cg * 8, x);
-            if (MODE != SUMS_STATS && b.hi) tv_load8(b, (size_t)q, cg * 8, y);
-            if (MODE == SUMS_BN_BWD && m.hi) tv_load8(m, (size_t)q, cg * 8, k);
-        };
+        const bool has_b = (MODE != SUMS_STATS) && b.hi != nullptr, has_m = (MODE == SUMS_BN_BWD) && m.hi != nullptr;
+        const TView& vb = has_b ? b : a;                   // absent operands alias `a`: the loads stay unconditional, the values unused
+        const TView& vm = has_m ? m : a;
         for (; pos + stride < positions; pos += 2 * stride) {
+            // all twelve 16-byte loads of the two positions are in flight before the first conversion
+            const Raw8 ra0 = tv_raw8(a, (size_t)pos, cg * 8), ra1 = tv_raw8(a, (size_t)(pos + stride), cg * 8);
+            Raw8 rb0 = ra0, rb1 = ra1, rm0 = ra0, rm1 = ra1;
+            if (MODE != SUMS_STATS) { rb0 = tv_raw8(vb, (size_t)pos, cg * 8); rb1 = tv_raw8(vb, (size_t)(pos + stride), cg * 8); }
+            if (MODE == SUMS_BN_BWD) { rm0 = tv_raw8(vm, (size_t)pos, cg * 8); rm1 = tv_raw8(vm, (size_t)(pos + stride), cg * 8); }
             float x0[8], y0[8], k0[8], x1[8], y1[8], k1[8];
-            load(pos, x0, y0, k0);
-            load(pos + stride, x1, y1, k1);
+            raw_decode8(ra0, x0); raw_decode8(rb0, y0); raw_decode8(rm0, k0);
+            raw_decode8(ra1, x1); raw_decode8(rb1, y1); raw_decode8(rm1, k1);
             accumulate(x0, y0, k0);
             accumulate(x1, y1, k1);
         }
         if (pos < positions) {
             float x0[8], y0[8], k0[8];
-            load(pos, x0, y0, k0);
+            raw_decode8(tv_raw8(a, (size_t)pos, cg * 8), x0);
+            raw_decode8(tv_raw8(vb, (size_t)pos, cg * 8), y0);
+            raw_decode8(tv_raw8(vm, (size_t)pos, cg * 8), k0);
             accumulate(x0, y0, k0);
         }
     }

@@ -74,3 +74,28 @@ def test_gt_annotation_and_dataset_bookkeeping(tmp_path):
     assert ds.annots[5]["imageId"] == 900002 and ds.annots[5]["joints"].shape == (14, 2)
     with pytest.raises(ValueError):
         HuPR3D_horivert("training", cfg, types.SimpleNamespace(sampling_ratio=1))
+
+
+def test_pack_table_layout_of_the_batched_pack_launch():
+    """ops.PackTable (host logic of hupr_pack_conv_weights_multi / hupr_unpack_wgrad_multi): CTA ranges of the jobs tile the grid without
+    gaps, block_job names the owning job of every CTA, and the serialised jobs are the C struct's bytes."""
+    import ctypes
+
+    import torch
+    from hupr_b200 import _C, ops
+    jobs = [(0x1000, 0x2000, 0x3000, 0x4000, 0x5000, 64, 32, 27, 64, 64, 0),
+            (0x6000, 0x7000, 0x8000, 0, 0, 14, 32, 1, 64, 64, 0),
+            (0x9000, 0xa000, 0xb000, 0xc000, 0xd000, 128, 128, 9, 256, 128, 128)]
+    t = ops.PackTable(jobs, torch.device("cpu"))
+    blocks = [(-(-j[5] // 16)) * (-(-j[6] // 16)) for j in jobs]
+    assert t.total_blocks == sum(blocks) and t.max_taps == 27
+    assert t.block_job.tolist() == [0] * blocks[0] + [1] * blocks[1] + [2] * blocks[2]
+    raw = bytes(t.jobs.numpy().tobytes())
+    assert len(raw) == 3 * ctypes.sizeof(_C.PackJob)
+    arr = (_C.PackJob * 3).from_buffer_copy(raw)
+    assert [a.block_begin for a in arr] == [0, blocks[0], blocks[0] + blocks[1]]
+    assert [(a.cout, a.cin, a.taps, a.cout_total, a.cin_pad, a.cout_off) for a in arr] == [j[5:] for j in jobs]
+    assert arr[1].b_hi is None and arr[2].w == 0x9000
+    import pytest
+    with pytest.raises(ValueError):
+        ops.PackTable([(1, 2, 3, 4, 5, 63, 32, 27, 64, 64, 0)], torch.device("cpu"))       # odd cout: bf16 pairs
