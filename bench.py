@@ -231,9 +231,11 @@ def run_reference_arm(args):
 def summarise_profile(rec):
     fam = {}
     for name, flops, ms in rec:
-        key = "conv_gemm" if name.startswith("conv_gemm") else name
-        f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launch_calls": 0})
+        # the operand-plane pass of the two-unit convolutions (ops.quantize_planes) is part of the convolution family's time
+        key = "conv_gemm" if name.startswith("conv_gemm") or name == "quantize_planes" else name
+        f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launch_calls": 0, "unit_flops": 0.0})
         f["ms"] += ms; f["flops"] += flops; f["launch_calls"] += 1
+        f["unit_flops"] += flops * (2 if name.endswith(".q") else 3)      # tensor units per k-step: 2 (fp16 + 2 e4m3 at twice the rate) or 3 bf16
     sub = {}
     for name, flops, ms in rec:
         if name.startswith("conv_gemm"):
@@ -635,10 +637,12 @@ def main():
                     "traffic": 269696256.0 + 484221184.0, "traffic_algorithmic_bytes": 269317120.0 + 536870912.0,
                     "traffic_of": "one conv_halo_kernel<128,3> launch (64->128 channels, 3x3x3, batch 32), ncu dram__bytes_read.sum + dram__bytes_write.sum",
                     "kernel": "hupr::conv_gemm_kernel (all %d launches of one step; FLOPs = 2 x MACs of the fp32 contraction — the "
-                              "tensor pipe executes %dx that)" % (conv["launch_calls"], 1 if args.single_bf16 else 3),
+                              "tensor pipe executes %s that)" % (conv["launch_calls"], "1x" if args.single_bf16 else
+                                                                "3x (bf16 hi/lo products), 2x on the two-unit 3-tap convolutions (fp16 + e4m3 cross terms)"),
                     "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "algorithmic_flops_per_step": conv["flops"],
                     "kernel_ms_per_step": conv["ms"], "share_of_step": conv["ms"] / total_ms,
-                    "executed_tensor_tflops": achieved * (1 if args.single_bf16 else 3)}
+                    "executed_tensor_tflops": achieved if args.single_bf16 else conv["unit_flops"] / (conv["ms"] * 1e-3) / 1e12,
+                    "two_unit_share_of_flops": sum(v["flops"] for k, v in sub.items() if k.endswith(".q")) / max(conv["flops"], 1.0)}
         # the other named kernel families of this step against their own rooflines (algorithmic work / CUDA-event time of the family)
         families = {}
         for key in ("attention_fwd", "attention_bwd", "conv_wgrad", "matmul_tn"):

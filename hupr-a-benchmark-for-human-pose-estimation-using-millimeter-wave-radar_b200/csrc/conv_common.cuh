@@ -37,7 +37,21 @@ struct ConvParams {
     int n_fastest;                 // work-item order: column tile fastest (wide outputs) instead of row tile fastest
     double* stats;                 // optional per-output-channel sums of the epilogue values: stats[ch] += sum v, stats[stats_ld + ch] += sum v^2
     int stats_ld;                  // (train-mode BatchNorm batch statistics fused into the producing convolution, layers.py:45-53)
+    float acc_scale;               // exact power of two applied to the accumulator first (2^-16 for the two-unit arithmetic, else 1)
+    __half* o_q16;                 // optional second form of the output: activation operand planes of the two-unit arithmetic
+    uint8_t* o_q8;                 // ([positions][o_ld] at o_ch_off like o_hi; hupr_conv_desc.o_q*)
+    uint8_t* o_q8l;
+    int st256;                     // 1: every output plane row segment is 32-byte aligned -> 256-bit stores (one full sector per lane)
 };
+
+// 32-byte store (STG.256, sm_100): a thread that owns one output row writes whole 32-byte sectors instead of two half-sector pieces in two
+// instructions — the thread-per-row epilogue's scattered 16-byte stores were what the L1/L2 write path choked on.
+__device__ __forceinline__ void st_global_256(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                              uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+                 "r"(a6), "r"(a7)
+                 : "memory");
+}
 
 // Column sums over a warp: every lane holds 32 values (one row of a 32-row x 32-column block); after five exchange rounds
 // (recursive halving, 31 shuffles) lane j holds the sum of column j over the 32 rows.
@@ -89,7 +103,7 @@ __device__ __forceinline__ void conv_epilogue_values(const ConvParams& p, const 
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(acc[j]);
-        const float sc = p.scale ? __ldg(p.scale + ch0 + j) : 1.0f;
+        const float sc = (p.scale ? __ldg(p.scale + ch0 + j) : 1.0f) * p.acc_scale;     // power-of-two factor: exact
         const float sh = p.shift ? __ldg(p.shift + ch0 + j) : 0.0f;
         v[j] = fmaf(x, sc, sh);
     }
@@ -164,12 +178,51 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, const f
 #pragma unroll
         for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);      // same roundings, one cvt.rn.bf16x2 per plane
         uint4* dh = reinterpret_cast<uint4*>(p.o_hi + pos * p.o_ld + p.o_ch_off + ch0);
+        uint4* dl = p.o_lo ? reinterpret_cast<uint4*>(p.o_lo + pos * p.o_ld + p.o_ch_off + ch0) : nullptr;
+        if (p.st256) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) dh[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-        if (p.o_lo) {
-            uint4* dl = reinterpret_cast<uint4*>(p.o_lo + pos * p.o_ld + p.o_ch_off + ch0);
+            for (int g = 0; g < 2; ++g) {
+                st_global_256(dh + 2 * g, hi[8 * g], hi[8 * g + 1], hi[8 * g + 2], hi[8 * g + 3], hi[8 * g + 4], hi[8 * g + 5], hi[8 * g + 6], hi[8 * g + 7]);
+                if (dl) st_global_256(dl + 2 * g, lo[8 * g], lo[8 * g + 1], lo[8 * g + 2], lo[8 * g + 3], lo[8 * g + 4], lo[8 * g + 5], lo[8 * g + 6], lo[8 * g + 7]);
+            }
+        } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) dl[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+            for (int g = 0; g < 4; ++g) dh[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+            if (dl) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dl[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+            }
+        }
+    }
+    if (p.o_q16 && p.st256) {
+        const QuantScales q = quant_scales(false);
+        const size_t at = pos * p.o_ld + p.o_ch_off + ch0;
+        uint4 h[4];
+        uint2 a8[4], l8[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float v8[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
+            quant8(v8, q, h[g], a8[g], l8[g]);
+        }
+        st_global_256(p.o_q16 + at, h[0].x, h[0].y, h[0].z, h[0].w, h[1].x, h[1].y, h[1].z, h[1].w);
+        st_global_256(p.o_q16 + at + 16, h[2].x, h[2].y, h[2].z, h[2].w, h[3].x, h[3].y, h[3].z, h[3].w);
+        st_global_256(p.o_q8 + at, a8[0].x, a8[0].y, a8[1].x, a8[1].y, a8[2].x, a8[2].y, a8[3].x, a8[3].y);
+        st_global_256(p.o_q8l + at, l8[0].x, l8[0].y, l8[1].x, l8[1].y, l8[2].x, l8[2].y, l8[3].x, l8[3].y);
+    } else if (p.o_q16) {
+        const QuantScales q = quant_scales(false);
+        const size_t at = pos * p.o_ld + p.o_ch_off + ch0;
+        uint4* d16 = reinterpret_cast<uint4*>(p.o_q16 + at);
+        uint2* d8 = reinterpret_cast<uint2*>(p.o_q8 + at);
+        uint2* d8l = reinterpret_cast<uint2*>(p.o_q8l + at);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float v8[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
+            uint4 h;
+            uint2 a8, l8;
+            quant8(v8, q, h, a8, l8);
+            d16[g] = h;
+            d8[g] = a8;
+            d8l[g] = l8;
         }
     }
 }

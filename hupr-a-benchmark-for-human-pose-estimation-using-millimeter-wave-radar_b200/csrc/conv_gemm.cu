@@ -438,16 +438,32 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream);   // conv_halo.cu
+int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream, bool probe);   // conv_halo.cu
+
+// Validation + parameter block shared by hupr_conv_gemm and hupr_conv_quant_eligible; `launch` = false stops before any launch and returns
+// 1 / 0 for "the two-unit halo kernel would take this descriptor".
+static int conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch);
 
 }  // namespace hupr
 
-extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
+extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) { return hupr::conv_gemm_impl(d, stream, true); }
+
+extern "C" int hupr_conv_quant_eligible(const hupr_conv_desc* d) { return hupr::conv_gemm_impl(d, nullptr, false); }
+
+int hupr::conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch) {
     using namespace hupr;
     if (!d || !d->a_hi || !d->w_hi) return HUPR_ERR_BAD_ARG;
-    if (d->nprod != 0 && d->nprod != 1 && d->nprod != 3) return HUPR_ERR_BAD_ARG;
+    if (d->nprod < 0 || d->nprod > 3) return HUPR_ERR_BAD_ARG;
     if (d->nprod != 1 && (d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
-    if (d->nprod == 3 && !d->a_lo) return HUPR_ERR_BAD_ARG;
+    if (d->nprod >= 2 && !d->a_lo) return HUPR_ERR_BAD_ARG;
+    {   // the quantised planes come in complete sets
+        const int na = (d->a_q16 != nullptr) + (d->a_q8 != nullptr) + (d->a_q8l != nullptr);
+        const int nw = (d->w_q16 != nullptr) + (d->w_q8 != nullptr) + (d->w_q8l != nullptr);
+        const int no = (d->o_q16 != nullptr) + (d->o_q8 != nullptr) + (d->o_q8l != nullptr);
+        if (na % 3 || nw % 3 || no % 3 || (no && !d->o_hi)) return HUPR_ERR_BAD_ARG;
+        if (d->nprod == 2 && launch && (!na || !nw)) return HUPR_ERR_BAD_ARG;
+        if (no && (d->k_split > 1)) return HUPR_ERR_BAD_ARG;
+    }
     if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return HUPR_ERR_BAD_ARG;
     if (d->a_n_stride < 0 || d->a_n_stride % 8) return HUPR_ERR_BAD_ARG;
     if (d->ca % 8 || d->cin % BK || d->cin <= 0 || d->a_ch_off % 8 || d->a_ch_off + d->cin > ((d->ca + BK - 1) / BK) * BK) return HUPR_ERR_BAD_ARG;
@@ -468,7 +484,9 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     const int bh = BM / bw;
     if (d->h % bh) return HUPR_ERR_BAD_ARG;
     const uintptr_t align_or = (uintptr_t)d->a_hi | (uintptr_t)d->a_lo | (uintptr_t)d->w_hi | (uintptr_t)d->w_lo | (uintptr_t)d->o_hi |
-                               (uintptr_t)d->o_lo | (uintptr_t)d->o_f32 | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo;
+                               (uintptr_t)d->o_lo | (uintptr_t)d->o_f32 | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo | (uintptr_t)d->a_q16 |
+                               (uintptr_t)d->a_q8 | (uintptr_t)d->a_q8l | (uintptr_t)d->w_q16 | (uintptr_t)d->w_q8 | (uintptr_t)d->w_q8l |
+                               (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8 | (uintptr_t)d->o_q8l;
     if (align_or & 15) return HUPR_ERR_ALIGNMENT;
 
     ConvParams p;
@@ -484,6 +502,13 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     p.w_k_off = d->w_k_off;
     p.row_vec = d->row_vec; p.row_mode = d->row_vec ? d->row_mode : 0;
     p.stats = d->stats; p.stats_ld = d->stats_ld;
+    p.acc_scale = 1.0f;
+    p.o_q16 = static_cast<__half*>(d->o_q16); p.o_q8 = static_cast<uint8_t*>(d->o_q8); p.o_q8l = static_cast<uint8_t*>(d->o_q8l);
+    {   // 256-bit stores need 32-byte aligned row segments in every plane that is written (e4m3 planes: one byte per element)
+        const uintptr_t o_or = (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8 | (uintptr_t)d->o_q8l;
+        const int unit = d->o_q8 ? 32 : 16;
+        p.st256 = (d->o_hi && !(o_or & 31) && d->o_ld % unit == 0 && d->o_ch_off % unit == 0 && !getenv("HUPR_NO_ST256")) ? 1 : 0;
+    }
     if (d->stats && (d->stats_ld < d->cout || d->k_split > 1 || ((uintptr_t)d->stats & 7))) return HUPR_ERR_BAD_ARG;
     p.coop_ws = static_cast<float*>(d->ws); p.coop_ws_bytes = d->ws ? d->ws_bytes : 0; p.coop_counters = nullptr; p.coop = 0;
     if (d->ws && ((uintptr_t)d->ws & 15)) return HUPR_ERR_ALIGNMENT;
@@ -499,7 +524,8 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     }
 
     {   // 3-tap-in-H convolutions with enough tiles go to the halo-reuse kernel (conv_halo.cu)
-        const int hr = conv_halo_try(d, p, static_cast<cudaStream_t>(stream));
+        const int hr = conv_halo_try(d, p, static_cast<cudaStream_t>(stream), !launch);
+        if (!launch) return hr == 2 ? 1 : (hr < 0 ? hr : 0);      // probe: 2 = the two-unit kernel takes it
         if (hr <= 0) return hr;
     }
     const int bn = (d->cout % 128 == 0) ? 128 : 64;
@@ -526,7 +552,7 @@ extern "C" int hupr_conv_gemm(const hupr_conv_desc* d, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // row tiles with bf16 split output and enough tiles to fill the GPU: TMA-store epilogue
     const bool tstore = bw == BM && d->o_hi && d->o_lo && !d->o_f32 && !p.atomic && m_tiles_ll * (d->cout / bn) >= 148 &&
-                        (long long)d->n * d_out * d->h * d->w < 2147483647LL && !d->no_tma_store;
+                        (long long)d->n * d_out * d->h * d->w < 2147483647LL && !d->no_tma_store && !d->o_q16;
     if (tstore && split) return bn == 128 ? launch_conv<128, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 3, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
     if (tstore) return bn == 128 ? launch_conv<128, 1, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<64, 1, true>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);
     if (bn == 128) return split ? launch_conv<128, 3, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s) : launch_conv<128, 1, false>(a_hi, a_lo, b_hi, b_lo, p, m_tiles, s);

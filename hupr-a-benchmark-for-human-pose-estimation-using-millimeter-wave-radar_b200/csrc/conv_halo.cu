@@ -12,11 +12,19 @@
 //     stays under 96 KiB and two to three stages fit;
 //   * the kernel is persistent (one CTA per SM walks the tiles) with two accumulator sets in TMEM, so the epilogue of one tile
 //     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next;
+//   * EIGHT epilogue warps, four per accumulator of the tile: the epilogue is a long dependent chain per thread (one output row, ~20
+//     instructions per value with the stores), and with one warp per scheduler nothing hides its latencies — ncu of the two-unit variant
+//     with four warps: the MMA thread spun 7 M times on accum_empty, tensor pipe 37 % active, i.e. the epilogue (77 k cycles per tile)
+//     and not the 37 k-cycle main loop set the pace; the single-product training kernels were bound the same way;
 //   * cout = 64 tiles (BN = 64, three products) are bound by the tensor core's shared-memory operand reads: an M = 128, N = 64, K = 16
 //     MMA reads 4 KB of A and 2 KB of B per 32 cycles = 192 B/cycle against a 128 B/cycle port (ncu: 34 % tensor-active).  There the
 //     weight tiles of a tap are stored as one 128-row B operand [w_hi | w_lo], so a_hi meets both in ONE N = 128 MMA (columns 0..63 =
 //     hi*hi, 64..127 = hi*lo) and a_lo * w_hi is a second, N = 64 MMA into columns 0..63: the A planes are read twice instead of three
 //     times per k-step (14 KB instead of 18 KB per 96 tensor cycles); the epilogue adds the two column halves.
+//   * NPROD == 2 is the two-unit arithmetic of hupr_conv_desc (include/hupr_b200.h): per 32-channel block ONE kind::f16 pair of MMAs on
+//     fp16 planes (a16 x w16) plus TWO kind::f8f6f4 MMAs (K = 32: a whole 32-byte row) on e4m3 planes (al x w, a x wl), all into the same
+//     fp32 accumulator at a common 2^16 scale — 64 + 32 + 32 tensor cycles per N = 128 tile-tap instead of 3 x 64, and 2/3 of the
+//     shared-memory operand bytes.  The e4m3 planes are 32-byte rows under SWIZZLE_32B; a stage has the same size as the hi/lo one.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
 #include <stdlib.h>
 
@@ -27,8 +35,8 @@ namespace hupr {
 
 constexpr int HK = 32;             // channels per k-block (64-byte swizzled rows)
 constexpr int HM = 256;            // output positions per CTA
-constexpr int kHaloThreads = 192;
-constexpr int kHaloStatBytes = 4 * 2 * 128 * 4;      // per-warp running column sums of the fused BatchNorm statistics
+constexpr int kHaloThreads = 320;                    // TMA warp, MMA warp, 2 x 4 epilogue warps (one group per accumulator of a tile)
+constexpr int kHaloStatBytes = 8 * 2 * 128 * 4;      // per-warp running column sums of the fused BatchNorm statistics
 
 struct HaloGeom {
     int halo_rows;                 // (bh + 2) * bw
@@ -40,7 +48,18 @@ struct HaloGeom {
     int tap_stride_bytes;          // bw * 64: one h-row of the halo
     int acc_stride_bytes;          // (bh / 2) * bw * 64: first row of accumulator 1
     int m_tiles, n_tiles;          // 256-position tiles x BN-column tiles, walked persistently
+    int b_merged;                  // three products: tmB_hi is a 5-D map over BOTH weight planes (cin, cout, plane, kw, kd*3 + kh): one box per stage
 };
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;                   // stride byte offset: 8 rows * 32 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                            // SWIZZLE_32B
+    return d;
+}
 
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -55,8 +74,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
 template <int BN, int NPROD>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const ConvParams p,
-                 const HaloGeom g) {
+                 const __grid_constant__ CUtensorMap tmA_x,      // NPROD == 2: A maps are (fp16 a16, e4m3 a, e4m3 al), B maps (w16, w, wl)
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmB_x, const ConvParams p, const HaloGeom g) {
     // Persistent: CTA b walks tiles b, b + gridDim.x, ...; the TMA->MMA smem ring runs continuously across tiles and the two
     // accumulator SETS in TMEM (2 x [2 x BN] columns) let the epilogue of tile i overlap the main loop of tile i + 1.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -67,12 +87,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint64_t* accum_full = bars + 8;     // [2]
     uint64_t* accum_empty = bars + 10;   // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
-    float* s_stat = reinterpret_cast<float*>(bars + 32);      // [4 epilogue warps][2][BN] running column sums (fused BatchNorm statistics)
+    float* s_stat = reinterpret_cast<float*>(bars + 32);      // [8 epilogue warps][2][BN] running column sums (fused BatchNorm statistics)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
     constexpr bool three = NPROD == 3;      // compile-time: the single-thread MMA issue loop carries no runtime branches
+    constexpr bool quant = NPROD == 2;      // fp16 main product + two e4m3 cross products (header comment)
     constexpr bool ncat = (BN == 64 && NPROD == 3);         // [w_hi | w_lo] as one N = 128 operand (header comment)
     constexpr int ACC = ncat ? 128 : BN;                    // TMEM columns of one accumulator
     constexpr int TMEM_COLS = 4 * ACC;                      // two sets x two accumulators
@@ -85,10 +106,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&accum_full[s], 1);
-            mbar_init(&accum_empty[s], 128);
+            mbar_init(&accum_empty[s], 256);
         }
         fence_mbar_init();
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+        if (quant) { prefetch_tmap(&tmA_x); prefetch_tmap(&tmB_x); }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS));
@@ -127,13 +149,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const int ac = p.a_ch_off + cb * HK;
                     tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                     if (three) tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                    if (quant) {       // stage = [a16 | a8 | a8l | w16 x3 | w8 x3 | w8l x3]; e4m3 planes and tiles are half the bytes
+                        tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                        tma_load_5d(st + g.a_plane_bytes + g.a_plane_bytes / 2, &tmA_x, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                        uint8_t* sq = st + 2 * g.a_plane_bytes;
+                        // one box per plane brings the three kh taps (weight map dims: cin, cout, kw, kd*3 + kh)
+                        tma_load_4d(sq, &tmB_hi, &full[s], cb * HK, n0, tkw, tkd * 3);
+                        tma_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tkw, tkd * 3);
+                        tma_load_4d(sq + 3 * g.b_tile_bytes + 3 * (g.b_tile_bytes / 2), &tmB_x, &full[s], cb * HK, n0, tkw, tkd * 3);
+                    }
                     uint8_t* sb = st + (three ? 2 : 1) * g.a_plane_bytes;
+                    // The TMA unit ingests about one box row per clock plus ~110 clocks per box (tools_dev/micro/tma_rate.cu): six 128-row weight
+                    // boxes cost 1 430 clocks of a 2 400-clock stage.  Weight maps therefore have (kw, kd*3 + kh) as separate dimensions so that
+                    // one box brings the three kh taps, and, where the two planes can be addressed as one tensor, both planes:
+                    // B tiles of a three-product stage: [hi0 lo0 hi1 lo1 hi2 lo2] (for cout = 64, hi|lo of a tap form one N = 128 operand)
+                    if (three) {
+                        if (g.b_merged) {
+                            tma_load_5d_w(sb, &tmB_hi, &full[s], cb * HK, n0, 0, tkw, tkd * 3);
+                        } else {
 #pragma unroll
-                    for (int tkh = 0; tkh < 3; ++tkh) {
-                        const int tap = (tkd * 3 + tkh) * p.kw + tkw;
-                        // B tiles of a stage: [hi0 hi1 hi2 lo0 lo1 lo2], or [hi0 lo0 hi1 lo1 hi2 lo2] when hi|lo form one N = 128 operand
-                        tma_load_3d(sb + (ncat ? 2 * tkh : tkh) * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tap);
-                        if (three) tma_load_3d(sb + (ncat ? 2 * tkh + 1 : 3 + tkh) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tap);
+                            for (int tkh = 0; tkh < 3; ++tkh) {
+                                tma_load_4d(sb + 2 * tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, n0, tkw, tkd * 3 + tkh);
+                                tma_load_4d(sb + (2 * tkh + 1) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tkw, tkd * 3 + tkh);
+                            }
+                        }
+                    } else if (!quant) {
+                        tma_load_4d(sb, &tmB_hi, &full[s], cb * HK, n0, tkw, tkd * 3);      // [hi0 hi1 hi2]
                     }
                     if (++cb == p.cin_blocks) {
                         cb = 0;
@@ -146,7 +187,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // fp32 accumulate; A / B formats: bf16 (1), or for NPROD == 2 fp16 under kind::f16 and e4m3 under kind::f8f6f4 (both 0)
+            const uint32_t fmt = quant ? 0u : ((1u << 7) | (1u << 10));
+            const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 128
             int it = 0, lt = 0, sidx = 0;
             uint32_t sph = 0;
@@ -161,10 +204,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * g.stage_bytes);
                     const uint32_t sb = st + (three ? 2 : 1) * g.a_plane_bytes;
+                    if (quant) {
+                        const uint32_t sq = st + 2 * g.a_plane_bytes;
 #pragma unroll
-                    for (int tkh = 0; tkh < 3; ++tkh) {
-                        const uint64_t db_hi = make_smem_desc_sw64(sb + (ncat ? 2 * tkh : tkh) * g.b_tile_bytes);
-                        const uint64_t db_lo = make_smem_desc_sw64(sb + (ncat ? 2 * tkh + 1 : 3 + tkh) * g.b_tile_bytes);
+                        for (int tkh = 0; tkh < 3; ++tkh) {
+                            const uint64_t db16 = make_smem_desc_sw64(sq + tkh * g.b_tile_bytes);
+                            const uint64_t db8 = make_smem_desc_sw32(sq + 3 * g.b_tile_bytes + tkh * (g.b_tile_bytes / 2));
+                            const uint64_t db8l = make_smem_desc_sw32(sq + 3 * g.b_tile_bytes + (3 + tkh) * (g.b_tile_bytes / 2));
+#pragma unroll
+                            for (int a = 0; a < 2; ++a) {
+                                const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
+                                const uint64_t da16 = make_smem_desc_sw64(st + aoff);
+                                const uint64_t da8 = make_smem_desc_sw32(st + g.a_plane_bytes + aoff / 2);
+                                const uint64_t da8l = make_smem_desc_sw32(st + g.a_plane_bytes + g.a_plane_bytes / 2 + aoff / 2);
+                                const uint32_t tacc = tset + (uint32_t)(a * ACC);
+                                umma_f8(tacc, da8l, db8, idesc, (uint32_t)((gi | tkh) != 0));      // (a - a16) x w   (e4m3, K = 32)
+                                umma_f8(tacc, da8, db8l, idesc, 1u);                                // a x (w - w16)
+                                umma_bf16(tacc, da16, db16, idesc, 1u);                             // a16 x w16 (fp16, K = 16 twice)
+                                umma_bf16(tacc, da16 + 2, db16 + 2, idesc, 1u);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int tkh = 0; tkh < (quant ? 0 : 3); ++tkh) {
+                        const uint64_t db_hi = make_smem_desc_sw64(sb + (three ? 2 * tkh : tkh) * g.b_tile_bytes);
+                        const uint64_t db_lo = make_smem_desc_sw64(sb + (2 * tkh + 1) * g.b_tile_bytes);
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
@@ -195,14 +259,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31, accumulator 0 then 1 =================
+        // ================= epilogue warps: TMEM lanes 32*(warp%4) .. +31; warps 2..5 drain accumulator 0, warps 6..9 accumulator 1 ====
         const int q = warp & 3;
+        const int a = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         int lt = 0;
         // fused BatchNorm statistics: this warp's running column sums (sum v, sum v^2 of channel n0 + col over all rows it has seen) live
         // in shared memory, lane j owning columns j, j + 32, ...; a CTA's tiles come in non-decreasing n0 order, so the sums are flushed
         // (double atomics) when n0 changes and at the end
-        float* wstat = s_stat + q * 2 * BN;
+        float* wstat = s_stat + (warp - 2) * 2 * BN;
         if (p.stats) {
             for (int j = lane; j < 2 * BN; j += 32) wstat[j] = 0.f;
         }
@@ -218,8 +283,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             mbar_wait(&accum_full[as], (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             const uint32_t tset = tmem_base + (uint32_t)(as * 2 * ACC) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int a = 0; a < 2; ++a) {
+            {
                 const int ow = row % p.bw, oh = h0 + a * (p.bh / 2) + row / p.bw;
                 const size_t pos = (((size_t)n * p.d_out + od) * p.h + oh) * p.w + ow;
 #pragma unroll 1
@@ -235,7 +299,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     } else {
                         tmem_ld32(tset + (uint32_t)(a * BN + c * 32), acc);
                     }
-                    if (a == 1 && c == BN / 32 - 1) {      // last TMEM read of this set: hand it back before the stores
+                    if (c == BN / 32 - 1) {                // this thread's last TMEM read of the set: hand it back before the stores
                         tc_fence_before();
                         mbar_arrive(&accum_empty[as]);
                     }
@@ -252,36 +316,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
 }
 
-static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h, long long n_stride) {
+// esize: bytes per element — 2: bf16 / fp16 planes (64-byte rows, SWIZZLE_64B), 1: e4m3 planes (32-byte rows, SWIZZLE_32B)
+static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h, long long n_stride,
+                               int esize = 2) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return HUPR_ERR_CUDA;
+    const cuuint64_t e = (cuuint64_t)esize;
     cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
-    cuuint64_t strides[4] = {(cuuint64_t)ca * 2, (cuuint64_t)w * ca * 2, (cuuint64_t)h * w * ca * 2,
-                             (cuuint64_t)(n_stride > 0 ? n_stride : (long long)d * h * w * ca) * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)ca * e, (cuuint64_t)w * ca * e, (cuuint64_t)h * w * ca * e,
+                             (cuuint64_t)(n_stride > 0 ? n_stride : (long long)d * h * w * ca) * e};
     cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bw, (cuuint32_t)box_h, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
-static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int taps, int bn, int ld) {
+// Weights [kd][kh][kw][cout][ld] seen as (cin, cout, kw, kd*3 + kh): a box of `box_kh` = 3 consecutive entries of the last dimension is the
+// three kh taps of one (kd, kw) — one TMA instruction instead of three.
+static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int cout, int kd, int kw, int bn, int ld, int box_kh, int esize = 2) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return HUPR_ERR_CUDA;
-    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)cout * ld * 2};
-    cuuint32_t box[3] = {(cuuint32_t)HK, (cuuint32_t)bn, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t e = (cuuint64_t)esize;
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)kw, (cuuint64_t)kd * 3};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * e, (cuuint64_t)cout * ld * e, (cuuint64_t)kw * cout * ld * e};
+    cuuint32_t box[4] = {(cuuint32_t)HK, (cuuint32_t)bn, 1, (cuuint32_t)box_kh};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
 template <int BN, int NPROD>
-static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                       const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
+static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& a_x, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const CUtensorMap& b_x, const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
     static bool configured[kMaxDevices] = {};
     const int smem_max = 232448;
     if (int crc = ensure_smem_optin(conv_halo_kernel<BN, NPROD>, smem_max, configured)) return crc;
@@ -293,15 +363,21 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     gg.m_tiles = m_tiles;
     gg.n_tiles = p.cout / BN;
     const int total = gg.m_tiles * gg.n_tiles;
-    dim3 grid(total < num_sms ? total : num_sms, 1, 1);
-    launch_k(conv_halo_kernel<BN, NPROD>, grid, dim3(kHaloThreads), (size_t)smem, stream, a_hi, a_lo, b_hi, b_lo, p, gg);
+    int ctas = total < num_sms ? total : num_sms;
+    if (const char* cap = getenv("HUPR_HALO_GRID")) {      // measurement switch: fewer persistent CTAs (per-SM vs chip-wide operand bandwidth)
+        const int c = atoi(cap);
+        if (c > 0 && c < ctas) ctas = c;
+    }
+    dim3 grid(ctas, 1, 1);
+    launch_k(conv_halo_kernel<BN, NPROD>, grid, dim3(kHaloThreads), (size_t)smem, stream, a_hi, a_lo, a_x, b_hi, b_lo, b_x, p, gg);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
 // Returns HUPR_OK after launching, or a positive value (1) if the shape is not handled here (caller falls through to the
 // generic kernel).  Arguments were validated by hupr_conv_gemm.
-int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream) {
+// `probe`: no launch; returns 2 when the two-unit (NPROD == 2) kernel would take the descriptor, 1 otherwise.
+int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t stream, bool probe) {
     const bool three = d->a_lo != nullptr && d->w_lo != nullptr && d->nprod != 1;
     if (d->w_batched || d->k_split > 1 || d->w_k_off != 0) return 1;
     if (!three && getenv("HUPR_HALO1_OFF")) return 1;      // A/B switch: single-product convolutions on the generic kernel
@@ -322,6 +398,7 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     p.bw = bw; p.bh = bh; p.tiles_w = 1; p.tiles_h = d->h / bh;
     p.cin_blocks = cin_eff / HK;
     HaloGeom g;
+    g.b_merged = 0;
     g.halo_rows = (bh + 2) * bw;
     g.a_plane_bytes = g.halo_rows * 64;
     g.b_tile_bytes = bn * 64;
@@ -336,19 +413,64 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
 
     const int taps = d->kd * d->kh * d->kw;
     const int w_ld = d->w_ld ? d->w_ld : d->cin;
+    // two-unit arithmetic: cout = 128-column tiles only (the cout = 64 tiles are bound by shared-memory operand reads either way and keep
+    // the [w_hi | w_lo] form), dense samples, no fused statistics (train mode never asks for it)
+    const bool quant = three && d->nprod == 2 && bn == 128 && d->a_n_stride == 0 && !d->stats && d->ca % 16 == 0 && w_ld % 16 == 0 &&
+                       d->w_ch_off % 16 == 0 && !getenv("HUPR_QUANT_OFF");
+    if (probe) return quant ? 2 : 1;
+    if (quant && d->a_q16 && d->w_q16) {
+        CUtensorMap a16, a8, a8l, b16, b8, b8l;
+        int rc;
+        if ((rc = encode_halo_act_map(&a16, d->a_q16, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_act_map(&a8, d->a_q8, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0, 1)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_act_map(&a8l, d->a_q8l, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0, 1)) != HUPR_OK) return rc;
+        const char* w16 = static_cast<const char*>(d->w_q16) + (size_t)d->w_ch_off * 2;
+        const char* w8 = static_cast<const char*>(d->w_q8) + d->w_ch_off;
+        const char* w8l = static_cast<const char*>(d->w_q8l) + d->w_ch_off;
+        if ((rc = encode_halo_wgt_map(&b16, w16, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b8, w8, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3, 1)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b8l, w8l, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3, 1)) != HUPR_OK) return rc;
+        g.nprod = 2;
+        p.acc_scale = 1.0f / 65536.0f;
+        return launch_halo<128, 2>(a16, a8, a8l, b16, b8, b8l, p, g, m_tiles, stream);
+    }
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
     const __nv_bfloat16* w_lo = three ? static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off : w_hi;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     if ((rc = encode_halo_act_map(&a_lo, three ? d->a_lo : d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
-    if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
-    if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, taps, bn, w_ld)) != HUPR_OK) return rc;
+    g.b_merged = 0;
+    if (three) {
+        // both planes through ONE map when lo lies a 16-byte-multiple above hi in the address space (always true for the halves of one
+        // allocation, SplitTensor.from_float; otherwise one box per tile and plane)
+        const long long plane = (const char*)w_lo - (const char*)w_hi;
+        if (plane > 0 && plane % 16 == 0 && plane < (1LL << 40) && !getenv("HUPR_HALO_B_UNMERGED")) {
+            EncodeTiledFn fn = get_encode_fn();
+            if (!fn) return HUPR_ERR_CUDA;
+            cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout, 2, (cuuint64_t)d->kw, (cuuint64_t)d->kd * 3};
+            cuuint64_t strides[4] = {(cuuint64_t)w_ld * 2, (cuuint64_t)plane, (cuuint64_t)d->cout * w_ld * 2, (cuuint64_t)d->kw * d->cout * w_ld * 2};
+            cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bn, 2, 1, 3};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            if (fn(&b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(w_hi), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                g.b_merged = 1;
+                b_lo = b_hi;
+            }
+        }
+        if (!g.b_merged) {
+            if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 1)) != HUPR_OK) return rc;
+            if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 1)) != HUPR_OK) return rc;
+        }
+    } else {
+        if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3)) != HUPR_OK) return rc;
+        b_lo = b_hi;
+    }
     if (three)
-        return bn == 128 ? launch_halo<128, 3>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
-                         : launch_halo<64, 3>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
-    return bn == 128 ? launch_halo<128, 1>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream)
-                     : launch_halo<64, 1>(a_hi, a_lo, b_hi, b_lo, p, g, m_tiles, stream);
+        return bn == 128 ? launch_halo<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
+                         : launch_halo<64, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
+    return bn == 128 ? launch_halo<128, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
+                     : launch_halo<64, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
 }
 
 }  // namespace hupr

@@ -12,6 +12,8 @@
 //   hupr_gcn_bias_rows       bias fp32 [1024][14] -> hi/lo rows [(b,j)][1024] (residual operand of the transposed-layout GCN GEMMs)
 //   hupr_bump_i32            ++*counter                                      (device-side Adam step count)
 //   hupr_memset_zero         cudaMemsetAsync (a memset node when captured)
+// and, for the inference path, hupr_quantize_planes: bf16 hi/lo -> the fp16 + e4m3 operand planes of the two-unit 3-tap convolution
+// (hupr_conv_desc.nprod == 2); HBM-bound, 4 B read + 4 B written per element.
 #include "common.cuh"
 #include "split.cuh"
 
@@ -128,6 +130,26 @@ reduce_f64_kernel(const double* __restrict__ src, int groups, int n, float* __re
     dst[g] = (float)s;
 }
 
+// thread = 8 consecutive channels of one row; two independent items per iteration so that four 16-byte loads are in flight
+__global__ void __launch_bounds__(256)
+quantize_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long items, int ld, int ch_off, int groups,
+                       __half* __restrict__ q16, uint8_t* __restrict__ q8, uint8_t* __restrict__ q8l, int is_weight) {
+    const QuantScales q = quant_scales(is_weight != 0);
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < items; i += stride) {
+        const long long row = i / groups;
+        const size_t at = (size_t)row * ld + ch_off + (size_t)(i - row * groups) * 8;
+        float v[8];
+        load8(hi + at, lo ? lo + at : nullptr, v);
+        uint4 h;
+        uint2 a8, l8;
+        quant8(v, q, h, a8, l8);
+        *reinterpret_cast<uint4*>(q16 + at) = h;
+        *reinterpret_cast<uint2*>(q8 + at) = a8;
+        *reinterpret_cast<uint2*>(q8l + at) = l8;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 broadcast_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -221,6 +243,25 @@ extern "C" int hupr_reduce_f64(const double* src, int groups, int n, float* dst,
     if (!src || !dst) return HUPR_ERR_BAD_ARG;
     if (int rc = device_check_sm100()) return rc;
     reduce_f64_kernel<<<(groups + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, groups, n, dst);
+    return pack_status();
+}
+
+extern "C" int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, void* q8l,
+                                    int is_weight, void* stream) {
+    using namespace hupr;
+    if (rows < 0 || ld <= 0 || ch < 0 || ch_off < 0 || ch_off + ch > ld || ld % 8 || ch % 8 || ch_off % 8) return HUPR_ERR_BAD_ARG;
+    if (rows == 0 || ch == 0) return HUPR_OK;
+    if (!hi || !q16 || !q8 || !q8l) return HUPR_ERR_BAD_ARG;
+    if (((uintptr_t)hi | (uintptr_t)lo | (uintptr_t)q16 | (uintptr_t)q8 | (uintptr_t)q8l) & 15) return HUPR_ERR_ALIGNMENT;
+    if (int rc = device_check_sm100()) return rc;
+    const int groups = ch / 8;
+    const long long items = rows * groups;
+    const int sms = device_sm_count();
+    if (sms <= 0) return HUPR_ERR_CUDA;
+    long long blocks = (items + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    quantize_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, items, ld, ch_off,
+                                                                                groups, (__half*)q16, (uint8_t*)q8, (uint8_t*)q8l, is_weight);
     return pack_status();
 }
 

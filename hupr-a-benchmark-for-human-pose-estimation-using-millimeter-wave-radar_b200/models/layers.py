@@ -81,13 +81,20 @@ def pack_block2d(sd, prefix, cin, cout, split):
     return b
 
 
-def run_block(x, blk, tmp, out, o_ch_off=0):
+def block_wants_q(x, blk, tmp):
+    """True when the block's first convolution would read ``x`` through the two-unit kernel (ops.quant()): the producer of ``x`` then
+    writes the quantised operand planes from its epilogue (``out_q``) instead of leaving them to a separate pass."""
+    return ops._QUANT and ops.conv_gemm(x, blk.cin, blk.w1, 2 * blk.cmid, kernel=blk.taps, pad=blk.pad, out=tmp, probe=True)
+
+
+def run_block(x, blk, tmp, out, o_ch_off=0, out_q=False):
     """x -> out[..., o_ch_off : o_ch_off + cmid];  tmp is a ``[..., 2*cmid]`` scratch tensor."""
     c = blk.cmid
+    q2 = ops._QUANT and ops.conv_gemm(tmp, c, blk.w2, c, kernel=blk.taps, pad=blk.pad, out=out, o_ch_off=o_ch_off, probe=True)
     ops.conv_gemm(x, blk.cin, blk.w1, 2 * c, kernel=blk.taps, pad=blk.pad, scale=blk.scale1, shift=blk.shift1,
-                  slope=blk.slope1, out=tmp, lcout=2 * blk.lc)
+                  slope=blk.slope1, out=tmp, lcout=2 * blk.lc, out_q=q2)
     ops.conv_gemm(tmp, c, blk.w2, c, kernel=blk.taps, pad=blk.pad, scale=blk.scale2, shift=blk.shift2, slope=blk.slope2,
-                  residual=tmp, r_ch_off=c, out=out, o_ch_off=o_ch_off, lcin=blk.lc, lcout=blk.lc)
+                  residual=tmp, r_ch_off=c, out=out, o_ch_off=o_ch_off, lcin=blk.lc, lcout=blk.lc, out_q=out_q)
     return out
 
 
@@ -129,13 +136,14 @@ class EncoderBuffers(object):
 def run_encoder(x, w, bf):
     """x: SplitTensor ``[B, G, 64, 64, nf]`` chirp features -> (f1, f2, f3) temporal-merged maps."""
     nf, g = w.nf, w.g
-    ops.conv_gemm(x, pad64(nf), w.l1_w, 2 * nf, kernel=(3, 3, 3), pad=(1, 1, 1), shift=w.l1_shift, out=bf.l1a)
+    ops.conv_gemm(x, pad64(nf), w.l1_w, 2 * nf, kernel=(3, 3, 3), pad=(1, 1, 1), shift=w.l1_shift, out=bf.l1a,
+                  out_q=block_wants_q(bf.l1a, w.blocks[0], bf.t1))
     run_block(bf.l1a, w.blocks[0], bf.t1, bf.l1)
     ops.resample_linear(bf.l1, 2 * nf, bf.l2in)
-    run_block(bf.l2in, w.blocks[1], bf.t2, bf.l2a)
+    run_block(bf.l2in, w.blocks[1], bf.t2, bf.l2a, out_q=block_wants_q(bf.l2a, w.blocks[2], bf.t2))
     run_block(bf.l2a, w.blocks[2], bf.t2, bf.l2)
     ops.resample_linear(bf.l2, 4 * nf, bf.l3in)
-    run_block(bf.l3in, w.blocks[3], bf.t3, bf.l3a)
+    run_block(bf.l3in, w.blocks[3], bf.t3, bf.l3a, out_q=block_wants_q(bf.l3a, w.blocks[4], bf.t3))
     run_block(bf.l3a, w.blocks[4], bf.t3, bf.l3)
     ops.conv_gemm(bf.l1, 2 * nf, w.merge[0], 2 * nf, kernel=(g, 1, 1), out=bf.f1)
     ops.conv_gemm(bf.l2, 4 * nf, w.merge[1], 4 * nf, kernel=(g // 2, 1, 1), out=bf.f2)
@@ -289,15 +297,15 @@ def run_decoder(w, bf, feats_ra, feats_re, adj, concurrent=False):
     nf = w.nf
     l3, l2, l1 = bf.levels
     cat3 = run_attention_level(bf, l3, w.proj_hori[0], w.proj_vert[0], feats_ra[2], feats_re[2], concurrent)
-    run_block(cat3, w.blocks[0], bf.t3a, bf.o3a)
+    run_block(cat3, w.blocks[0], bf.t3a, bf.o3a, out_q=block_wants_q(bf.o3a, w.blocks[1], bf.t3b))
     run_block(bf.o3a, w.blocks[1], bf.t3b, bf.o3b)
     ops.resample_linear(bf.o3b, 4 * nf, l2["cat"])
     cat2 = run_attention_level(bf, l2, w.proj_hori[1], w.proj_vert[1], feats_ra[1], feats_re[1], concurrent)
-    run_block(cat2, w.blocks[2], bf.t2a, bf.o2a)
+    run_block(cat2, w.blocks[2], bf.t2a, bf.o2a, out_q=block_wants_q(bf.o2a, w.blocks[3], bf.t2b))
     run_block(bf.o2a, w.blocks[3], bf.t2b, bf.o2b)
     ops.resample_linear(bf.o2b, 2 * nf, l1["cat"])
     cat1 = run_attention_level(bf, l1, w.proj_hori[2], w.proj_vert[2], feats_ra[0], feats_re[0], concurrent)
-    run_block(cat1, w.blocks[4], bf.t1a, bf.o1a)
+    run_block(cat1, w.blocks[4], bf.t1a, bf.o1a, out_q=block_wants_q(bf.o1a, w.blocks[5], bf.t1b))
     run_block(bf.o1a, w.blocks[5], bf.t1b, bf.o1b)
     b = bf.o1b.hi.shape[0]
     ops.conv_gemm(bf.o1b, pad64(nf), w.head, bf.logits_out.shape[-1], out_f32=bf.logits_out.view(b, 1, 64, 64, -1), lcin=nf, lcout=w.keypoints)

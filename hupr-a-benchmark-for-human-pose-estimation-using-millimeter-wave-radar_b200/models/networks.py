@@ -15,6 +15,8 @@ any torch optimiser.  The fused path (``TrainStep.forward_backward`` + ``hupr_ad
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -107,8 +109,15 @@ class _TrainForward(torch.autograd.Function):
 class HuPRNet(nn.Module):
     def __init__(self, cfg, split=True):
         """``split=True``: bf16 hi/lo activations and weights, three tensor-core products per k-step — fp32-equivalent
-        results (the reference computes in fp32).  ``split=False``: single bf16 product (faster, ~1e-2 accuracy)."""
+        results (the reference computes in fp32).  ``split=False``: single bf16 product (faster, ~1e-2 accuracy).
+
+        ``quant_cross_terms`` (attribute, default False unless HUPR_QUANT=1; eval-mode ``split`` forward only): the large 3-tap
+        convolutions evaluate the two hi*lo cross terms as e4m3 products next to an fp16 main product (ops.quant; two tensor units per
+        k-step instead of three).  Parity-green (heat maps well inside the 1e-3 bar, keypoints unchanged; activations are assumed
+        |x| < 224 for full accuracy, finite up to 4094) but NOT faster on a B200: the halo kernels are bound by L2 -> shared-memory
+        operand delivery, which this arithmetic leaves unchanged (profiles/r02_halo128_q_*), so it stays opt-in."""
         super(HuPRNet, self).__init__()
+        self.quant_cross_terms = os.environ.get("HUPR_QUANT", "0") == "1"
         self.numFrames = cfg.DATASET.numFrames
         self.numFilters = nf = cfg.MODEL.numFilters
         self.rangeSize = cfg.DATASET.rangeSize
@@ -236,7 +245,8 @@ class HuPRNet(nn.Module):
         plan's output buffers — valid until the next forward)."""
         batch = chirp_ra.hi.shape[0]
         pk, plan = self._plan(batch)
-        with ops.coop_scope(plan["coop"]), ops.pdl(batch <= 4 or ops._C.lib().hupr_set_pdl(-1) == 1):
+        with ops.coop_scope(plan["coop"]), ops.pdl(batch <= 4 or ops._C.lib().hupr_set_pdl(-1) == 1), \
+                ops.quant(self.split and self.quant_cross_terms):
             return self._forward_features(pk, plan, batch, chirp_ra, chirp_re)
 
     def _forward_features(self, pk, plan, batch, chirp_ra, chirp_re):

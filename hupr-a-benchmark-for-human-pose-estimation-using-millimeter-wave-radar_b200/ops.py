@@ -40,13 +40,28 @@ def _timed(name, flops=0):
 class SplitTensor(object):
     """Channels-last activation ``[N, D, H, W, C]`` stored as two bf16 planes: value = hi + lo.
 
-    ``lo is None`` means single-bf16 mode (fast, not fp32-equivalent)."""
+    ``lo is None`` means single-bf16 mode (fast, not fp32-equivalent).
 
-    __slots__ = ("hi", "lo")
+    ``q`` (optional) holds the same values a second time as the operand planes of the two-unit 3-tap convolution
+    (hupr_conv_desc.nprod == 2): ``(q16 float16, q8 uint8 e4m3, q8l uint8 e4m3)`` with the tensor's shape.  ``q_fresh`` is the channel
+    range ``(first, end)`` a producing convolution has just written there (one-shot: the consuming convolution clears it)."""
+
+    __slots__ = ("hi", "lo", "q", "q_fresh")
 
     def __init__(self, hi, lo=None):
         self.hi = hi
         self.lo = lo
+        self.q = None
+        self.q_fresh = None
+
+    def ensure_q(self):
+        if self.q is None:
+            if not self.hi.is_contiguous():
+                raise ValueError("quantised operand planes need a dense tensor")
+            dev, shape = self.hi.device, self.hi.shape
+            self.q = (torch.empty(shape, dtype=torch.float16, device=dev), torch.empty(shape, dtype=torch.uint8, device=dev),
+                      torch.empty(shape, dtype=torch.uint8, device=dev))
+        return self.q
 
     @property
     def shape(self):
@@ -54,18 +69,29 @@ class SplitTensor(object):
 
     @staticmethod
     def empty(shape, device, split=True, zero=False):
+        """Both planes are halves of ONE allocation (lo right above hi): a tensor map can then address them as one tensor with a plane
+        dimension, which lets the halo convolution fetch hi and lo weight tiles with a single TMA box (csrc/conv_halo.cu)."""
         mk = torch.zeros if zero else torch.empty
-        hi = mk(shape, dtype=torch.bfloat16, device=device)
-        lo = mk(shape, dtype=torch.bfloat16, device=device) if split else None
-        return SplitTensor(hi, lo)
+        if not split:
+            return SplitTensor(mk(shape, dtype=torch.bfloat16, device=device), None)
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        if numel % 64:          # keep both planes 128-byte aligned
+            return SplitTensor(mk(shape, dtype=torch.bfloat16, device=device), mk(shape, dtype=torch.bfloat16, device=device))
+        both = mk((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
+        return SplitTensor(both[0], both[1])
 
     @staticmethod
     def from_float(x, split=True):
         """Host-side packing helper (weights, test inputs): fp32 -> hi/lo bf16."""
         x = x.float().contiguous()
-        hi = x.to(torch.bfloat16)
-        lo = (x - hi.float()).to(torch.bfloat16) if split else None
-        return SplitTensor(hi, lo)
+        if not split:
+            return SplitTensor(x.to(torch.bfloat16), None)
+        out = SplitTensor.empty(x.shape, x.device, True)
+        out.hi.copy_(x)
+        out.lo.copy_(x - out.hi.float())
+        return out
 
     def float(self):
         return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
@@ -156,10 +182,39 @@ def products(n):
         _NPROD = prev
 
 
+_QUANT = False      # the running launch sequence asks for the two-unit arithmetic where a convolution's shape allows it (quant())
+QUANT_FUSE = os.environ.get("HUPR_QUANT_FUSE", "1") != "0"      # A/B switch: producers write the planes vs a separate pass per consumer
+
+
+@contextlib.contextmanager
+def quant(on=True):
+    """Convolutions in the block whose shape the two-unit kernel handles (3-tap, cout a multiple of 128, enough tiles) run with
+    hupr_conv_desc.nprod == 2: fp16 main product + e4m3 cross terms (include/hupr_b200.h; ~1e-4 whole-network error instead of 3e-5,
+    2/3 of the tensor-core work).  Inference only: the planes' fixed scales assume activation magnitudes (|x| < 224), not gradients."""
+    global _QUANT
+    prev, _QUANT = _QUANT, bool(on)
+    try:
+        yield
+    finally:
+        _QUANT = prev
+
+
+def quantize_planes(t, ch_off=0, ch=None, is_weight=False):
+    """hupr_quantize_planes: fill ``t.q`` (allocated on first use) for channels [ch_off, ch_off + ch) from the hi/lo planes."""
+    q16, q8, q8l = t.ensure_q()
+    ld = t.hi.shape[-1]
+    ch = ld - ch_off if ch is None else ch
+    rows = t.hi.numel() // ld
+    with torch.cuda.device(t.hi.device), _timed("quantize_planes"):
+        _C.check(_C.lib().hupr_quantize_planes(t.hi.data_ptr(), _C.optr(t.lo), rows, ld, ch_off, ch, q16.data_ptr(), q8.data_ptr(),
+                                               q8l.data_ptr(), 1 if is_weight else 0, _C.stream_ptr()), "hupr_quantize_planes")
+    return t.q
+
+
 def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0, w_batched=False,
               scale=None, shift=None, slope=None, residual=None, r_ch_off=0,
               out=None, o_ch_off=0, out_f32=None, w_ld=0, w_ch_off=0, k_split=0, w_k_off=0, row_vec=None, row_mode=0, coop=True, tma_store=True,
-              nprod=None, lcin=None, lcout=None, lrows=None, stats=None):
+              nprod=None, lcin=None, lcout=None, lrows=None, stats=None, out_q=False, probe=False):
     """out = act(scale * conv(a[..., a_ch_off:a_ch_off+cin], weight) + shift + residual)  — see hupr_conv_gemm.
 
     a        : SplitTensor [N, D, H, W, Ca]
@@ -168,6 +223,8 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     out_f32  : fp32 tensor [N, Dout, H, W, ld]
     lcin, lcout, lrows : LOGICAL contraction / output widths / GEMM rows of the reference layer when the call is zero-padded to the
                          kernel's 64-channel / 128-row granularity — only used for the algorithmic FLOP count of the profile.
+    out_q    : also store ``out`` as quantised operand planes (``out.q``) for a following two-unit convolution (see quant())
+    probe    : do not launch; return True when this call would run on the two-unit kernel (inside quant())
     """
     n, d, h, w, ca = a.hi.shape
     desc = _C.ConvDesc()
@@ -206,10 +263,32 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
         desc.o_ld, desc.o_ch_off = out.hi.shape[-1], o_ch_off
     if out_f32 is not None:
         desc.o_f32, desc.o_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
+    use_q = False
+    if _QUANT and kernel[1] == 3 and desc.nprod in (0, 3) and a.lo is not None and weight.lo is not None and stats is None:
+        desc.nprod = 2
+        use_q = _C.lib().hupr_conv_quant_eligible(desc) == 1
+        if use_q and weight.q is None and torch.cuda.is_current_stream_capturing():
+            use_q = False               # weight planes are made by an eager warm-up pass, never inside a captured graph
+        if not use_q:
+            desc.nprod = 3
+    if probe:
+        return use_q
+    if use_q:
+        if weight.q is None:
+            quantize_planes(weight, is_weight=True)
+        span = (a_ch_off, a_ch_off + min(cin, ca - a_ch_off))
+        if a.q is None or a.q_fresh is None or a.q_fresh[0] > span[0] or a.q_fresh[1] < span[1]:
+            quantize_planes(a, span[0], span[1] - span[0])
+        a.q_fresh = None                # one-shot: whoever rewrites `a` must refresh the planes
+        desc.a_q16, desc.a_q8, desc.a_q8l = (t.data_ptr() for t in a.q)
+        desc.w_q16, desc.w_q8, desc.w_q8l = (t.data_ptr() for t in weight.q)
+    if out_q and out is not None and QUANT_FUSE:
+        desc.o_q16, desc.o_q8, desc.o_q8l = (t.data_ptr() for t in out.ensure_q())
+        out.q_fresh = (o_ch_off, o_ch_off + cout)
     d_out = d + 2 * pad[0] - kernel[0] + 1
     rows = n * d_out * h * w if lrows is None else lrows
     flops = 2.0 * rows * (cout if lcout is None else lcout) * (min(cin, ca - a_ch_off) if lcin is None else lcin) * kernel[0] * kernel[1] * kernel[2]
-    tag = "conv_gemm.%s" % ("attn" if w_batched else ("k%dx%dx%d" % tuple(kernel)))
+    tag = "conv_gemm.%s%s" % ("attn" if w_batched else ("k%dx%dx%d" % tuple(kernel)), ".q" if use_q else "")
     with torch.cuda.device(a.hi.device), _timed(tag, flops):
         _C.check(_C.lib().hupr_conv_gemm(desc, _C.stream_ptr()), "hupr_conv_gemm")
     return out if out is not None else out_f32

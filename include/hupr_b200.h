@@ -107,14 +107,37 @@ typedef struct hupr_conv_desc {
                                                                      epilogue applies (row tiles: w a multiple of 128, bf16 split output) — for A/B measurements */
     int nprod;                                                    /* tensor-core products per k-step: 0 = by operands (3 when the lo planes are given, else 1);
                                                                      1 = hi*hi only although lo planes exist (they are not read): plain bf16 compute with fp32
-                                                                     accumulation, the precision BASELINE.json configs[3] names for training; 3 = require lo planes */
+                                                                     accumulation, the precision BASELINE.json configs[3] names for training; 3 = require lo planes;
+                                                                     2 = the quantised-cross-term arithmetic below where the shape allows it (else 3) */
     double* stats; int stats_ld;                                  /* optional: per-output-channel sums of the epilogue values over all positions, ADDED to
                                                                      stats[co] (sum v) and stats[stats_ld + co] (sum v^2); zero-filled by the caller.  Fuses the
                                                                      batch statistics of a train-mode nn.BatchNorm3d (/root/reference/models/layers.py:45-53)
                                                                      into the convolution that produces its input */
+    /* Two-unit arithmetic for the 3-tap convolutions (nprod == 2): with x = x16 + xl, the product a*w is evaluated as
+     *   a16*w16 (fp16 operands, full tensor rate)  +  al*w  +  a*wl  (both cross terms as e4m3 x e4m3 products at twice the rate)
+     * into ONE fp32 accumulator: 1 + 1/2 + 1/2 = 2 tensor units per k-step instead of the 3 bf16 products, ~2^-13 relative per product
+     * (measured whole-network error: DESIGN.md §3).  The operands carry fixed power-of-two scales so that every product is scaled by
+     * 2^16 (undone exactly in the epilogue):  a_q16 = fp16(a * 2^4), a_q8 = e4m3(a * 2^1), a_q8l = e4m3((a - a16) * 2^12);
+     * w_q16 = fp16(w * 2^12), w_q8 = e4m3(w * 2^4), w_q8l = e4m3((w - w16) * 2^15); conversions saturate (|a| < 224 keeps full accuracy,
+     * |a| < 4094 stays finite).  Planes have the geometry of a_hi / w_hi (same ca, a_ch_off, w_ld, ...), 1 byte per element for the e4m3
+     * ones; hupr_quantize_planes writes them, or a producing hupr_conv_gemm call does through o_q*.  All six NULL = not available. */
+    const void* a_q16; const void* a_q8; const void* a_q8l;
+    const void* w_q16; const void* w_q8; const void* w_q8l;
+    void* o_q16; void* o_q8; void* o_q8l;                         /* optional: ALSO store the output as activation planes of that form ([positions][o_ld]
+                                                                     at o_ch_off like o_hi), for a following nprod == 2 convolution; needs o_hi */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
+
+/* 1 when hupr_conv_gemm would run `desc` (with nprod == 2 and its quantised operand planes) on the two-unit kernel, 0 when it would fall
+ * back to the three bf16 products (shape not handled there), negative = HUPR_ERR_*.  Lets a caller skip producing planes nobody reads. */
+int hupr_conv_quant_eligible(const hupr_conv_desc* desc);
+
+/* The operand planes of the two-unit arithmetic from a bf16 split tensor: rows x [ch_off, ch_off + ch) of [rows][ld] (ch a multiple of 8).
+ * is_weight selects the scale set (0: activation 2^4 / 2^1 / 2^12, 1: weight 2^12 / 2^4 / 2^15).  q16: fp16 [rows][ld]; q8, q8l: e4m3 bytes
+ * [rows][ld].  lo may be NULL. */
+int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, void* q8l,
+                         int is_weight, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused spatial attention (flash-style: the [S, S] logits never leave the SM).  Replaces

@@ -172,8 +172,10 @@ def test_argmax_and_loss_match_oracle(golden_dir):
     assert p.tolist() == [[7.0, 5.0], [0.0, 0.0]]
 
 
-@pytest.mark.parametrize("batch,seed", [(1, 0), (2, 5)])
-def test_huprnet_forward_matches_oracle_and_reference_golden(batch, seed, golden_dir):
+@pytest.mark.parametrize("batch,seed,quant", [(1, 0, True), (2, 5, True), (2, 5, False)])
+def test_huprnet_forward_matches_oracle_and_reference_golden(batch, seed, quant, golden_dir):
+    """``quant``: the default arithmetic (two-unit 3-tap convolutions where the shape allows: fp16 main product + e4m3 cross terms) vs the
+    three bf16 products everywhere; the same 1e-3 bar for the heat maps, a wider bound on the intermediate encoder features."""
     from hupr_b200 import ops
     from hupr_b200.models import HuPRNet
     from oracle import model as om
@@ -182,6 +184,7 @@ def test_huprnet_forward_matches_oracle_and_reference_golden(batch, seed, golden
     net = HuPRNet(make_cfg())
     net.load_state_dict(sd)
     net = net.cuda().eval()
+    net.quant_cross_terms = quant
     hori, vert = om.make_vrdae(batch, seed)
     heat, gcn = net(hori.cuda(), vert.cuda())
     torch.cuda.synchronize()
@@ -193,7 +196,7 @@ def test_huprnet_forward_matches_oracle_and_reference_golden(batch, seed, golden
                            ("enc_ra.f3", plan["enc_ra"].f3, inter["feats_ra"][2]), ("enc_re.f3", plan["enc_re"].f3, inter["feats_re"][2])):
         e = rel_err(cl_to_ncdhw(got, ref.shape[1])[:, :, 0], ref)
         print("%s rel err %.3g" % (name, e))
-        assert e < 1e-4, name
+        assert e < (4e-4 if quant else 1e-4), name
     logits = plan["dec"].logits_out[..., :14].reshape(batch, 64, 64, 14).permute(0, 3, 1, 2).cpu()
     print("logits rel err %.3g" % rel_err(logits, inter["logits"]))
     e_heat, e_gcn = rel_err(heat, ref_heat), rel_err(gcn, ref_gcn)

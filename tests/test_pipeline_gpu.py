@@ -102,6 +102,9 @@ def test_batch_32_stream_equals_single_window_streams():
     net = HuPRNet(make_cfg())
     net.load_state_dict(om.make_state_dict(3))
     net = net.cuda().eval()
+    # the property is about batching, so both sides use the same arithmetic everywhere: the opt-in two-unit convolutions only engage where a
+    # launch has enough tiles, i.e. on more layers at batch 32 than at batch 1
+    net.quant_cross_terms = False
     big = RadarPoseStream(net, 32, "cuda", use_graph=False).prepare()
     gen = torch.Generator(device="cuda").manual_seed(5)
     big.adc.copy_(torch.randint(-2048, 2048, big.adc.shape, generator=gen, dtype=torch.int16, device="cuda"))
@@ -138,8 +141,13 @@ def test_batch_32_stream_matches_oracle_forward_on_all_32_windows():
     kp = win.step().clone()
     heat, gcn = win.heatmap.reshape(32, 14, 64, 64).cpu(), win.gcn_heatmap.reshape(32, 14, 64, 64).cpu()
     vh, vv = win.vrdae_hori.cpu(), win.vrdae_vert.cpu()
+    # the same step with the opt-in two-unit convolutions (HuPRNet.quant_cross_terms: fp16 main product + e4m3 cross terms)
+    net.quant_cross_terms = True
+    kp_q = win.step().clone()
+    heat_q, gcn_q = win.heatmap.reshape(32, 14, 64, 64).cpu(), win.gcn_heatmap.reshape(32, 14, 64, 64).cpu()
+    net.quant_cross_terms = False
     torch.cuda.synchronize()
-    worst, worst_abs, smallest = 0.0, 0.0, 1.0
+    worst, worst_abs, smallest, worst_q = 0.0, 0.0, 1.0, 0.0
     for c in range(0, 32, 8):
         with torch.no_grad():
             ref_heat, ref_gcn = om.huprnet_forward(sd, vh[c:c + 8], vv[c:c + 8])
@@ -152,8 +160,14 @@ def test_batch_32_stream_matches_oracle_forward_on_all_32_windows():
         assert e1 < 1e-3 and e2 < 1e-3, (c, e1, e2)
         ref_kp, _ = ol.get_max_preds(ref_gcn.numpy())
         assert np.array_equal(kp[c:c + 8].cpu().numpy(), ref_kp), c
+        q1 = float(((heat_q[c:c + 8] - ref_heat).abs() / ref_heat.abs()).max())
+        q2 = float(((gcn_q[c:c + 8] - ref_gcn).abs() / ref_gcn.abs()).max())
+        worst_q = max(worst_q, q1, q2)
+        assert q1 < 1e-3 and q2 < 1e-3, (c, q1, q2)
+        assert np.array_equal(kp_q[c:c + 8].cpu().numpy(), ref_kp), c
     print("batch-32 stream vs oracle, all 32 windows: max element-wise relative heat-map error %.3g (max absolute error %.3g on maps in (0, 1); "
-          "smallest reference value %.3g — the relative figure is set by the near-zero cells)" % (worst, worst_abs, smallest))
+          "smallest reference value %.3g — the relative figure is set by the near-zero cells); with the two-unit convolutions %.3g"
+          % (worst, worst_abs, smallest, worst_q))
     # the variant bench.py times (per-frame features, overlapping window views, CUDA graph) on the same ADC words
     pf = RadarPoseStream(net, 32, "cuda", use_graph=True, per_frame=True).prepare()
     pf.adc.copy_(win.adc)

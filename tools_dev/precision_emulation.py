@@ -38,9 +38,32 @@ def q8(x):
     return (x * s).to(torch.float8_e4m3fn).float() / s
 
 
-def contract(fn, a, b):
+def e4m3(x, shift):
+    """e4m3 of x * 2**shift with saturation at +-448 (cvt.rn.satfinite.e4m3x2.f32), returned UNscaled."""
+    s = 2.0 ** shift
+    return (x * s).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float() / s
+
+
+def contract_halo_f16f8(fn, a, w):
+    """The scheme csrc/conv_halo.cu would run for the 3x3(x3) convolutions only (every other contraction stays bf16x3):
+    main product fp16(a * 2^4) x fp16(w * 2^12), cross terms e4m3(a_lo * 2^12) x e4m3(w * 2^4) and e4m3(a * 2^1) x e4m3(w_lo * 2^15),
+    all three at the common scale 2^16 in ONE fp32 accumulator; fixed scales, saturating conversions."""
+    a16 = (a * 16.0).clamp(-65504.0, 65504.0).to(torch.float16).float() / 16.0
+    w16 = (w * 4096.0).clamp(-65504.0, 65504.0).to(torch.float16).float() / 4096.0
+    a_lo, w_lo = a - a16, w - w16
+    return fn(a16, w16) + fn(e4m3(a_lo, 12), e4m3(w, 4)) + fn(e4m3(a, 1), e4m3(w_lo, 15))
+
+
+def contract(fn, a, b, halo=False):
     if MODE is None:
         return fn(a, b)
+    if MODE == "halo-f16f8":
+        if halo:
+            return contract_halo_f16f8(fn, a, b)
+        dt = torch.bfloat16
+        a_hi, a_lo = hi_lo(a, dt)
+        b_hi, b_lo = hi_lo(b, dt)
+        return fn(a_hi, b_hi) + fn(a_lo.to(dt).float(), b_hi) + fn(a_hi, b_lo.to(dt).float())
     if MODE in ("bf16x1", "fp16x1"):
         dt = torch.bfloat16 if MODE == "bf16x1" else torch.float16
         return fn(a.to(dt).float(), b.to(dt).float())
@@ -54,10 +77,13 @@ def contract(fn, a, b):
 
 
 def install():
-    F.conv3d = lambda x, w, bias=None, **k: contract(lambda a, b: _conv3d(a, b, **k), x, w) + (0 if bias is None else bias.view(1, -1, 1, 1, 1))
-    F.conv2d = lambda x, w, bias=None, **k: contract(lambda a, b: _conv2d(a, b, **k), x, w) + (0 if bias is None else bias.view(1, -1, 1, 1))
+    F.conv3d = lambda x, w, bias=None, **k: contract(lambda a, b: _conv3d(a, b, **k), x, w, halo=w.shape[-2] == 3) + (0 if bias is None else bias.view(1, -1, 1, 1, 1))
+    F.conv2d = lambda x, w, bias=None, **k: contract(lambda a, b: _conv2d(a, b, **k), x, w, halo=w.shape[-2] == 3) + (0 if bias is None else bias.view(1, -1, 1, 1))
     om.torch.einsum = lambda eq, a, b: contract(lambda p, q: _einsum(eq, p, q), a, b)
     om.torch.matmul = lambda a, b: contract(_matmul, a, b)
+
+
+MODES = ("bf16x3", "bf16x1", "fp16x1", "bf16+fp8x", "fp16+fp8x", "halo-f16f8")
 
 
 def main(n_seeds):
@@ -71,7 +97,7 @@ def main(n_seeds):
         with torch.no_grad():
             rh, rg = om.huprnet_forward(sd, h, v)
         rk, _ = oloss.get_max_preds(rg.view(1, 14, 64, 64).numpy())
-        for m in ("bf16x3", "bf16x1", "fp16x1", "bf16+fp8x", "fp16+fp8x"):
+        for m in MODES:
             MODE = m
             with torch.no_grad():
                 gh, gg = om.huprnet_forward(sd, h, v)
@@ -85,4 +111,6 @@ def main(n_seeds):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        MODES = tuple(sys.argv[2].split(","))
     main(int(sys.argv[1]) if len(sys.argv) > 1 else 3)

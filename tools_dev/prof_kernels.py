@@ -74,3 +74,12 @@ if which in ("attnbwd",):
         ops.conv_gemm(q, c, k, s_, w_batched=True, out=ds, residual=probs, row_vec=lse, row_mode=2)
 torch.cuda.synchronize()
 print("done")
+if which in ("conv128_q",):
+    # two-unit arithmetic (fp16 main product + e4m3 cross terms) on the same 64 -> 128 channel 3x3x3 layer as "conv128"
+    x = SplitTensor.from_float(torch.randn(b, 8, 64, 64, 64, device="cuda"))
+    w = SplitTensor.from_float(torch.randn(27, 128, 64, device="cuda") * 0.02)
+    out = SplitTensor.empty((b, 8, 64, 64, 128), "cuda")
+    with ops.quant():
+        for _ in range(3):
+            ops.conv_gemm(x, 64, w, 128, kernel=(3, 3, 3), pad=(1, 1, 1), out=out, out_q=True)
+torch.cuda.synchronize()
