@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, bool TWO>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmA_x,      // NPROD == 2: A maps are (fp16 a16, e4m3 a, e4m3 al), B maps (w16, w, wl)
@@ -94,6 +94,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int groups = p.kd * p.kw * p.cin_blocks;      // one stage per (kd, kw, channel block): 3 kh taps x 2 accumulators
     constexpr bool three = NPROD == 3;      // compile-time: the single-thread MMA issue loop carries no runtime branches
     constexpr bool quant = NPROD == 2;      // fp16 main product + two e4m3 cross products (header comment)
+    // TWO: CTA pairs (tc.cuh).  The pair works on two neighbouring position tiles (tile = blockIdx.x + i * gridDim.x, cluster ranks = blockIdx.x
+    // parity) that share their weight column tile; each CTA keeps the BN / 2 weight rows n0 + rank * BN / 2 ... and the leader's M = 256 MMAs
+    // fill both CTAs' accumulators.
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    constexpr int BROWS = TWO ? BN / 2 : BN;
+    static_assert(!TWO || BN == 128, "CTA pairs: cout = 128 tiles");
     constexpr bool ncat = (BN == 64 && NPROD == 3);         // [w_hi | w_lo] as one N = 128 operand (header comment)
     constexpr int ACC = ncat ? 128 : BN;                    // TMEM columns of one accumulator
     constexpr int TMEM_COLS = 4 * ACC;                      // two sets x two accumulators
@@ -106,18 +113,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&accum_full[s], 1);
-            mbar_init(&accum_empty[s], 256);
+            mbar_init(&accum_empty[s], TWO ? 512 : 256);      // TWO: the leader's barrier collects both CTAs' epilogue threads
         }
         fence_mbar_init();
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
         if (quant) { prefetch_tmap(&tmA_x); prefetch_tmap(&tmB_x); }
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (TWO) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();      // both CTAs' barriers are initialised and their tensor memory allocated before anything crosses over
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();                  // programmatic dependent launch: the predecessor's writes are visible from here on (common.cuh)
@@ -145,8 +158,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const int s = sidx;
                     mbar_wait(&empty[s], sph ^ 1u);
                     uint8_t* st = smem + s * g.stage_bytes;
-                    mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
                     const int ac = p.a_ch_off + cb * HK;
+                    if (TWO) {      // both CTAs' loads complete on the leader's barrier, which expects the bytes of both
+                        if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)g.stage_bytes);
+                        uint8_t* sb2 = st + (three ? 2 : 1) * g.a_plane_bytes;
+                        const int nrow = n0 + (int)cta_rank * BROWS;
+                        tma2_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                        if (quant) {
+                            tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                            tma2_load_5d(st + g.a_plane_bytes + g.a_plane_bytes / 2, &tmA_x, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                            uint8_t* sq = st + 2 * g.a_plane_bytes;
+                            tma2_load_4d(sq, &tmB_hi, &full[s], cb * HK, nrow, tkw, tkd * 3);
+                            tma2_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, nrow, tkw, tkd * 3);
+                            tma2_load_4d(sq + 3 * g.b_tile_bytes + 3 * (g.b_tile_bytes / 2), &tmB_x, &full[s], cb * HK, nrow, tkw, tkd * 3);
+                        } else if (three) {
+                            tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                            if (g.b_merged) {
+                                tma2_load_5d(sb2, &tmB_hi, &full[s], cb * HK, nrow, 0, tkw, tkd * 3);
+                            } else {
+#pragma unroll
+                                for (int tkh = 0; tkh < 3; ++tkh) {
+                                    tma2_load_4d(sb2 + 2 * tkh * g.b_tile_bytes, &tmB_hi, &full[s], cb * HK, nrow, tkw, tkd * 3 + tkh);
+                                    tma2_load_4d(sb2 + (2 * tkh + 1) * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, nrow, tkw, tkd * 3 + tkh);
+                                }
+                            }
+                        } else {
+                            tma2_load_4d(sb2, &tmB_hi, &full[s], cb * HK, nrow, tkw, tkd * 3);
+                        }
+                        if (++cb == p.cin_blocks) {
+                            cb = 0;
+                            if (++tkw == p.kw) { tkw = 0; ++tkd; }
+                        }
+                        if (++sidx == g.stages) { sidx = 0; sph ^= 1u; }
+                        continue;
+                    }
+                    mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
                     tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                     if (three) tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                     if (quant) {       // stage = [a16 | a8 | a8l | w16 x3 | w8 x3 | w8l x3]; e4m3 planes and tiles are half the bytes
@@ -186,10 +232,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
-        if (elect_one()) {
+        if ((!TWO || leader) && elect_one()) {
             // fp32 accumulate; A / B formats: bf16 (1), or for NPROD == 2 fp16 under kind::f16 and e4m3 under kind::f8f6f4 (both 0)
             const uint32_t fmt = quant ? 0u : ((1u << 7) | (1u << 10));
-            const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);
             const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 128
             int it = 0, lt = 0, sidx = 0;
             uint32_t sph = 0;
@@ -218,10 +264,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                 const uint64_t da8 = make_smem_desc_sw32(st + g.a_plane_bytes + aoff / 2);
                                 const uint64_t da8l = make_smem_desc_sw32(st + g.a_plane_bytes + g.a_plane_bytes / 2 + aoff / 2);
                                 const uint32_t tacc = tset + (uint32_t)(a * ACC);
-                                umma_f8(tacc, da8l, db8, idesc, (uint32_t)((gi | tkh) != 0));      // (a - a16) x w   (e4m3, K = 32)
-                                umma_f8(tacc, da8, db8l, idesc, 1u);                                // a x (w - w16)
-                                umma_bf16(tacc, da16, db16, idesc, 1u);                             // a16 x w16 (fp16, K = 16 twice)
-                                umma_bf16(tacc, da16 + 2, db16 + 2, idesc, 1u);
+                                if (TWO) {
+                                    umma2_f8(tacc, da8l, db8, idesc, (uint32_t)((gi | tkh) != 0));
+                                    umma2_f8(tacc, da8, db8l, idesc, 1u);
+                                    umma2_bf16(tacc, da16, db16, idesc, 1u);
+                                    umma2_bf16(tacc, da16 + 2, db16 + 2, idesc, 1u);
+                                } else {
+                                    umma_f8(tacc, da8l, db8, idesc, (uint32_t)((gi | tkh) != 0));      // (a - a16) x w   (e4m3, K = 32)
+                                    umma_f8(tacc, da8, db8l, idesc, 1u);                                // a x (w - w16)
+                                    umma_bf16(tacc, da16, db16, idesc, 1u);                             // a16 x w16 (fp16, K = 16 twice)
+                                    umma_bf16(tacc, da16 + 2, db16 + 2, idesc, 1u);
+                                }
                             }
                         }
                     }
@@ -243,19 +296,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc_cat, acc_flag);      // a_hi x [w_hi | w_lo] -> columns 0..127
                                     umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, 1u);                // a_lo x w_hi -> columns 0..63
                                 } else if (three) {
-                                    umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
-                                    umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
-                                    umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                                    if (TWO) {
+                                        umma2_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
+                                        umma2_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                                        umma2_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                                    } else {
+                                        umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, acc_flag);
+                                        umma_bf16(tacc, da_hi + koff, db_lo + koff, idesc, 1u);
+                                        umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, 1u);
+                                    }
+                                } else if (TWO) {
+                                    umma2_bf16(tacc, da_hi + koff, db_hi + koff, idesc, acc_flag);
                                 } else {
                                     umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc, acc_flag);
                                 }
                             }
                         }
                     }
-                    tc_commit(&empty[s]);
+                    if (TWO) tc_commit2(&empty[s]); else tc_commit(&empty[s]);
                     if (++sidx == g.stages) { sidx = 0; sph ^= 1u; }
                 }
-                tc_commit(&accum_full[as]);
+                if (TWO) tc_commit2(&accum_full[as]); else tc_commit(&accum_full[as]);
             }
         }
     } else {
@@ -301,7 +362,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
                     if (c == BN / 32 - 1) {                // this thread's last TMEM read of the set: hand it back before the stores
                         tc_fence_before();
-                        mbar_arrive(&accum_empty[as]);
+                        if (TWO) mbar_arrive_leader(&accum_empty[as]); else mbar_arrive(&accum_empty[as]);
                     }
                     conv_epilogue32(p, acc, pos, n0 + c * 32, p.row_mode ? __ldg(p.row_vec + pos) : 0.f, wstat + c * 32, BN, lane);
                 }
@@ -311,8 +372,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();      // the leader's MMAs read the peer's shared memory and write its tensor memory until its last tile is done
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -349,12 +412,62 @@ static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int 
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
+// CTA-pair launch (conv_halo_kernel<.., true>): clusters of two CTAs, as many as can be co-resident (a persistent kernel must not queue).
+template <int BN, int NPROD>
+static int launch_halo_pairs(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& a_x, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                             const CUtensorMap& b_x, const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
+    static bool configured[kMaxDevices] = {};
+    static int max_clusters[kMaxDevices] = {};
+    const int smem_max = 232448;
+    auto kernel = conv_halo_kernel<BN, NPROD, true>;
+    if (int crc = ensure_smem_optin(kernel, smem_max, configured)) return crc;
+    const int smem = g.stages * g.stage_bytes + 1024 + 256 + kHaloStatBytes;
+    if (smem > smem_max) return HUPR_ERR_BAD_ARG;
+    HaloGeom gg = g;
+    gg.m_tiles = m_tiles;
+    gg.n_tiles = p.cout / BN;
+    const int pairs = gg.m_tiles * gg.n_tiles / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kHaloThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int dev = device_index();
+    if (dev < 0 || dev >= kMaxDevices) return HUPR_ERR_CUDA;
+    if (max_clusters[dev] == 0) {
+        cfg.gridDim = dim3(2 * device_sm_count(), 1, 1);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) return HUPR_ERR_CUDA;
+        max_clusters[dev] = n;
+    }
+    int clusters = pairs < max_clusters[dev] ? pairs : max_clusters[dev];
+    if (const char* cap = getenv("HUPR_HALO_GRID")) {
+        const int c = atoi(cap) / 2;
+        if (c > 0 && c < clusters) clusters = c;
+    }
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    if (pdl_enabled()) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, a_hi, a_lo, a_x, b_hi, b_lo, b_x, p, gg);
+    note_launches(1);
+    return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
+}
+
 template <int BN, int NPROD>
 static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& a_x, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const CUtensorMap& b_x, const ConvParams& p, const HaloGeom& g, int m_tiles, cudaStream_t stream) {
     static bool configured[kMaxDevices] = {};
     const int smem_max = 232448;
-    if (int crc = ensure_smem_optin(conv_halo_kernel<BN, NPROD>, smem_max, configured)) return crc;
+    if (int crc = ensure_smem_optin(conv_halo_kernel<BN, NPROD, false>, smem_max, configured)) return crc;
     const int smem = g.stages * g.stage_bytes + 1024 + 256 + kHaloStatBytes;
     if (smem > smem_max) return HUPR_ERR_BAD_ARG;
     const int num_sms = device_sm_count();
@@ -369,7 +482,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
         if (c > 0 && c < ctas) ctas = c;
     }
     dim3 grid(ctas, 1, 1);
-    launch_k(conv_halo_kernel<BN, NPROD>, grid, dim3(kHaloThreads), (size_t)smem, stream, a_hi, a_lo, a_x, b_hi, b_lo, b_x, p, gg);
+    launch_k(conv_halo_kernel<BN, NPROD, false>, grid, dim3(kHaloThreads), (size_t)smem, stream, a_hi, a_lo, a_x, b_hi, b_lo, b_x, p, gg);
     note_launches(1);
     return cudaGetLastError() == cudaSuccess ? HUPR_OK : HUPR_ERR_CUDA;
 }
@@ -397,11 +510,14 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     ConvParams p = base;
     p.bw = bw; p.bh = bh; p.tiles_w = 1; p.tiles_h = d->h / bh;
     p.cin_blocks = cin_eff / HK;
+    // CTA pairs (cta_group::2 MMAs, each CTA holds half of the weight rows): cout = 128 tiles, an even number of position tiles so that the
+    // two CTAs of a pair always share their weight column tile; HUPR_HALO_SINGLE=1 is the A/B switch
+    const bool pairs = bn == 128 && m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
     HaloGeom g;
     g.b_merged = 0;
     g.halo_rows = (bh + 2) * bw;
     g.a_plane_bytes = g.halo_rows * 64;
-    g.b_tile_bytes = bn * 64;
+    g.b_tile_bytes = (pairs ? bn / 2 : bn) * 64;
     g.nprod = three ? 3 : 1;
     g.stage_bytes = (three ? 2 : 1) * (g.a_plane_bytes + 3 * g.b_tile_bytes);
     g.stages = (232448 - 1024 - 256 - kHaloStatBytes) / g.stage_bytes;
@@ -427,11 +543,13 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
         const char* w16 = static_cast<const char*>(d->w_q16) + (size_t)d->w_ch_off * 2;
         const char* w8 = static_cast<const char*>(d->w_q8) + d->w_ch_off;
         const char* w8l = static_cast<const char*>(d->w_q8l) + d->w_ch_off;
-        if ((rc = encode_halo_wgt_map(&b16, w16, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_wgt_map(&b8, w8, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3, 1)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_wgt_map(&b8l, w8l, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3, 1)) != HUPR_OK) return rc;
+        const int brows = pairs ? bn / 2 : bn;
+        if ((rc = encode_halo_wgt_map(&b16, w16, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b8, w8, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3, 1)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b8l, w8l, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3, 1)) != HUPR_OK) return rc;
         g.nprod = 2;
         p.acc_scale = 1.0f / 65536.0f;
+        if (pairs) return launch_halo_pairs<128, 2>(a16, a8, a8l, b16, b8, b8l, p, g, m_tiles, stream);
         return launch_halo<128, 2>(a16, a8, a8l, b16, b8, b8l, p, g, m_tiles, stream);
     }
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
@@ -450,7 +568,7 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
             if (!fn) return HUPR_ERR_CUDA;
             cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->cout, 2, (cuuint64_t)d->kw, (cuuint64_t)d->kd * 3};
             cuuint64_t strides[4] = {(cuuint64_t)w_ld * 2, (cuuint64_t)plane, (cuuint64_t)d->cout * w_ld * 2, (cuuint64_t)d->kw * d->cout * w_ld * 2};
-            cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bn, 2, 1, 3};
+            cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)(pairs ? bn / 2 : bn), 2, 1, 3};
             cuuint32_t estr[5] = {1, 1, 1, 1, 1};
             if (fn(&b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(w_hi), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
@@ -459,13 +577,16 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
             }
         }
         if (!g.b_merged) {
-            if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 1)) != HUPR_OK) return rc;
-            if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 1)) != HUPR_OK) return rc;
+            if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, pairs ? bn / 2 : bn, w_ld, 1)) != HUPR_OK) return rc;
+            if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, d->kd, d->kw, pairs ? bn / 2 : bn, w_ld, 1)) != HUPR_OK) return rc;
         }
     } else {
-        if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, bn, w_ld, 3)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, pairs ? bn / 2 : bn, w_ld, 3)) != HUPR_OK) return rc;
         b_lo = b_hi;
     }
+    if (pairs)
+        return three ? launch_halo_pairs<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
+                     : launch_halo_pairs<128, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
     if (three)
         return bn == 128 ? launch_halo<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
                          : launch_halo<64, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);

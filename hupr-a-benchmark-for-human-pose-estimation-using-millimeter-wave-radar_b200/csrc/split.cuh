@@ -55,8 +55,8 @@ struct QuantScales {
 };
 __device__ __forceinline__ QuantScales quant_scales(bool is_weight) {
     QuantScales q;
-    q.s16 = is_weight ? 4096.f : 16.f;
-    q.inv16 = is_weight ? 1.f / 4096.f : 1.f / 16.f;
+    q.s16 = is_weight ? 16384.f : 4.f;          // fp16 plane: activations up to 16 376, weights up to 3.99 before saturation
+    q.inv16 = is_weight ? 1.f / 16384.f : 1.f / 4.f;
     q.s8 = is_weight ? 16.f : 2.f;
     q.s8l = is_weight ? 32768.f : 4096.f;
     return q;

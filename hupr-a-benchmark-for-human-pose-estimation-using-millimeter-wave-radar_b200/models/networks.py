@@ -111,13 +111,14 @@ class HuPRNet(nn.Module):
         """``split=True``: bf16 hi/lo activations and weights, three tensor-core products per k-step — fp32-equivalent
         results (the reference computes in fp32).  ``split=False``: single bf16 product (faster, ~1e-2 accuracy).
 
-        ``quant_cross_terms`` (attribute, default False unless HUPR_QUANT=1; eval-mode ``split`` forward only): the large 3-tap
-        convolutions evaluate the two hi*lo cross terms as e4m3 products next to an fp16 main product (ops.quant; two tensor units per
-        k-step instead of three).  Parity-green (heat maps well inside the 1e-3 bar, keypoints unchanged; activations are assumed
-        |x| < 224 for full accuracy, finite up to 4094) but NOT faster on a B200: the halo kernels are bound by L2 -> shared-memory
-        operand delivery, which this arithmetic leaves unchanged (profiles/r02_halo128_q_*), so it stays opt-in."""
+        ``quant_cross_terms`` (attribute, default True unless HUPR_QUANT=0; eval-mode ``split`` forward only): the large 3-tap
+        convolutions (cout a multiple of 128, enough tiles to fill the GPU) evaluate the two hi*lo cross terms as e4m3 products next to an
+        fp16 main product (ops.quant: two tensor units per k-step instead of three).  Heat maps stay well inside the 1e-3
+        bar (tests/test_model_gpu.py, tests/test_pipeline_gpu.py: the error against the oracle is the same size as with three bf16
+        products), keypoints unchanged.  Range: activations keep full accuracy for |x| < 224 and must stay below 16 376 (fp16 plane);
+        filters with a weight >= 3.99 keep the three bf16 products automatically.  Set False for three bf16 products everywhere."""
         super(HuPRNet, self).__init__()
-        self.quant_cross_terms = os.environ.get("HUPR_QUANT", "0") == "1"
+        self.quant_cross_terms = os.environ.get("HUPR_QUANT", "1") != "0"
         self.numFrames = cfg.DATASET.numFrames
         self.numFilters = nf = cfg.MODEL.numFilters
         self.rangeSize = cfg.DATASET.rangeSize

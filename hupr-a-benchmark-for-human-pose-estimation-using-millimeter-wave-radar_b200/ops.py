@@ -189,8 +189,9 @@ QUANT_FUSE = os.environ.get("HUPR_QUANT_FUSE", "1") != "0"      # A/B switch: pr
 @contextlib.contextmanager
 def quant(on=True):
     """Convolutions in the block whose shape the two-unit kernel handles (3-tap, cout a multiple of 128, enough tiles) run with
-    hupr_conv_desc.nprod == 2: fp16 main product + e4m3 cross terms (include/hupr_b200.h; ~1e-4 whole-network error instead of 3e-5,
-    2/3 of the tensor-core work).  Inference only: the planes' fixed scales assume activation magnitudes (|x| < 224), not gradients."""
+    hupr_conv_desc.nprod == 2: fp16 main product + e4m3 cross terms (include/hupr_b200.h; 2/3 of the tensor-core work, error of the same
+    order as the three bf16 products).  Inference only: the planes' fixed scales assume activation magnitudes (full accuracy for
+    |x| < 224, hard limit 16 376; weights below 3.99 — checked when their planes are made), not gradients."""
     global _QUANT
     prev, _QUANT = _QUANT, bool(on)
     try:
@@ -267,15 +268,20 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     if _QUANT and kernel[1] == 3 and desc.nprod in (0, 3) and a.lo is not None and weight.lo is not None and stats is None:
         desc.nprod = 2
         use_q = _C.lib().hupr_conv_quant_eligible(desc) == 1
-        if use_q and weight.q is None and torch.cuda.is_current_stream_capturing():
-            use_q = False               # weight planes are made by an eager warm-up pass, never inside a captured graph
+        if use_q and weight.q is None:
+            if torch.cuda.is_current_stream_capturing():
+                use_q = False           # weight planes are made by an eager warm-up pass, never inside a captured graph
+            elif float(weight.hi.abs().max()) >= 3.99:
+                weight.q = False        # outside the fp16 plane's range (w * 2^14): this filter keeps the three bf16 products
+            else:
+                quantize_planes(weight, is_weight=True)
+        if weight.q is False:
+            use_q = False
         if not use_q:
             desc.nprod = 3
     if probe:
         return use_q
     if use_q:
-        if weight.q is None:
-            quantize_planes(weight, is_weight=True)
         span = (a_ch_off, a_ch_off + min(cin, ca - a_ch_off))
         if a.q is None or a.q_fresh is None or a.q_fresh[0] > span[0] or a.q_fresh[1] < span[1]:
             quantize_planes(a, span[0], span[1] - span[0])

@@ -20,7 +20,7 @@ def _e4m3(x, scale):
 
 def _planes(x, is_weight):
     """(x16, x8, x8l) as UNscaled float32 values, rounded the way hupr_quantize_planes rounds them."""
-    s16, s8, s8l = (4096.0, 16.0, 32768.0) if is_weight else (16.0, 2.0, 4096.0)
+    s16, s8, s8l = (16384.0, 16.0, 32768.0) if is_weight else (4.0, 2.0, 4096.0)
     x16 = (x * s16).clamp(-65504.0, 65504.0).to(torch.float16).float() / s16
     return x16, _e4m3(x, s8), _e4m3(x - x16, s8l)
 
@@ -40,7 +40,7 @@ def test_quantize_planes_match_torch_roundings(is_weight):
         p.zero_()
     ops.quantize_planes(u, 16, 32, is_weight)
     torch.cuda.synchronize()
-    s16, s8, s8l = (4096.0, 16.0, 32768.0) if is_weight else (16.0, 2.0, 4096.0)
+    s16, s8, s8l = (16384.0, 16.0, 32768.0) if is_weight else (4.0, 2.0, 4096.0)
     ref16, ref8, ref8l = _planes(t.float(), is_weight)
     q16, q8, q8l = t.q
     assert torch.equal(q16.float() / s16, ref16)
@@ -100,10 +100,10 @@ def test_two_unit_conv_matches_its_emulation_and_the_fp64_convolution(n, d, hw, 
     q16, q8, q8l = out2.q
     assert out2.q_fresh == (0, cout)
     r16, r8, r8l = _planes(out2.float(), False)
-    got = q16.float() / 16.0 + q8l.view(torch.float8_e4m3fn).float() / 4096.0
+    got = q16.float() / 4.0 + q8l.view(torch.float8_e4m3fn).float() / 4096.0
     val = out2.float()
     assert float(((got - val).abs() / val.abs().clamp_min(1e-2)).max()) < 2.0 ** -14
-    assert float((q16.float() / 16.0 - r16).abs().max()) <= float(val.abs().max()) * 2.0 ** -10       # at most one fp16 ulp apart
+    assert float((q16.float() / 4.0 - r16).abs().max()) <= float(val.abs().max()) * 2.0 ** -10       # at most one fp16 ulp apart
     assert float((q8.view(torch.float8_e4m3fn).float() / 2.0 - r8).abs().max()) <= float(val.abs().max()) * 2.0 ** -3
     # a second two-unit convolution consumes them without a separate pass (q_fresh is one-shot)
     w2 = SplitTensor.from_float(torch.randn(9, 256, cout, device=DEV) * (2.0 / (9 * cout)) ** 0.5)
