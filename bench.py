@@ -83,9 +83,26 @@ class ClockSampler(object):
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "25"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            # nvidia-smi can take a second to come up on a fresh box: wait for its first line, then only count the samples taken after
+            # mark() — the ones inside the timed regions
+            deadline = time.time() + 4.0
+            while time.time() < deadline and self._lines() == 0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+        self.skip = self._lines()
+
+    def _lines(self):
+        try:
+            with open(self.path) as fp:
+                return sum(1 for _ in fp)
+        except Exception:
+            return 0
+
+    def mark(self):
+        """Call right before the timed region: samples taken so far (idle GPU) are not reported."""
+        self.skip = self._lines()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -98,7 +115,9 @@ class ClockSampler(object):
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            for i, line in enumerate(open(self.path)):
+                if i < getattr(self, "skip", 0):
+                    continue
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -519,6 +538,9 @@ def main():
         torch.manual_seed(0)
         model = HuPRNet(make_cfg(), split=not args.single_bf16).to(dev).eval()      # random-init weights of the reference architecture
         dtype = "bf16 tensor-core products, fp32 accumulate" + ("" if args.single_bf16 else " (3-product hi/lo split: fp32-equivalent)")
+        if not args.single_bf16 and model.quant_cross_terms:
+            dtype += ("; the 3-tap convolutions with cout % 128 == 0 use 2 tensor units per k-step instead (fp16 main product + the two hi*lo cross "
+                      "terms as e4m3 products, fp32 accumulate; HUPR_QUANT=0 turns this off) — heat maps within the same 1e-3 bar, keypoints identical")
         if args.workload == "e2e":
             units = args.batch
             stream = RadarPoseStream(model, units, dev).prepare()
@@ -580,8 +602,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
     sync_all()
+    if rank == 0:
+        sampler.mark()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):

@@ -100,7 +100,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     constexpr int BROWS = TWO ? BN / 2 : BN;
-    static_assert(!TWO || BN == 128, "CTA pairs: cout = 128 tiles");
+    static_assert(!TWO || BN == 128 || NPROD == 3, "CTA pairs: cout = 128 tiles, or the [w_hi | w_lo] form of the cout = 64 tiles");
     constexpr bool ncat = (BN == 64 && NPROD == 3);         // [w_hi | w_lo] as one N = 128 operand (header comment)
     constexpr int ACC = ncat ? 128 : BN;                    // TMEM columns of one accumulator
     constexpr int TMEM_COLS = 4 * ACC;                      // two sets x two accumulators
@@ -164,7 +164,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         uint8_t* sb2 = st + (three ? 2 : 1) * g.a_plane_bytes;
                         const int nrow = n0 + (int)cta_rank * BROWS;
                         tma2_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                        if (quant) {
+                        if (ncat) {
+                            // cout = 64 in pairs: the N = 128 operand [w_hi | w_lo] splits into the leader's w_hi tile and the peer's w_lo tile
+                            // (X, 64 rows each), the N = 64 operand w_hi into two 32-row halves (Y): stage B region = [X0 X1 X2 | Y0 Y1 Y2]
+                            tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                            tma2_load_4d(sb2, leader ? &tmB_hi : &tmB_lo, &full[s], cb * HK, n0, tkw, tkd * 3);
+                            tma2_load_4d(sb2 + 3 * g.b_tile_bytes, &tmB_x, &full[s], cb * HK, n0 + (int)cta_rank * 32, tkw, tkd * 3);
+                        } else if (quant) {
                             tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                             tma2_load_5d(st + g.a_plane_bytes + g.a_plane_bytes / 2, &tmA_x, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                             uint8_t* sq = st + 2 * g.a_plane_bytes;
@@ -236,7 +242,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             // fp32 accumulate; A / B formats: bf16 (1), or for NPROD == 2 fp16 under kind::f16 and e4m3 under kind::f8f6f4 (both 0)
             const uint32_t fmt = quant ? 0u : ((1u << 7) | (1u << 10));
             const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);
-            const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 128
+            const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)((TWO ? 256 : 128) >> 4) << 24);      // N = 128
             int it = 0, lt = 0, sidx = 0;
             uint32_t sph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -280,8 +286,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
 #pragma unroll
                     for (int tkh = 0; tkh < (quant ? 0 : 3); ++tkh) {
-                        const uint64_t db_hi = make_smem_desc_sw64(sb + (three ? 2 * tkh : tkh) * g.b_tile_bytes);
-                        const uint64_t db_lo = make_smem_desc_sw64(sb + (2 * tkh + 1) * g.b_tile_bytes);
+                        // (pairs with cout = 64: db_hi = this tap's X tile, db_lo = its 32-row Y tile — see the producer)
+                        const uint64_t db_hi = make_smem_desc_sw64(sb + ((TWO && ncat) ? tkh : three ? 2 * tkh : tkh) * g.b_tile_bytes);
+                        const uint64_t db_lo = make_smem_desc_sw64(sb + ((TWO && ncat) ? 3 * g.b_tile_bytes + tkh * (g.b_tile_bytes / 2)
+                                                                                      : (2 * tkh + 1) * g.b_tile_bytes));
 #pragma unroll
                         for (int a = 0; a < 2; ++a) {
                             const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
@@ -292,7 +300,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             for (int k = 0; k < HK / 16; ++k) {
                                 const uint64_t koff = (uint64_t)(k * 2);   // 32 bytes >> 4
                                 const uint32_t acc_flag = (gi | tkh | k) != 0;
-                                if (ncat) {
+                                if (ncat && TWO) {
+                                    umma2_bf16(tacc, da_hi + koff, db_hi + koff, idesc_cat, acc_flag);     // a_hi x [w_hi (leader) | w_lo (peer)]
+                                    umma2_bf16(tacc, da_lo + koff, db_lo + koff, idesc, 1u);               // a_lo x w_hi (32 rows from each CTA)
+                                } else if (ncat) {
                                     umma_bf16(tacc, da_hi + koff, db_hi + koff, idesc_cat, acc_flag);      // a_hi x [w_hi | w_lo] -> columns 0..127
                                     umma_bf16(tacc, da_lo + koff, db_hi + koff, idesc, 1u);                // a_lo x w_hi -> columns 0..63
                                 } else if (three) {
@@ -512,14 +523,16 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     p.cin_blocks = cin_eff / HK;
     // CTA pairs (cta_group::2 MMAs, each CTA holds half of the weight rows): cout = 128 tiles, an even number of position tiles so that the
     // two CTAs of a pair always share their weight column tile; HUPR_HALO_SINGLE=1 is the A/B switch
-    const bool pairs = bn == 128 && m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
+    const bool pairs = (bn == 128 || three) && m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
+    const bool pairs64 = pairs && bn == 64;      // [w_hi | w_lo] form: a 64-row X tile and a 32-row Y tile per tap and CTA
     HaloGeom g;
     g.b_merged = 0;
     g.halo_rows = (bh + 2) * bw;
     g.a_plane_bytes = g.halo_rows * 64;
-    g.b_tile_bytes = (pairs ? bn / 2 : bn) * 64;
+    g.b_tile_bytes = (pairs && !pairs64 ? bn / 2 : bn) * 64;
     g.nprod = three ? 3 : 1;
-    g.stage_bytes = (three ? 2 : 1) * (g.a_plane_bytes + 3 * g.b_tile_bytes);
+    g.stage_bytes = pairs64 ? 2 * g.a_plane_bytes + 3 * g.b_tile_bytes + 3 * (g.b_tile_bytes / 2)
+                            : (three ? 2 : 1) * (g.a_plane_bytes + 3 * g.b_tile_bytes);
     g.stages = (232448 - 1024 - 256 - kHaloStatBytes) / g.stage_bytes;
     if (g.stages > 4) g.stages = 4;
     if (g.stages < 2) return 1;
@@ -559,6 +572,13 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     if ((rc = encode_halo_act_map(&a_hi, d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     if ((rc = encode_halo_act_map(&a_lo, three ? d->a_lo : d->a_hi, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, d->a_n_stride)) != HUPR_OK) return rc;
     g.b_merged = 0;
+    if (pairs64) {
+        CUtensorMap b_y;
+        if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, 64, w_ld, 3)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b_lo, w_lo, d->cin, d->cout, d->kd, d->kw, 64, w_ld, 3)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b_y, w_hi, d->cin, d->cout, d->kd, d->kw, 32, w_ld, 3)) != HUPR_OK) return rc;
+        return launch_halo_pairs<64, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_y, p, g, m_tiles, stream);
+    }
     if (three) {
         // both planes through ONE map when lo lies a 16-byte-multiple above hi in the address space (always true for the halves of one
         // allocation, SplitTensor.from_float; otherwise one box per tile and plane)
