@@ -39,8 +39,7 @@ struct ConvParams {
     int stats_ld;                  // (train-mode BatchNorm batch statistics fused into the producing convolution, layers.py:45-53)
     float acc_scale;               // exact power of two applied to the accumulator first (2^-16 for the two-unit arithmetic, else 1)
     __half* o_q16;                 // optional second form of the output: activation operand planes of the two-unit arithmetic
-    uint8_t* o_q8;                 // ([positions][o_ld] at o_ch_off like o_hi; hupr_conv_desc.o_q*)
-    uint8_t* o_q8l;
+    uint8_t* o_q8;                 // ([positions][o_ld] at o_ch_off like o_hi; e4m3 plane [positions][o_ld / 32][2][32]; hupr_conv_desc.o_q*)
     int st256;                     // 1: every output plane row segment is 32-byte aligned -> 256-bit stores (one full sector per lane)
 };
 
@@ -206,14 +205,15 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, const f
         }
         st_global_256(p.o_q16 + at, h[0].x, h[0].y, h[0].z, h[0].w, h[1].x, h[1].y, h[1].z, h[1].w);
         st_global_256(p.o_q16 + at + 16, h[2].x, h[2].y, h[2].z, h[2].w, h[3].x, h[3].y, h[3].z, h[3].w);
-        st_global_256(p.o_q8 + at, a8[0].x, a8[0].y, a8[1].x, a8[1].y, a8[2].x, a8[2].y, a8[3].x, a8[3].y);
-        st_global_256(p.o_q8l + at, l8[0].x, l8[0].y, l8[1].x, l8[1].y, l8[2].x, l8[2].y, l8[3].x, l8[3].y);
+        uint8_t* d8 = p.o_q8 + 2 * at;          // ch0 and o_ch_off are multiples of 32: this chunk's 64-byte block [values | residuals]
+        st_global_256(d8, a8[0].x, a8[0].y, a8[1].x, a8[1].y, a8[2].x, a8[2].y, a8[3].x, a8[3].y);
+        st_global_256(d8 + 32, l8[0].x, l8[0].y, l8[1].x, l8[1].y, l8[2].x, l8[2].y, l8[3].x, l8[3].y);
     } else if (p.o_q16) {
         const QuantScales q = quant_scales(false);
         const size_t at = pos * p.o_ld + p.o_ch_off + ch0;
         uint4* d16 = reinterpret_cast<uint4*>(p.o_q16 + at);
-        uint2* d8 = reinterpret_cast<uint2*>(p.o_q8 + at);
-        uint2* d8l = reinterpret_cast<uint2*>(p.o_q8l + at);
+        uint2* d8 = reinterpret_cast<uint2*>(p.o_q8 + 2 * at);
+        uint2* d8l = d8 + 4;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const float v8[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};

@@ -457,10 +457,11 @@ int hupr::conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch) {
     if (d->nprod != 1 && (d->a_lo == nullptr) != (d->w_lo == nullptr)) return HUPR_ERR_BAD_ARG;
     if (d->nprod >= 2 && !d->a_lo) return HUPR_ERR_BAD_ARG;
     {   // the quantised planes come in complete sets
-        const int na = (d->a_q16 != nullptr) + (d->a_q8 != nullptr) + (d->a_q8l != nullptr);
-        const int nw = (d->w_q16 != nullptr) + (d->w_q8 != nullptr) + (d->w_q8l != nullptr);
-        const int no = (d->o_q16 != nullptr) + (d->o_q8 != nullptr) + (d->o_q8l != nullptr);
-        if (na % 3 || nw % 3 || no % 3 || (no && !d->o_hi)) return HUPR_ERR_BAD_ARG;
+        const int na = (d->a_q16 != nullptr) + (d->a_q8 != nullptr);
+        const int nw = (d->w_q16 != nullptr) + (d->w_q8 != nullptr);
+        const int no = (d->o_q16 != nullptr) + (d->o_q8 != nullptr);
+        if (na % 2 || nw % 2 || no % 2 || (no && !d->o_hi)) return HUPR_ERR_BAD_ARG;
+        if (no && (d->o_ld % 32 || d->o_ch_off % 32)) return HUPR_ERR_BAD_ARG;      // 32-channel blocks of the e4m3 plane
         if (d->nprod == 2 && launch && (!na || !nw)) return HUPR_ERR_BAD_ARG;
         if (no && (d->k_split > 1)) return HUPR_ERR_BAD_ARG;
     }
@@ -485,8 +486,7 @@ int hupr::conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch) {
     if (d->h % bh) return HUPR_ERR_BAD_ARG;
     const uintptr_t align_or = (uintptr_t)d->a_hi | (uintptr_t)d->a_lo | (uintptr_t)d->w_hi | (uintptr_t)d->w_lo | (uintptr_t)d->o_hi |
                                (uintptr_t)d->o_lo | (uintptr_t)d->o_f32 | (uintptr_t)d->r_hi | (uintptr_t)d->r_lo | (uintptr_t)d->a_q16 |
-                               (uintptr_t)d->a_q8 | (uintptr_t)d->a_q8l | (uintptr_t)d->w_q16 | (uintptr_t)d->w_q8 | (uintptr_t)d->w_q8l |
-                               (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8 | (uintptr_t)d->o_q8l;
+                               (uintptr_t)d->a_q8 | (uintptr_t)d->w_q16 | (uintptr_t)d->w_q8 | (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8;
     if (align_or & 15) return HUPR_ERR_ALIGNMENT;
 
     ConvParams p;
@@ -503,9 +503,9 @@ int hupr::conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch) {
     p.row_vec = d->row_vec; p.row_mode = d->row_vec ? d->row_mode : 0;
     p.stats = d->stats; p.stats_ld = d->stats_ld;
     p.acc_scale = 1.0f;
-    p.o_q16 = static_cast<__half*>(d->o_q16); p.o_q8 = static_cast<uint8_t*>(d->o_q8); p.o_q8l = static_cast<uint8_t*>(d->o_q8l);
+    p.o_q16 = static_cast<__half*>(d->o_q16); p.o_q8 = static_cast<uint8_t*>(d->o_q8);
     {   // 256-bit stores need 32-byte aligned row segments in every plane that is written (e4m3 planes: one byte per element)
-        const uintptr_t o_or = (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8 | (uintptr_t)d->o_q8l;
+        const uintptr_t o_or = (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8;
         const int unit = d->o_q8 ? 32 : 16;
         p.st256 = (d->o_hi && !(o_or & 31) && d->o_ld % unit == 0 && d->o_ch_off % unit == 0 && !getenv("HUPR_NO_ST256")) ? 1 : 0;
     }

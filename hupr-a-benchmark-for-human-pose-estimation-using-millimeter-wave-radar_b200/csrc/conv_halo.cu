@@ -24,7 +24,9 @@
 //   * NPROD == 2 is the two-unit arithmetic of hupr_conv_desc (include/hupr_b200.h): per 32-channel block ONE kind::f16 pair of MMAs on
 //     fp16 planes (a16 x w16) plus TWO kind::f8f6f4 MMAs (K = 32: a whole 32-byte row) on e4m3 planes (al x w, a x wl), all into the same
 //     fp32 accumulator at a common 2^16 scale — 64 + 32 + 32 tensor cycles per N = 128 tile-tap instead of 3 x 64, and 2/3 of the
-//     shared-memory operand bytes.  The e4m3 planes are 32-byte rows under SWIZZLE_32B; a stage has the same size as the hi/lo one.
+//     shared-memory operand bytes.  The two e4m3 planes of a tensor are interleaved per 32-channel block ([values | residuals] = 64-byte
+//     rows, SWIZZLE_64B like the fp16 plane; as separate 32-byte-row planes under SWIZZLE_32B the tensor core read them at half the rate):
+//     the two cross-term operands are the K = 32 slices at byte 0 and byte 32 of the same rows.  A stage has the size of the hi/lo one.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
 #include <stdlib.h>
 
@@ -171,12 +173,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             tma2_load_4d(sb2, leader ? &tmB_hi : &tmB_lo, &full[s], cb * HK, n0, tkw, tkd * 3);
                             tma2_load_4d(sb2 + 3 * g.b_tile_bytes, &tmB_x, &full[s], cb * HK, n0 + (int)cta_rank * 32, tkw, tkd * 3);
                         } else if (quant) {
-                            tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                            tma2_load_5d(st + g.a_plane_bytes + g.a_plane_bytes / 2, &tmA_x, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                            tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], 2 * ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                             uint8_t* sq = st + 2 * g.a_plane_bytes;
                             tma2_load_4d(sq, &tmB_hi, &full[s], cb * HK, nrow, tkw, tkd * 3);
-                            tma2_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, nrow, tkw, tkd * 3);
-                            tma2_load_4d(sq + 3 * g.b_tile_bytes + 3 * (g.b_tile_bytes / 2), &tmB_x, &full[s], cb * HK, nrow, tkw, tkd * 3);
+                            tma2_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], 2 * cb * HK, nrow, tkw, tkd * 3);
                         } else if (three) {
                             tma2_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                             if (g.b_merged) {
@@ -201,14 +201,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     mbar_expect_tx(&full[s], (uint32_t)g.stage_bytes);
                     tma_load_5d(st, &tmA_hi, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                     if (three) tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                    if (quant) {       // stage = [a16 | a8 | a8l | w16 x3 | w8 x3 | w8l x3]; e4m3 planes and tiles are half the bytes
-                        tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
-                        tma_load_5d(st + g.a_plane_bytes + g.a_plane_bytes / 2, &tmA_x, &full[s], ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
+                    if (quant) {       // stage = [a16 | a8x | w16 x3 | w8x x3]; the e4m3 maps count bytes: 64 per 32-channel block
+                        tma_load_5d(st + g.a_plane_bytes, &tmA_lo, &full[s], 2 * ac, tkw - p.pw, h0 - 1, od + tkd - p.pd, n);
                         uint8_t* sq = st + 2 * g.a_plane_bytes;
                         // one box per plane brings the three kh taps (weight map dims: cin, cout, kw, kd*3 + kh)
                         tma_load_4d(sq, &tmB_hi, &full[s], cb * HK, n0, tkw, tkd * 3);
-                        tma_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], cb * HK, n0, tkw, tkd * 3);
-                        tma_load_4d(sq + 3 * g.b_tile_bytes + 3 * (g.b_tile_bytes / 2), &tmB_x, &full[s], cb * HK, n0, tkw, tkd * 3);
+                        tma_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], 2 * cb * HK, n0, tkw, tkd * 3);
                     }
                     uint8_t* sb = st + (three ? 2 : 1) * g.a_plane_bytes;
                     // The TMA unit ingests about one box row per clock plus ~110 clocks per box (tools_dev/micro/tma_rate.cu): six 128-row weight
@@ -261,14 +259,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                         for (int tkh = 0; tkh < 3; ++tkh) {
                             const uint64_t db16 = make_smem_desc_sw64(sq + tkh * g.b_tile_bytes);
-                            const uint64_t db8 = make_smem_desc_sw32(sq + 3 * g.b_tile_bytes + tkh * (g.b_tile_bytes / 2));
-                            const uint64_t db8l = make_smem_desc_sw32(sq + 3 * g.b_tile_bytes + (3 + tkh) * (g.b_tile_bytes / 2));
+                            const uint64_t db8 = make_smem_desc_sw64(sq + (3 + tkh) * g.b_tile_bytes);      // values: bytes 0..31 of the 64-byte rows
+                            const uint64_t db8l = db8 + 2;                                                   // residuals: bytes 32..63
 #pragma unroll
                             for (int a = 0; a < 2; ++a) {
                                 const uint32_t aoff = (uint32_t)(tkh * g.tap_stride_bytes + a * g.acc_stride_bytes);
                                 const uint64_t da16 = make_smem_desc_sw64(st + aoff);
-                                const uint64_t da8 = make_smem_desc_sw32(st + g.a_plane_bytes + aoff / 2);
-                                const uint64_t da8l = make_smem_desc_sw32(st + g.a_plane_bytes + g.a_plane_bytes / 2 + aoff / 2);
+                                const uint64_t da8 = make_smem_desc_sw64(st + g.a_plane_bytes + aoff);
+                                const uint64_t da8l = da8 + 2;
                                 const uint32_t tacc = tset + (uint32_t)(a * ACC);
                                 if (TWO) {
                                     umma2_f8(tacc, da8l, db8, idesc, (uint32_t)((gi | tkh) != 0));
@@ -390,7 +388,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
 }
 
-// esize: bytes per element — 2: bf16 / fp16 planes (64-byte rows, SWIZZLE_64B), 1: e4m3 planes (32-byte rows, SWIZZLE_32B)
+// esize: bytes per element — 2: bf16 / fp16 planes, 1: the interleaved e4m3 plane (a byte tensor with 2 x channels per row); 64-byte rows
 static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w, int h, int d, int n, int bw, int box_h, long long n_stride,
                                int esize = 2) {
     EncodeTiledFn fn = get_encode_fn();
@@ -399,11 +397,11 @@ static int encode_halo_act_map(CUtensorMap* map, const void* base, int ca, int w
     cuuint64_t dims[5] = {(cuuint64_t)ca, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
     cuuint64_t strides[4] = {(cuuint64_t)ca * e, (cuuint64_t)w * ca * e, (cuuint64_t)h * w * ca * e,
                              (cuuint64_t)(n_stride > 0 ? n_stride : (long long)d * h * w * ca) * e};
-    cuuint32_t box[5] = {(cuuint32_t)HK, (cuuint32_t)bw, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(64 / esize), (cuuint32_t)bw, (cuuint32_t)box_h, 1, 1};      // 64-byte rows either way
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
@@ -415,11 +413,11 @@ static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int 
     const cuuint64_t e = (cuuint64_t)esize;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)kw, (cuuint64_t)kd * 3};
     cuuint64_t strides[3] = {(cuuint64_t)ld * e, (cuuint64_t)cout * ld * e, (cuuint64_t)kw * cout * ld * e};
-    cuuint32_t box[4] = {(cuuint32_t)HK, (cuuint32_t)bn, 1, (cuuint32_t)box_kh};
+    cuuint32_t box[4] = {(cuuint32_t)(64 / esize), (cuuint32_t)bn, 1, (cuuint32_t)box_kh};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
@@ -544,26 +542,25 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     const int w_ld = d->w_ld ? d->w_ld : d->cin;
     // two-unit arithmetic: cout = 128-column tiles only (the cout = 64 tiles are bound by shared-memory operand reads either way and keep
     // the [w_hi | w_lo] form), dense samples, no fused statistics (train mode never asks for it)
-    const bool quant = three && d->nprod == 2 && bn == 128 && d->a_n_stride == 0 && !d->stats && d->ca % 16 == 0 && w_ld % 16 == 0 &&
-                       d->w_ch_off % 16 == 0 && !getenv("HUPR_QUANT_OFF");
+    const bool quant = three && d->nprod == 2 && bn == 128 && d->a_n_stride == 0 && !d->stats && d->ca % 32 == 0 && d->a_ch_off % 32 == 0 &&
+                       w_ld % 32 == 0 && d->w_ch_off % 32 == 0 && !getenv("HUPR_QUANT_OFF");
     if (probe) return quant ? 2 : 1;
     if (quant && d->a_q16 && d->w_q16) {
-        CUtensorMap a16, a8, a8l, b16, b8, b8l;
+        // the e4m3 planes are byte tensors with 2 * channels bytes per position / filter row ([values | residuals] per 32-channel block):
+        // the same map builders with esize 1, doubled channel extents and a 64-byte box
+        CUtensorMap a16, a8, b16, b8;
         int rc;
         if ((rc = encode_halo_act_map(&a16, d->a_q16, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_act_map(&a8, d->a_q8, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0, 1)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_act_map(&a8l, d->a_q8l, d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0, 1)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_act_map(&a8, d->a_q8, 2 * d->ca, d->w, d->h, d->d, d->n, bw, bh + 2, 0, 1)) != HUPR_OK) return rc;
         const char* w16 = static_cast<const char*>(d->w_q16) + (size_t)d->w_ch_off * 2;
-        const char* w8 = static_cast<const char*>(d->w_q8) + d->w_ch_off;
-        const char* w8l = static_cast<const char*>(d->w_q8l) + d->w_ch_off;
+        const char* w8 = static_cast<const char*>(d->w_q8) + (size_t)d->w_ch_off * 2;
         const int brows = pairs ? bn / 2 : bn;
         if ((rc = encode_halo_wgt_map(&b16, w16, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_wgt_map(&b8, w8, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3, 1)) != HUPR_OK) return rc;
-        if ((rc = encode_halo_wgt_map(&b8l, w8l, d->cin, d->cout, d->kd, d->kw, brows, w_ld, 3, 1)) != HUPR_OK) return rc;
+        if ((rc = encode_halo_wgt_map(&b8, w8, 2 * d->cin, d->cout, d->kd, d->kw, brows, 2 * w_ld, 3, 1)) != HUPR_OK) return rc;
         g.nprod = 2;
         p.acc_scale = 1.0f / 65536.0f;
-        if (pairs) return launch_halo_pairs<128, 2>(a16, a8, a8l, b16, b8, b8l, p, g, m_tiles, stream);
-        return launch_halo<128, 2>(a16, a8, a8l, b16, b8, b8l, p, g, m_tiles, stream);
+        if (pairs) return launch_halo_pairs<128, 2>(a16, a8, a16, b16, b8, b16, p, g, m_tiles, stream);
+        return launch_halo<128, 2>(a16, a8, a16, b16, b8, b16, p, g, m_tiles, stream);
     }
     const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(d->w_hi) + d->w_ch_off;
     const __nv_bfloat16* w_lo = three ? static_cast<const __nv_bfloat16*>(d->w_lo) + d->w_ch_off : w_hi;

@@ -43,7 +43,8 @@ class SplitTensor(object):
     ``lo is None`` means single-bf16 mode (fast, not fp32-equivalent).
 
     ``q`` (optional) holds the same values a second time as the operand planes of the two-unit 3-tap convolution
-    (hupr_conv_desc.nprod == 2): ``(q16 float16, q8 uint8 e4m3, q8l uint8 e4m3)`` with the tensor's shape.  ``q_fresh`` is the channel
+    (hupr_conv_desc.nprod == 2): ``(q16 float16 [..., C], q8 uint8 [..., 2 C])`` — q8 holds, per 32-channel block, 32 e4m3 values
+    followed by the 32 e4m3 residuals.  ``q_fresh`` is the channel
     range ``(first, end)`` a producing convolution has just written there (one-shot: the consuming convolution clears it)."""
 
     __slots__ = ("hi", "lo", "q", "q_fresh")
@@ -59,8 +60,10 @@ class SplitTensor(object):
             if not self.hi.is_contiguous():
                 raise ValueError("quantised operand planes need a dense tensor")
             dev, shape = self.hi.device, self.hi.shape
-            self.q = (torch.empty(shape, dtype=torch.float16, device=dev), torch.empty(shape, dtype=torch.uint8, device=dev),
-                      torch.empty(shape, dtype=torch.uint8, device=dev))
+            if shape[-1] % 32:
+                raise ValueError("quantised operand planes need a channel count that is a multiple of 32")
+            self.q = (torch.empty(shape, dtype=torch.float16, device=dev),
+                      torch.empty(tuple(shape[:-1]) + (2 * shape[-1],), dtype=torch.uint8, device=dev))
         return self.q
 
     @property
@@ -202,13 +205,13 @@ def quant(on=True):
 
 def quantize_planes(t, ch_off=0, ch=None, is_weight=False):
     """hupr_quantize_planes: fill ``t.q`` (allocated on first use) for channels [ch_off, ch_off + ch) from the hi/lo planes."""
-    q16, q8, q8l = t.ensure_q()
+    q16, q8 = t.ensure_q()
     ld = t.hi.shape[-1]
     ch = ld - ch_off if ch is None else ch
     rows = t.hi.numel() // ld
     with torch.cuda.device(t.hi.device), _timed("quantize_planes"):
         _C.check(_C.lib().hupr_quantize_planes(t.hi.data_ptr(), _C.optr(t.lo), rows, ld, ch_off, ch, q16.data_ptr(), q8.data_ptr(),
-                                               q8l.data_ptr(), 1 if is_weight else 0, _C.stream_ptr()), "hupr_quantize_planes")
+                                               1 if is_weight else 0, _C.stream_ptr()), "hupr_quantize_planes")
     return t.q
 
 
@@ -282,14 +285,14 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
     if probe:
         return use_q
     if use_q:
-        span = (a_ch_off, a_ch_off + min(cin, ca - a_ch_off))
+        span = (a_ch_off, a_ch_off + min(cin, ca - a_ch_off))      # multiples of 32 (eligibility)
         if a.q is None or a.q_fresh is None or a.q_fresh[0] > span[0] or a.q_fresh[1] < span[1]:
             quantize_planes(a, span[0], span[1] - span[0])
         a.q_fresh = None                # one-shot: whoever rewrites `a` must refresh the planes
-        desc.a_q16, desc.a_q8, desc.a_q8l = (t.data_ptr() for t in a.q)
-        desc.w_q16, desc.w_q8, desc.w_q8l = (t.data_ptr() for t in weight.q)
+        desc.a_q16, desc.a_q8 = (t.data_ptr() for t in a.q)
+        desc.w_q16, desc.w_q8 = (t.data_ptr() for t in weight.q)
     if out_q and out is not None and QUANT_FUSE:
-        desc.o_q16, desc.o_q8, desc.o_q8l = (t.data_ptr() for t in out.ensure_q())
+        desc.o_q16, desc.o_q8 = (t.data_ptr() for t in out.ensure_q())
         out.q_fresh = (o_ch_off, o_ch_off + cout)
     d_out = d + 2 * pad[0] - kernel[0] + 1
     rows = n * d_out * h * w if lrows is None else lrows

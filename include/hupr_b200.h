@@ -116,15 +116,18 @@ typedef struct hupr_conv_desc {
     /* Two-unit arithmetic for the 3-tap convolutions (nprod == 2): with x = x16 + xl, the product a*w is evaluated as
      *   a16*w16 (fp16 operands, full tensor rate)  +  al*w  +  a*wl  (both cross terms as e4m3 x e4m3 products at twice the rate)
      * into ONE fp32 accumulator: 1 + 1/2 + 1/2 = 2 tensor units per k-step instead of the 3 bf16 products, ~2^-13 relative per product
-     * (measured whole-network error: DESIGN.md §3).  The operands carry fixed power-of-two scales so that every product is scaled by
-     * 2^16 (undone exactly in the epilogue):  a_q16 = fp16(a * 2^2), a_q8 = e4m3(a * 2^1), a_q8l = e4m3((a - a16) * 2^12);
-     * w_q16 = fp16(w * 2^14), w_q8 = e4m3(w * 2^4), w_q8l = e4m3((w - w16) * 2^15).  Conversions saturate: beyond |a| = 224 the cross terms
+     * (measured whole-network error: DESIGN.md §2).  The operands carry fixed power-of-two scales so that every product is scaled by
+     * 2^16 (undone exactly in the epilogue):  a16 = fp16(a * 2^2), a8 = e4m3(a * 2^1), al8 = e4m3((a - a16) * 2^12);
+     * w16 = fp16(w * 2^14), w8 = e4m3(w * 2^4), wl8 = e4m3((w - w16) * 2^15).  Conversions saturate: beyond |a| = 224 the cross terms
      * lose accuracy gradually (a term then has single-fp16-product accuracy, 2^-12); the hard limits are |a| < 16 376 and |w| < 3.99 (fp16
-     * planes).  Planes have the geometry of a_hi / w_hi (same ca, a_ch_off, w_ld, ...), 1 byte per element for the e4m3
-     * ones; hupr_quantize_planes writes them, or a producing hupr_conv_gemm call does through o_q*.  All six NULL = not available. */
-    const void* a_q16; const void* a_q8; const void* a_q8l;
-    const void* w_q16; const void* w_q8; const void* w_q8l;
-    void* o_q16; void* o_q8; void* o_q8l;                         /* optional: ALSO store the output as activation planes of that form ([positions][o_ld]
+     * planes).  Two planes per tensor, with the geometry of a_hi / w_hi (same ca, a_ch_off, w_ld, ... all multiples of 32 here):
+     *   *_q16 : fp16 [rows][ld]
+     *   *_q8  : e4m3 bytes [rows][ld / 32][2][32] — per 32-channel block the 32 values x8 followed by the 32 residuals xl8, i.e. 64-byte
+     *           rows that the tensor core reads as two K = 32 slices (32-byte rows under SWIZZLE_32B read at half the rate)
+     * hupr_quantize_planes writes them, or a producing hupr_conv_gemm call does through o_q*.  All NULL = not available. */
+    const void* a_q16; const void* a_q8;
+    const void* w_q16; const void* w_q8;
+    void* o_q16; void* o_q8;                                      /* optional: ALSO store the output as activation planes of that form ([positions][o_ld]
                                                                      at o_ch_off like o_hi), for a following nprod == 2 convolution; needs o_hi */
 } hupr_conv_desc;
 
@@ -134,11 +137,11 @@ int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
  * back to the three bf16 products (shape not handled there), negative = HUPR_ERR_*.  Lets a caller skip producing planes nobody reads. */
 int hupr_conv_quant_eligible(const hupr_conv_desc* desc);
 
-/* The operand planes of the two-unit arithmetic from a bf16 split tensor: rows x [ch_off, ch_off + ch) of [rows][ld] (ch a multiple of 8).
- * is_weight selects the scale set (0: activation 2^2 / 2^1 / 2^12, 1: weight 2^14 / 2^4 / 2^15).  q16: fp16 [rows][ld]; q8, q8l: e4m3 bytes
- * [rows][ld].  lo may be NULL. */
-int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, void* q8l,
-                         int is_weight, void* stream);
+/* The operand planes of the two-unit arithmetic from a bf16 split tensor: rows x [ch_off, ch_off + ch) of [rows][ld] (ld, ch_off, ch
+ * multiples of 32).  is_weight selects the scale set (0: activation 2^2 / 2^1 / 2^12, 1: weight 2^14 / 2^4 / 2^15).  q16: fp16 [rows][ld];
+ * q8: e4m3 bytes [rows][ld / 32][2][32] (hupr_conv_desc).  lo may be NULL. */
+int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, int is_weight,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused spatial attention (flash-style: the [S, S] logits never leave the SM).  Replaces

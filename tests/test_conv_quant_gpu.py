@@ -18,6 +18,12 @@ def _e4m3(x, scale):
     return (x * scale).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float() / scale
 
 
+def _unpack_q8(q8, shape):
+    """e4m3 plane [..., C/32, 2, 32] bytes -> (values, residuals) as float32 tensors of ``shape`` (still scaled)."""
+    v = q8.view(torch.float8_e4m3fn).float().view(tuple(shape[:-1]) + (shape[-1] // 32, 2, 32))
+    return v[..., 0, :].reshape(shape), v[..., 1, :].reshape(shape)
+
+
 def _planes(x, is_weight):
     """(x16, x8, x8l) as UNscaled float32 values, rounded the way hupr_quantize_planes rounds them."""
     s16, s8, s8l = (16384.0, 16.0, 32768.0) if is_weight else (4.0, 2.0, 4096.0)
@@ -38,16 +44,18 @@ def test_quantize_planes_match_torch_roundings(is_weight):
     u = SplitTensor.from_float(x)
     for p in u.ensure_q():
         p.zero_()
-    ops.quantize_planes(u, 16, 32, is_weight)
+    ops.quantize_planes(u, 32, 32, is_weight)
     torch.cuda.synchronize()
     s16, s8, s8l = (16384.0, 16.0, 32768.0) if is_weight else (4.0, 2.0, 4096.0)
     ref16, ref8, ref8l = _planes(t.float(), is_weight)
-    q16, q8, q8l = t.q
+    q16, q8x = t.q
+    q8, q8l = _unpack_q8(q8x, x.shape)
     assert torch.equal(q16.float() / s16, ref16)
-    assert torch.equal(q8.view(torch.float8_e4m3fn).float() / s8, ref8)
-    assert torch.equal(q8l.view(torch.float8_e4m3fn).float() / s8l, ref8l)
-    assert torch.equal(u.q[0][..., 16:48], q16[..., 16:48]) and float(u.q[0][..., :16].float().abs().sum()) == 0
-    assert torch.equal(u.q[2][..., 16:48], q8l[..., 16:48]) and int(u.q[1][..., 48:].sum()) == 0
+    assert torch.equal(q8 / s8, ref8)
+    assert torch.equal(q8l / s8l, ref8l)
+    u8, u8l = _unpack_q8(u.q[1], x.shape)
+    assert torch.equal(u.q[0][..., 32:], q16[..., 32:]) and float(u.q[0][..., :32].float().abs().sum()) == 0
+    assert torch.equal(u8l[..., 32:], q8l[..., 32:]) and torch.equal(u8[..., 32:], q8[..., 32:]) and int(u.q[1][..., :64].sum()) == 0
     # the planes reproduce the value: x16 + x8l is within 2^-11 (fp16 residual) * 2^-4 (e4m3 rounding) of |x| wherever the residual is in
     # e4m3's normal range; small values lose part of the correction (flush to e4m3 subnormals), never more than the fp16 residual itself
     val = t.float()
@@ -97,14 +105,15 @@ def test_two_unit_conv_matches_its_emulation_and_the_fp64_convolution(n, d, hw, 
     assert e_ref2 < 4e-5         # the accuracy of the scheme itself: ~2^-13 per product, averaging over the contraction
     assert e_ref3 < 2e-5
     # planes written by the epilogue == planes of the stored hi/lo output, up to the 2^-17 the hi/lo rounding of the output moves a value
-    q16, q8, q8l = out2.q
+    q16, q8x = out2.q
+    q8, q8l = _unpack_q8(q8x, out2.hi.shape)
     assert out2.q_fresh == (0, cout)
     r16, r8, r8l = _planes(out2.float(), False)
-    got = q16.float() / 4.0 + q8l.view(torch.float8_e4m3fn).float() / 4096.0
+    got = q16.float() / 4.0 + q8l / 4096.0
     val = out2.float()
     assert float(((got - val).abs() / val.abs().clamp_min(1e-2)).max()) < 2.0 ** -14
     assert float((q16.float() / 4.0 - r16).abs().max()) <= float(val.abs().max()) * 2.0 ** -10       # at most one fp16 ulp apart
-    assert float((q8.view(torch.float8_e4m3fn).float() / 2.0 - r8).abs().max()) <= float(val.abs().max()) * 2.0 ** -3
+    assert float((q8 / 2.0 - r8).abs().max()) <= float(val.abs().max()) * 2.0 ** -3
     # a second two-unit convolution consumes them without a separate pass (q_fresh is one-shot)
     w2 = SplitTensor.from_float(torch.randn(9, 256, cout, device=DEV) * (2.0 / (9 * cout)) ** 0.5)
     o_a, o_b = SplitTensor.empty((n, d, hw, hw, 256), DEV), SplitTensor.empty((n, d, hw, hw, 256), DEV)
