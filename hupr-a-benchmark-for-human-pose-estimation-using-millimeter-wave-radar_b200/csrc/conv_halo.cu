@@ -102,7 +102,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     constexpr int BROWS = TWO ? BN / 2 : BN;
-    static_assert(!TWO || BN == 128 || NPROD == 3, "CTA pairs: cout = 128 tiles, or the [w_hi | w_lo] form of the cout = 64 tiles");
+    static_assert(!TWO || NPROD != 2 || BN == 128, "two-unit arithmetic: cout = 128 tiles");
     constexpr bool ncat = (BN == 64 && NPROD == 3);         // [w_hi | w_lo] as one N = 128 operand (header comment)
     constexpr int ACC = ncat ? 128 : BN;                    // TMEM columns of one accumulator
     constexpr int TMEM_COLS = 4 * ACC;                      // two sets x two accumulators
@@ -521,8 +521,8 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     p.cin_blocks = cin_eff / HK;
     // CTA pairs (cta_group::2 MMAs, each CTA holds half of the weight rows): cout = 128 tiles, an even number of position tiles so that the
     // two CTAs of a pair always share their weight column tile; HUPR_HALO_SINGLE=1 is the A/B switch
-    const bool pairs = (bn == 128 || three) && m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
-    const bool pairs64 = pairs && bn == 64;      // [w_hi | w_lo] form: a 64-row X tile and a 32-row Y tile per tap and CTA
+    const bool pairs = m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
+    const bool pairs64 = pairs && bn == 64 && three;      // [w_hi | w_lo] form: a 64-row X tile and a 32-row Y tile per tap and CTA
     HaloGeom g;
     g.b_merged = 0;
     g.halo_rows = (bh + 2) * bw;
@@ -601,9 +601,11 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
         if ((rc = encode_halo_wgt_map(&b_hi, w_hi, d->cin, d->cout, d->kd, d->kw, pairs ? bn / 2 : bn, w_ld, 3)) != HUPR_OK) return rc;
         b_lo = b_hi;
     }
-    if (pairs)
-        return three ? launch_halo_pairs<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
-                     : launch_halo_pairs<128, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
+    if (pairs) {
+        if (three) return launch_halo_pairs<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
+        return bn == 128 ? launch_halo_pairs<128, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
+                         : launch_halo_pairs<64, 1>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);
+    }
     if (three)
         return bn == 128 ? launch_halo<128, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream)
                          : launch_halo<64, 3>(a_hi, a_lo, a_hi, b_hi, b_lo, b_hi, p, g, m_tiles, stream);

@@ -150,3 +150,33 @@ def test_shapes_outside_the_two_unit_kernel_fall_back_bit_exactly():
         torch.cuda.synchronize()
         assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
         assert x.q is None and w.q is None
+
+
+def test_large_activations_degrade_gracefully_and_large_weights_fall_back():
+    """Beyond |a| = 224 the e4m3 operands saturate: a term then keeps single-fp16-product accuracy (2^-12) instead of ~2^-16 — the result
+    stays close, nothing blows up; a filter with a weight >= 3.99 (outside the fp16 plane w * 2^14) keeps the three bf16 products."""
+    from hupr_b200 import ops
+    from hupr_b200.ops import SplitTensor
+    torch.manual_seed(5)
+    n, d, hw, cin, cout = 16, 2, 32, 64, 128
+    x = torch.randn(n, d, hw, hw, cin, device=DEV) * 300.0           # |x| up to ~1500: a8 saturates for most of the tensor
+    w = torch.randn(27, cout, cin, device=DEV) * (2.0 / (27 * cin)) ** 0.5
+    xs, ws = SplitTensor.from_float(x), SplitTensor.from_float(w)
+    out = SplitTensor.empty((n, d, hw, hw, cout), DEV)
+    with ops.quant():
+        ops.conv_gemm(xs, cin, ws, cout, kernel=(3, 3, 3), pad=(1, 1, 1), out=out)
+    torch.cuda.synchronize()
+    ref = _reference_conv(xs.float().double(), ws.float().double(), (1, 1, 1))
+    err = float((out.float().double() - ref).abs().max()) / float(ref.abs().max())
+    print("two-unit conv with |x| up to %.0f: max error / max |output| %.3g" % (float(x.abs().max()), err))
+    assert torch.isfinite(out.float()).all() and err < 4e-4          # CPU emulation of this case: 1.3e-4 (1.2e-5 inside the range)
+    big = w.clone()
+    big[3, 5, 7] = 4.5
+    wb = SplitTensor.from_float(big)
+    xs2 = SplitTensor.from_float(torch.randn(n, d, hw, hw, cin, device=DEV))
+    a, b = SplitTensor.empty((n, d, hw, hw, cout), DEV), SplitTensor.empty((n, d, hw, hw, cout), DEV)
+    ops.conv_gemm(xs2, cin, wb, cout, kernel=(3, 3, 3), pad=(1, 1, 1), out=a)
+    with ops.quant():
+        ops.conv_gemm(xs2, cin, wb, cout, kernel=(3, 3, 3), pad=(1, 1, 1), out=b)
+    torch.cuda.synchronize()
+    assert wb.q is False and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)

@@ -99,3 +99,27 @@ def test_pack_table_layout_of_the_batched_pack_launch():
     import pytest
     with pytest.raises(ValueError):
         ops.PackTable([(1, 2, 3, 4, 5, 63, 32, 27, 64, 64, 0)], torch.device("cpu"))       # odd cout: bf16 pairs
+
+
+def test_split_tensor_planes_are_halves_of_one_allocation():
+    """ops.SplitTensor.empty / from_float: lo lies right above hi in ONE allocation (so that a tensor map can address both weight planes
+    with a plane dimension: csrc/conv_halo.cu fetches hi and lo weight tiles with a single TMA box); odd sizes fall back to two
+    allocations that keep both planes 128-byte aligned; the operand planes of the two-unit convolution have the documented shapes."""
+    import torch
+    from hupr_b200.ops import SplitTensor
+    t = SplitTensor.empty((3, 4, 64), "cpu")
+    assert t.lo.data_ptr() - t.hi.data_ptr() == t.hi.numel() * 2 and t.hi.is_contiguous() and t.lo.is_contiguous()
+    x = torch.randn(2, 5, 64)
+    f = SplitTensor.from_float(x)
+    assert f.lo.data_ptr() - f.hi.data_ptr() == f.hi.numel() * 2
+    assert torch.equal(f.hi, x.to(torch.bfloat16)) and torch.equal(f.lo, (x - x.to(torch.bfloat16).float()).to(torch.bfloat16))
+    assert float((f.float() - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -16
+    odd = SplitTensor.empty((3, 5), "cpu")
+    assert odd.hi.shape == odd.lo.shape == (3, 5)
+    single = SplitTensor.from_float(x, split=False)
+    assert single.lo is None and single.q is None and single.q_fresh is None
+    q16, q8 = t.ensure_q()
+    assert q16.shape == (3, 4, 64) and q16.dtype == torch.float16 and q8.shape == (3, 4, 128) and q8.dtype == torch.uint8
+    import pytest
+    with pytest.raises(ValueError):
+        SplitTensor.empty((2, 48), "cpu").ensure_q()          # channel count must be a multiple of 32
