@@ -104,24 +104,28 @@ channel_sums_kernel(TView a, TView b, TView m, const float* __restrict__ mean, c
         const bool has_b = (MODE != SUMS_STATS) && b.hi != nullptr, has_m = (MODE == SUMS_BN_BWD) && m.hi != nullptr;
         const TView& vb = has_b ? b : a;                   // absent operands alias `a`: the loads stay unconditional, the values unused
         const TView& vm = has_m ? m : a;
-        for (; pos + stride < positions; pos += 2 * stride) {
-            // all twelve 16-byte loads of the two positions are in flight before the first conversion
-            const Raw8 ra0 = tv_raw8(a, (size_t)pos, cg * 8), ra1 = tv_raw8(a, (size_t)(pos + stride), cg * 8);
-            Raw8 rb0 = ra0, rb1 = ra1, rm0 = ra0, rm1 = ra1;
-            if (MODE != SUMS_STATS) { rb0 = tv_raw8(vb, (size_t)pos, cg * 8); rb1 = tv_raw8(vb, (size_t)(pos + stride), cg * 8); }
-            if (MODE == SUMS_BN_BWD) { rm0 = tv_raw8(vm, (size_t)pos, cg * 8); rm1 = tv_raw8(vm, (size_t)(pos + stride), cg * 8); }
-            float x0[8], y0[8], k0[8], x1[8], y1[8], k1[8];
-            raw_decode8(ra0, x0); raw_decode8(rb0, y0); raw_decode8(rm0, k0);
-            raw_decode8(ra1, x1); raw_decode8(rb1, y1); raw_decode8(rm1, k1);
-            accumulate(x0, y0, k0);
-            accumulate(x1, y1, k1);
-        }
+        // software-pipelined over positions: the six 16-byte loads of position p + stride are issued BEFORE the conversion / double-precision
+        // accumulation chain of position p runs (~300 instructions), so every warp keeps loads in flight while it computes.  (Issuing the
+        // loads of two positions and then consuming both left the memory system idle during the arithmetic: 16 resident warps per SM at
+        // 127 registers alternate between waiting and computing — ncu: 0.40 of the HBM peak, every stall a long-scoreboard one.)
         if (pos < positions) {
-            float x0[8], y0[8], k0[8];
-            raw_decode8(tv_raw8(a, (size_t)pos, cg * 8), x0);
-            raw_decode8(tv_raw8(vb, (size_t)pos, cg * 8), y0);
-            raw_decode8(tv_raw8(vm, (size_t)pos, cg * 8), k0);
-            accumulate(x0, y0, k0);
+            Raw8 ca = tv_raw8(a, (size_t)pos, cg * 8), cb = ca, cm = ca;
+            if (MODE != SUMS_STATS) cb = tv_raw8(vb, (size_t)pos, cg * 8);
+            if (MODE == SUMS_BN_BWD) cm = tv_raw8(vm, (size_t)pos, cg * 8);
+            for (;;) {
+                const long long nxt = pos + stride;
+                const bool more = nxt < positions;
+                const size_t np = (size_t)(more ? nxt : pos);      // the last iteration re-reads its own (cached) position: loads stay unconditional
+                Raw8 na = tv_raw8(a, np, cg * 8), nb = na, nm = na;
+                if (MODE != SUMS_STATS) nb = tv_raw8(vb, np, cg * 8);
+                if (MODE == SUMS_BN_BWD) nm = tv_raw8(vm, np, cg * 8);
+                float x0[8], y0[8], k0[8];
+                raw_decode8(ca, x0); raw_decode8(cb, y0); raw_decode8(cm, k0);
+                accumulate(x0, y0, k0);
+                if (!more) break;
+                ca = na; cb = nb; cm = nm;
+                pos = nxt;
+            }
         }
     }
     double* r1 = sred;
@@ -301,6 +305,7 @@ struct ResampleBwdParams {
     int n, di, hi, wi, dout, ho, wo, c8;
     int g_ld, g_off, o_ld, o_off;
     float sd, sh, sw;
+    int vec4;
 };
 
 // Adjoint of resample_kernel: every OUTPUT element of the forward scatters its gradient to its (up to) 8 sources.
@@ -332,8 +337,17 @@ resample_bwd_kernel(TView g, float* __restrict__ din, const ResampleBwdParams p)
                     const float wgt = wd[a] * wh[b] * ww[c];
                     if (wgt == 0.f) continue;
                     float* dst = din + ((((size_t)n * p.di + ds[a]) * p.hi + hs[b]) * p.wi + ws[c]) * p.o_ld + p.o_off + cg * 8;
+                    if (p.vec4) {       // 16-byte aligned rows: two vector reductions instead of eight scalar atomics
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(wgt * v[0]), "f"(wgt * v[1]), "f"(wgt * v[2]),
+                                     "f"(wgt * v[3])
+                                     : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(wgt * v[4]), "f"(wgt * v[5]), "f"(wgt * v[6]),
+                                     "f"(wgt * v[7])
+                                     : "memory");
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) atomicAdd(dst + i, wgt * v[i]);
+                        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, wgt * v[i]);
+                    }
                 }
             }
         }
@@ -530,6 +544,7 @@ extern "C" int hupr_resample_linear_bwd(const hupr_tensor_view* g, int n, int do
     p.sd = dout > 1 ? (float)(di - 1) / (float)(dout - 1) : 0.f;
     p.sh = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) : 0.f;
     p.sw = wo > 1 ? (float)(wi - 1) / (float)(wo - 1) : 0.f;
+    p.vec4 = (in_ld % 4 == 0 && in_ch_off % 4 == 0 && ((uintptr_t)din & 15) == 0) ? 1 : 0;
     resample_bwd_kernel<<<ew_blocks((long long)n * dout * ho * wo * p.c8), 256, 0, (cudaStream_t)stream>>>(mk_view(g), din, p);
     return finish(1);
 }
@@ -650,7 +665,21 @@ mnet_bwd_kernel(const float* __restrict__ vrdae, const float* __restrict__ weigh
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
+    // the thread's 32 output gradients = one 64-byte row per plane: eight 16-byte loads up front.  (Reading them as 2-byte scalars inside the
+    // channel loop made every warp-level load touch 32 sectors for 64 useful bytes, 64 times: the kernel was bound by L1 sector requests,
+    // 295 us per launch for 134 MB of input.)
+    float gv[32];
+    {
+        const size_t row = live ? gid : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float g8[8];
+            load8(g_hi + row * 32 + q * 8, g_lo ? g_lo + row * 32 + q * 8 : nullptr, g8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gv[q * 8 + e] = g8[e];
+        }
+    }
+#pragma unroll
     for (int o = 0; o < 32; ++o) {
         float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (live) {
@@ -662,7 +691,7 @@ mnet_bwd_kernel(const float* __restrict__ vrdae, const float* __restrict__ weigh
                 const float y = fmaf(w11, m[9 + 2 * t], fmaf(w10, m[8 + 2 * t], fmaf(w01, m[2 * t + 1], w00 * m[2 * t]))) + bb;
                 if (y > best) { best = y; bt = t; }       // first maximum wins (torch max_pool3d backward)
             }
-            const float g = __bfloat162float(g_hi[gid * 32 + o]) + (g_lo ? __bfloat162float(g_lo[gid * 32 + o]) : 0.f);
+            const float g = gv[o];
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
