@@ -2,31 +2,34 @@
 //
 // Same contract as conv_gemm.cu (hupr_conv_gemm dispatches here for kh == 3 split-bf16 convolutions, i.e. every 3x3x3
 // Conv3d and 3x3 Conv2d of MSCSA-PRGCN, /root/reference/models/layers.py:24-32,45-63).  The generic kernel re-reads the
-// activation tile once per filter tap and the weight tile once per 128 output rows; at ~85 B/cycle/SM of operand traffic
-// that saturates the L2 -> SM path (ncu: tensor pipe 38 % active).  This kernel halves the traffic per FLOP:
+// activation tile once per filter tap and the weight tile once per 128 output rows.  This kernel:
 //   * one CTA owns 256 output positions (bh x bw, two 128-row TMEM accumulators) so every weight tile feeds two MMAs;
 //   * for each (kd, kw, 32-channel block) ONE activation box of bh+2 rows is loaded; the three kh taps of both
 //     accumulators are sub-views of it (start address + kh*bw rows — legal because bw*64 B is a multiple of the swizzle
 //     atom), i.e. 6 tile-taps per load instead of 1;
-//   * k-blocks are 32 channels (64-byte rows, SWIZZLE_64B) so that a stage (halo box + 3 weight tiles, hi and lo planes)
-//     stays under 96 KiB and two to three stages fit;
+//   * k-blocks are 32 channels (64-byte rows, SWIZZLE_64B) so that a stage (halo box + 3 weight tiles, two planes) stays under
+//     96 KiB and two to four stages fit; one TMA box brings the three kh taps of a weight plane and, when lo lies above hi in the
+//     address space (SplitTensor: always), both planes (weight map dims cin, cout, plane, kw, kd*3 + kh);
 //   * the kernel is persistent (one CTA per SM walks the tiles) with two accumulator sets in TMEM, so the epilogue of one tile
-//     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next;
-//   * EIGHT epilogue warps, four per accumulator of the tile: the epilogue is a long dependent chain per thread (one output row, ~20
-//     instructions per value with the stores), and with one warp per scheduler nothing hides its latencies — ncu of the two-unit variant
-//     with four warps: the MMA thread spun 7 M times on accum_empty, tensor pipe 37 % active, i.e. the epilogue (77 k cycles per tile)
-//     and not the 37 k-cycle main loop set the pace; the single-product training kernels were bound the same way;
-//   * cout = 64 tiles (BN = 64, three products) are bound by the tensor core's shared-memory operand reads: an M = 128, N = 64, K = 16
-//     MMA reads 4 KB of A and 2 KB of B per 32 cycles = 192 B/cycle against a 128 B/cycle port (ncu: 34 % tensor-active).  There the
-//     weight tiles of a tap are stored as one 128-row B operand [w_hi | w_lo], so a_hi meets both in ONE N = 128 MMA (columns 0..63 =
-//     hi*hi, 64..127 = hi*lo) and a_lo * w_hi is a second, N = 64 MMA into columns 0..63: the A planes are read twice instead of three
-//     times per k-step (14 KB instead of 18 KB per 96 tensor cycles); the epilogue adds the two column halves.
-//   * NPROD == 2 is the two-unit arithmetic of hupr_conv_desc (include/hupr_b200.h): per 32-channel block ONE kind::f16 pair of MMAs on
-//     fp16 planes (a16 x w16) plus TWO kind::f8f6f4 MMAs (K = 32: a whole 32-byte row) on e4m3 planes (al x w, a x wl), all into the same
-//     fp32 accumulator at a common 2^16 scale — 64 + 32 + 32 tensor cycles per N = 128 tile-tap instead of 3 x 64, and 2/3 of the
-//     shared-memory operand bytes.  The two e4m3 planes of a tensor are interleaved per 32-channel block ([values | residuals] = 64-byte
-//     rows, SWIZZLE_64B like the fp16 plane; as separate 32-byte-row planes under SWIZZLE_32B the tensor core read them at half the rate):
-//     the two cross-term operands are the K = 32 slices at byte 0 and byte 32 of the same rows.  A stage has the size of the hi/lo one.
+//     (TMEM -> scale/shift/residual/activation -> hi/lo stores) overlaps the tensor-core main loop of the next; EIGHT epilogue
+//     warps, four per accumulator of the tile, and 256-bit stores (conv_common.cuh): a thread owns one output row, and 16-byte
+//     stores wrote every 32-byte sector in two instructions — the first two-unit kernel spent 77 k cycles per tile in the epilogue
+//     against a 37 k-cycle main loop (ncu: profiles/r02_halo128_q_*);
+//   * what bounds the main loop is SHARED-MEMORY BANDWIDTH: an M128 x N128 x K16 MMA with both operands in shared memory reads
+//     4 KB + 4 KB in its 64 cycles = the whole 128 B/clk port, and the TMA fills of the next stage come on top.
+//     TWO = true runs CTA PAIRS (tcgen05.mma.cta_group::2, tc.cuh): the two CTAs of a cluster take neighbouring position tiles of the
+//     same weight column tile, each keeps HALF of the weight rows, the leader issues M = 256 MMAs that fill both CTAs'
+//     accumulators — 6 KB per MMA and 72 KB per stage and CTA: tensor pipe 76.8 -> 92.7 % active (three products);
+//   * cout = 64 tiles (BN = 64, three products): an M128 x N64 MMA reads 4 KB of A for 32 tensor cycles.  The weight tiles of a
+//     tap are used as one 128-row B operand [w_hi | w_lo], so a_hi meets both in ONE N = 128 MMA (columns 0..63 = hi*hi,
+//     64..127 = hi*lo) and a_lo * w_hi is a second, N = 64 MMA into columns 0..63; the epilogue adds the two column halves.
+//     In pairs the leader holds the w_hi tile and the peer the w_lo tile of that operand, plus a 32-row half of w_hi each;
+//   * NPROD == 2 is the two-unit arithmetic of hupr_conv_desc (include/hupr_b200.h): per 32-channel block ONE kind::f16 pair of
+//     MMAs on fp16 planes (a16 x w16) plus TWO kind::f8f6f4 MMAs (K = 32) on e4m3 operands (al x w, a x wl), all into the same
+//     fp32 accumulator at a common 2^16 scale — 2/3 of the tensor cycles of three bf16 products.  The two e4m3 planes of a tensor
+//     are interleaved per 32-channel block ([values | residuals] = 64-byte rows, SWIZZLE_64B like the fp16 plane; as separate
+//     32-byte-row planes under SWIZZLE_32B the tensor core read them at half the rate): the two cross-term operands are the K = 32
+//     slices at byte 0 and byte 32 of the same rows.  A stage has the size of the hi/lo one.
 // Warp roles and the hi/lo 3-product arithmetic are those of conv_gemm.cu.
 #include <stdlib.h>
 
@@ -43,7 +46,7 @@ constexpr int kHaloStatBytes = 8 * 2 * 128 * 4;      // per-warp running column 
 struct HaloGeom {
     int halo_rows;                 // (bh + 2) * bw
     int a_plane_bytes;             // halo_rows * 64
-    int b_tile_bytes;              // BN * 64
+    int b_tile_bytes;              // weight rows held by one CTA (BN, or BN / 2 in a CTA pair) * 64
     int nprod;                     // 3: hi/lo planes, three products per k-step; 1: hi planes only
     int stage_bytes;               // planes * (a_plane_bytes + 3 * b_tile_bytes), planes = 2 (nprod 3) or 1
     int stages;
@@ -52,16 +55,6 @@ struct HaloGeom {
     int m_tiles, n_tiles;          // 256-position tiles x BN-column tiles, walked persistently
     int b_merged;                  // three products: tmB_hi is a 5-D map over BOTH weight planes (cin, cout, plane, kw, kd*3 + kh): one box per stage
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;                   // stride byte offset: 8 rows * 32 B
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                            // SWIZZLE_32B
-    return d;
-}
 
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -76,7 +69,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
 template <int BN, int NPROD, bool TWO>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmA_x,      // NPROD == 2: A maps are (fp16 a16, e4m3 a, e4m3 al), B maps (w16, w, wl)
+                 const __grid_constant__ CUtensorMap tmA_x,      // NPROD == 2: A maps are (fp16 a16, interleaved e4m3 plane, -), B maps likewise;
+                                                                 // cout = 64 pairs: tmB_x = the 32-row half of w_hi
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmB_x, const ConvParams p, const HaloGeom g) {
     // Persistent: CTA b walks tiles b, b + gridDim.x, ...; the TMA->MMA smem ring runs continuously across tiles and the two
@@ -119,7 +113,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         fence_mbar_init();
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
-        if (quant) { prefetch_tmap(&tmA_x); prefetch_tmap(&tmB_x); }
+        prefetch_tmap(&tmB_x);
     }
     if (warp == 1) {
         if (TWO) {
@@ -209,13 +203,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         tma_load_4d(sq + 3 * g.b_tile_bytes, &tmB_lo, &full[s], 2 * cb * HK, n0, tkw, tkd * 3);
                     }
                     uint8_t* sb = st + (three ? 2 : 1) * g.a_plane_bytes;
-                    // The TMA unit ingests about one box row per clock plus ~110 clocks per box (tools_dev/micro/tma_rate.cu): six 128-row weight
-                    // boxes cost 1 430 clocks of a 2 400-clock stage.  Weight maps therefore have (kw, kd*3 + kh) as separate dimensions so that
-                    // one box brings the three kh taps, and, where the two planes can be addressed as one tensor, both planes:
+                    // The TMA unit ingests about one box row per clock plus ~110 clocks per box (tools_dev/micro/tma_rate.cu).  Weight maps have
+                    // (kw, kd*3 + kh) as separate dimensions so that one box brings the three kh taps, and, where the two planes can be addressed
+                    // as one tensor, both planes (fewer instructions for the producer thread; the stage time itself is set by shared-memory
+                    // bandwidth, not by TMA issue — merging the boxes changed nothing measurable):
                     // B tiles of a three-product stage: [hi0 lo0 hi1 lo1 hi2 lo2] (for cout = 64, hi|lo of a tap form one N = 128 operand)
                     if (three) {
                         if (g.b_merged) {
-                            tma_load_5d_w(sb, &tmB_hi, &full[s], cb * HK, n0, 0, tkw, tkd * 3);
+                            tma_load_5d(sb, &tmB_hi, &full[s], cb * HK, n0, 0, tkw, tkd * 3);
                         } else {
 #pragma unroll
                             for (int tkh = 0; tkh < 3; ++tkh) {
