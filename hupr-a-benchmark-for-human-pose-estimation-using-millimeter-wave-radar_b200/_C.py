@@ -36,6 +36,7 @@ class ConvDesc(ctypes.Structure):
         ("a_q16", ctypes.c_void_p), ("a_q8", ctypes.c_void_p),
         ("w_q16", ctypes.c_void_p), ("w_q8", ctypes.c_void_p),
         ("o_q16", ctypes.c_void_p), ("o_q8", ctypes.c_void_p),
+        ("q_sat", ctypes.c_void_p),
     ]
 
 
@@ -110,7 +111,7 @@ SIGNATURES = {
     "hupr_fft_cascade_i16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "hupr_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
     "hupr_conv_quant_eligible": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
-    "hupr_quantize_planes": (ctypes.c_int, [_P, _P, ctypes.c_longlong, _I, _I, _I, _P, _P, _I, _P]),
+    "hupr_quantize_planes": (ctypes.c_int, [_P, _P, ctypes.c_longlong, _I, _I, _I, _P, _P, _I, _P, _P]),
     "hupr_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), ctypes.c_void_p]),
     "hupr_attention_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdDesc), ctypes.c_void_p]),
     "hupr_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttnDesc), ctypes.c_void_p]),

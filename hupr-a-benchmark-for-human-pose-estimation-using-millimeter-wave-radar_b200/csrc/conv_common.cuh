@@ -40,6 +40,7 @@ struct ConvParams {
     float acc_scale;               // exact power of two applied to the accumulator first (2^-16 for the two-unit arithmetic, else 1)
     __half* o_q16;                 // optional second form of the output: activation operand planes of the two-unit arithmetic
     uint8_t* o_q8;                 // ([positions][o_ld] at o_ch_off like o_hi; e4m3 plane [positions][o_ld / 32][2][32]; hupr_conv_desc.o_q*)
+    int* q_sat;                    // optional device counter: incremented when a value written to o_q16 left the fp16 plane's range
     int st256;                     // 1: every output plane row segment is 32-byte aligned -> 256-bit stores (one full sector per lane)
 };
 
@@ -198,11 +199,13 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, const f
         const size_t at = pos * p.o_ld + p.o_ch_off + ch0;
         uint4 h[4];
         uint2 a8[4], l8[4];
+        bool sat = false;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const float v8[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
-            quant8(v8, q, h[g], a8[g], l8[g]);
+            sat |= quant8(v8, q, h[g], a8[g], l8[g]);
         }
+        quant_report(p.q_sat, sat);
         st_global_256(p.o_q16 + at, h[0].x, h[0].y, h[0].z, h[0].w, h[1].x, h[1].y, h[1].z, h[1].w);
         st_global_256(p.o_q16 + at + 16, h[2].x, h[2].y, h[2].z, h[2].w, h[3].x, h[3].y, h[3].z, h[3].w);
         uint8_t* d8 = p.o_q8 + 2 * at;          // ch0 and o_ch_off are multiples of 32: this chunk's 64-byte block [values | residuals]
@@ -219,7 +222,7 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, const f
             const float v8[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
             uint4 h;
             uint2 a8, l8;
-            quant8(v8, q, h, a8, l8);
+            quant_report(p.q_sat, quant8(v8, q, h, a8, l8));
             d16[g] = h;
             d8[g] = a8;
             d8l[g] = l8;

@@ -504,6 +504,7 @@ int hupr::conv_gemm_impl(const hupr_conv_desc* d, void* stream, bool launch) {
     p.stats = d->stats; p.stats_ld = d->stats_ld;
     p.acc_scale = 1.0f;
     p.o_q16 = static_cast<__half*>(d->o_q16); p.o_q8 = static_cast<uint8_t*>(d->o_q8);
+    p.q_sat = d->q_sat;
     {   // 256-bit stores need 32-byte aligned row segments in every plane that is written (e4m3 planes: one byte per element)
         const uintptr_t o_or = (uintptr_t)d->o_hi | (uintptr_t)d->o_lo | (uintptr_t)d->o_q16 | (uintptr_t)d->o_q8;
         const int unit = d->o_q8 ? 32 : 16;

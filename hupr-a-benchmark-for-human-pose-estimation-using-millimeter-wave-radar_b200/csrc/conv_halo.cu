@@ -416,6 +416,36 @@ static int encode_halo_wgt_map(CUtensorMap* map, const void* base, int cin, int 
     return r == CUDA_SUCCESS ? HUPR_OK : HUPR_ERR_CUDA;
 }
 
+// How many 2-CTA clusters of the pair kernels can be co-resident on the current device (cached per device; 0 = clusters of this size
+// cannot be scheduled here, e.g. a partitioned GPU: conv_halo_try then keeps the single-CTA kernels instead of failing).
+static int halo_pair_clusters() {
+    static int cached[kMaxDevices] = {};      // 0 = not queried yet, -1 = unavailable
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_index();
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    if (cached[dev] == 0) {
+        auto kernel = conv_halo_kernel<128, 3, true>;
+        int n = 0;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.blockDim = dim3(kHaloThreads);
+        cfg.dynamicSmemBytes = 232448;
+        cfg.gridDim = dim3(2 * (device_sm_count() > 0 ? device_sm_count() : 1), 1, 1);
+        if (ensure_smem_optin(kernel, 232448, configured) != HUPR_OK || cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();      // a failed query is not an error of the convolution
+            n = -1;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev] > 0 ? cached[dev] : 0;
+}
+
 // CTA-pair launch (conv_halo_kernel<.., true>): clusters of two CTAs, as many as can be co-resident (a persistent kernel must not queue).
 template <int BN, int NPROD>
 static int launch_halo_pairs(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& a_x, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
@@ -516,7 +546,7 @@ int conv_halo_try(const hupr_conv_desc* d, const ConvParams& base, cudaStream_t 
     p.cin_blocks = cin_eff / HK;
     // CTA pairs (cta_group::2 MMAs, each CTA holds half of the weight rows): cout = 128 tiles, an even number of position tiles so that the
     // two CTAs of a pair always share their weight column tile; HUPR_HALO_SINGLE=1 is the A/B switch
-    const bool pairs = m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE");
+    const bool pairs = m_tiles % 2 == 0 && !getenv("HUPR_HALO_SINGLE") && (probe || halo_pair_clusters() > 0);
     const bool pairs64 = pairs && bn == 64 && three;      // [w_hi | w_lo] form: a 64-row X tile and a 32-row Y tile per tap and CTA
     HaloGeom g;
     g.b_merged = 0;

@@ -133,7 +133,7 @@ reduce_f64_kernel(const double* __restrict__ src, int groups, int n, float* __re
 // thread = 8 consecutive channels of one row; two independent items per iteration so that four 16-byte loads are in flight
 __global__ void __launch_bounds__(256)
 quantize_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long items, int ld, int ch_off, int groups,
-                       __half* __restrict__ q16, uint8_t* __restrict__ q8, int is_weight) {
+                       __half* __restrict__ q16, uint8_t* __restrict__ q8, int is_weight, int* __restrict__ sat) {
     const QuantScales q = quant_scales(is_weight != 0);
     const long long stride = (long long)gridDim.x * 256;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < items; i += stride) {
@@ -143,7 +143,7 @@ quantize_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16
         load8(hi + at, lo ? lo + at : nullptr, v);
         uint4 h;
         uint2 a8, l8;
-        quant8(v, q, h, a8, l8);
+        quant_report(sat, quant8(v, q, h, a8, l8));
         *reinterpret_cast<uint4*>(q16 + at) = h;
         // e4m3 plane: [row][ld / 32][2][32] — the 32 values of a channel block, then its 32 residuals
         const int c = ch_off + (int)(i - row * groups) * 8;
@@ -250,7 +250,7 @@ extern "C" int hupr_reduce_f64(const double* src, int groups, int n, float* dst,
 }
 
 extern "C" int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, int is_weight,
-                                    void* stream) {
+                                    int* sat, void* stream) {
     using namespace hupr;
     if (rows < 0 || ld <= 0 || ch < 0 || ch_off < 0 || ch_off + ch > ld || ld % 32 || ch % 32 || ch_off % 32) return HUPR_ERR_BAD_ARG;
     if (rows == 0 || ch == 0) return HUPR_OK;
@@ -264,7 +264,7 @@ extern "C" int hupr_quantize_planes(const void* hi, const void* lo, long long ro
     long long blocks = (items + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     quantize_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, items, ld, ch_off,
-                                                                                groups, (__half*)q16, (uint8_t*)q8, is_weight);
+                                                                                groups, (__half*)q16, (uint8_t*)q8, is_weight, sat);
     return pack_status();
 }
 

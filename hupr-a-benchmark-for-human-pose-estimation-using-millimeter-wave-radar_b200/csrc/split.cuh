@@ -64,11 +64,14 @@ __device__ __forceinline__ QuantScales quant_scales(bool is_weight) {
 __device__ __forceinline__ uint32_t e4m3x2(float a, float b) {      // a in the low byte
     return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
 }
-__device__ __forceinline__ void quant8(const float (&v)[8], const QuantScales& q, uint4& h16, uint2& q8, uint2& q8l) {
+// Returns true when a value left the fp16 plane's range (|x * s16| > 65504: the plane saturates and the result is no longer the value).
+__device__ __forceinline__ bool quant8(const float (&v)[8], const QuantScales& q, uint4& h16, uint2& q8, uint2& q8l) {
     uint32_t h[4], a8[4], l8[4];
+    float top = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float a = v[2 * i], b = v[2 * i + 1];
+        top = fmaxf(top, fmaxf(fabsf(a), fabsf(b)));
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b * q.s16), "f"(a * q.s16));      // a in the low half; saturates to +-65504
         const __half2 hh = *reinterpret_cast<const __half2*>(&h[i]);
         const float ra = a - __low2float(hh) * q.inv16, rb = b - __high2float(hh) * q.inv16;
@@ -78,6 +81,11 @@ __device__ __forceinline__ void quant8(const float (&v)[8], const QuantScales& q
     h16 = make_uint4(h[0], h[1], h[2], h[3]);
     q8 = make_uint2(a8[0] | (a8[1] << 16), a8[2] | (a8[3] << 16));
     q8l = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    return !(top * q.s16 <= 65504.f);      // also true for NaN
+}
+// Saturation report of the quantised planes: a device counter that is only ever incremented (callers read and reset it).
+__device__ __forceinline__ void quant_report(int* flag, bool saturated) {
+    if (saturated && flag) atomicAdd(flag, 1);
 }
 
 }  // namespace hupr

@@ -184,6 +184,12 @@ class HuPRNet(nn.Module):
         state["_packed"], state["_plans"], state["_train_step"] = None, {}, None
         return state
 
+    def quant_saturations(self, reset=True):
+        """Values that left the range of the two-unit convolutions' operand planes (|activation| >= 16 376) on this model's device since
+        the last reset — 0 in normal operation (ops.quant_saturations; synchronises).  A non-zero count means those forwards were
+        wrong: set ``quant_cross_terms = False`` for this checkpoint / input scaling."""
+        return ops.quant_saturations(next(self.parameters()).device, reset)
+
     def invalidate(self):
         """Drop the packed (kernel-format) weights and cached launch plans; call after mutating parameters in place."""
         self._packed = None

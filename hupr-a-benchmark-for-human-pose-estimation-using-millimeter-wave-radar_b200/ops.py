@@ -203,6 +203,34 @@ def quant(on=True):
         _QUANT = prev
 
 
+_QUANT_SAT = {}      # device index -> int32[1] counter of values that left the fp16 operand planes' range (quant_saturations)
+
+
+def _quant_sat(device):
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _QUANT_SAT.get(index)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                 # counters are created by an eager pass; a graph captured without one simply does not report
+        t = _QUANT_SAT[index] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", index))
+    return t
+
+
+def quant_saturations(device=None, reset=True):
+    """How many values the two-unit convolutions' operand planes could not represent (|activation| >= 16 376) since the last reset, on
+    ``device`` — 0 in normal operation; anything else means those forwards were wrong and ``HuPRNet.quant_cross_terms`` should be off
+    for this model / input scaling.  Synchronises the device."""
+    index = None if device is None else torch.device(device).index
+    t = _QUANT_SAT.get(torch.cuda.current_device() if index is None else index)
+    if t is None:
+        return 0
+    n = int(t.item())
+    if reset and n:
+        t.zero_()
+    return n
+
+
 def quantize_planes(t, ch_off=0, ch=None, is_weight=False):
     """hupr_quantize_planes: fill ``t.q`` (allocated on first use) for channels [ch_off, ch_off + ch) from the hi/lo planes."""
     q16, q8 = t.ensure_q()
@@ -211,7 +239,8 @@ def quantize_planes(t, ch_off=0, ch=None, is_weight=False):
     rows = t.hi.numel() // ld
     with torch.cuda.device(t.hi.device), _timed("quantize_planes"):
         _C.check(_C.lib().hupr_quantize_planes(t.hi.data_ptr(), _C.optr(t.lo), rows, ld, ch_off, ch, q16.data_ptr(), q8.data_ptr(),
-                                               1 if is_weight else 0, _C.stream_ptr()), "hupr_quantize_planes")
+                                               1 if is_weight else 0, None if is_weight else _C.optr(_quant_sat(t.hi.device)),
+                                               _C.stream_ptr()), "hupr_quantize_planes")
     return t.q
 
 
@@ -293,6 +322,7 @@ def conv_gemm(a, cin, weight, cout, kernel=(1, 1, 1), pad=(0, 0, 0), a_ch_off=0,
         desc.w_q16, desc.w_q8 = (t.data_ptr() for t in weight.q)
     if out_q and out is not None and QUANT_FUSE:
         desc.o_q16, desc.o_q8 = (t.data_ptr() for t in out.ensure_q())
+        desc.q_sat = _C.optr(_quant_sat(out.hi.device))
         out.q_fresh = (o_ch_off, o_ch_off + cout)
     d_out = d + 2 * pad[0] - kernel[0] + 1
     rows = n * d_out * h * w if lrows is None else lrows

@@ -129,6 +129,8 @@ typedef struct hupr_conv_desc {
     const void* w_q16; const void* w_q8;
     void* o_q16; void* o_q8;                                      /* optional: ALSO store the output as activation planes of that form ([positions][o_ld]
                                                                      at o_ch_off like o_hi), for a following nprod == 2 convolution; needs o_hi */
+    int* q_sat;                                                   /* optional device counter, incremented whenever a value written to o_q16 lies outside
+                                                                     the fp16 plane's range (|a| >= 16 376): the planes then no longer represent the tensor */
 } hupr_conv_desc;
 
 int hupr_conv_gemm(const hupr_conv_desc* desc, void* stream);
@@ -139,9 +141,10 @@ int hupr_conv_quant_eligible(const hupr_conv_desc* desc);
 
 /* The operand planes of the two-unit arithmetic from a bf16 split tensor: rows x [ch_off, ch_off + ch) of [rows][ld] (ld, ch_off, ch
  * multiples of 32).  is_weight selects the scale set (0: activation 2^2 / 2^1 / 2^12, 1: weight 2^14 / 2^4 / 2^15).  q16: fp16 [rows][ld];
- * q8: e4m3 bytes [rows][ld / 32][2][32] (hupr_conv_desc).  lo may be NULL. */
+ * q8: e4m3 bytes [rows][ld / 32][2][32] (hupr_conv_desc).  lo may be NULL.  sat: optional device counter incremented when a value
+ * lies outside the fp16 plane's range (hupr_conv_desc.q_sat). */
 int hupr_quantize_planes(const void* hi, const void* lo, long long rows, int ld, int ch_off, int ch, void* q16, void* q8, int is_weight,
-                         void* stream);
+                         int* sat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused spatial attention (flash-style: the [S, S] logits never leave the SM).  Replaces

@@ -170,6 +170,12 @@ def test_large_activations_degrade_gracefully_and_large_weights_fall_back():
     err = float((out.float().double() - ref).abs().max()) / float(ref.abs().max())
     print("two-unit conv with |x| up to %.0f: max error / max |output| %.3g" % (float(x.abs().max()), err))
     assert torch.isfinite(out.float()).all() and err < 4e-4          # CPU emulation of this case: 1.3e-4 (1.2e-5 inside the range)
+    assert ops.quant_saturations("cuda") == 0                        # ... and nothing left the fp16 plane (|x| < 16 376)
+    huge = SplitTensor.from_float(x * 40.0)                          # |x| up to ~60 000: the fp16 plane itself saturates -> reported
+    with ops.quant():
+        ops.conv_gemm(huge, cin, ws, cout, kernel=(3, 3, 3), pad=(1, 1, 1), out=out, out_q=True)
+    n_sat = ops.quant_saturations("cuda")
+    assert n_sat > 0 and ops.quant_saturations("cuda") == 0          # counted once, reset by the read
     big = w.clone()
     big[3, 5, 7] = 4.5
     wb = SplitTensor.from_float(big)
