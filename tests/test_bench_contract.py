@@ -70,3 +70,31 @@ def test_clock_sampler_parses_nvidia_smi_rows(tmp_path):
     s.proc = _Done()
     out = s.stop()
     assert out["sm_max_mhz"] == 1965.0 and out["sm_mhz"] == 1942.5 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 3
+
+
+def test_clock_sampler_reports_only_samples_after_mark(tmp_path):
+    """The sampler is started (and waited for) before the timed region; mark() right before the region drops the idle-GPU samples taken
+    until then, so that a 0.2 s region is described by the samples that fell inside it (a run whose first sample arrived late used to
+    report none at all)."""
+    import bench
+    s = bench.ClockSampler(0)
+    s.path = str(tmp_path / "clocks.csv")
+    with open(s.path, "w") as fp:
+        fp.write("0, 345, 1965, 140.2, 0x0, Not Active, Not Active, Not Active, Not Active\n")
+        fp.write("0, 420, 1965, 150.0, 0x0, Not Active, Not Active, Not Active, Not Active\n")
+    s.mark()
+    assert s.skip == 2
+    with open(s.path, "a") as fp:
+        fp.write("0, 1800, 1965, 990.1, 0x4, Not Active, Not Active, Not Active, Active\n")
+        fp.write("0, 1790, 1965, 985.0, 0x4, Not Active, Not Active, Not Active, Active\n")
+        fp.write("0, 1780, 1965, 985.0, 0x4, Not Active, Not Active, Not Active, Active\n")
+
+    class _Done(object):
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+    s.proc = _Done()
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1790.0 and out["reasons"] == ["sw_power_cap"]
