@@ -653,12 +653,18 @@ def main():
         conv = fam["conv_gemm"]
         achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        # DRAM traffic of the family's dominant kernel from its ncu --set full capture (profiles/r01_halo128_persist_metrics.csv: ONE
-        # conv_halo_kernel<128,3> launch, 64 -> 128 channels, batch 32): 269.7 MB read + 484.2 MB written against 269.3 MB of input + weights
-        # and 536.9 MB of output — no DRAM re-reads: the 27-tap operand re-reads are served by L2 (part of the output is still in L2 at exit)
+        # DRAM traffic of the family's dominant kernel from its ncu --set full capture, ONE launch of the 64 -> 128 channel 3x3x3 layer at
+        # batch 32.  Default arithmetic (profiles/r02_halo128_q64_pairs_metrics.csv, conv_halo_kernel<128,2,true>: CTA pairs, two-unit
+        # products, output stored as hi/lo planes AND as the next layer's fp16 + e4m3 operand planes): 270.5 MB read + 1 019.9 MB written
+        # against 269.3 MB of input + weights and 1 073.7 MB of output.  Three bf16 products (profiles/r02_halo128_pairs_metrics.csv,
+        # conv_halo_kernel<128,3,true>): 270.3 MB + 487.7 MB against 269.3 + 536.9 MB.  No DRAM re-reads either way: the 27-tap operand
+        # re-reads are served by L2 (part of the output is still in L2 at exit).
+        two_unit = (not args.single_bf16) and any(k.endswith(".q") for k in sub)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": 269696256.0 + 484221184.0, "traffic_algorithmic_bytes": 269317120.0 + 536870912.0,
-                    "traffic_of": "one conv_halo_kernel<128,3> launch (64->128 channels, 3x3x3, batch 32), ncu dram__bytes_read.sum + dram__bytes_write.sum",
+                    "traffic": (270486272.0 + 1019883000.0) if two_unit else (270325248.0 + 487689728.0),
+                    "traffic_algorithmic_bytes": (269317120.0 + 1073741824.0) if two_unit else (269317120.0 + 536870912.0),
+                    "traffic_of": "one conv_halo_kernel<128,%s,true> launch (64->128 channels, 3x3x3, batch 32), ncu dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum" % ("2" if two_unit else "3"),
                     "kernel": "hupr::conv_gemm_kernel (all %d launches of one step; FLOPs = 2 x MACs of the fp32 contraction — the "
                               "tensor pipe executes %s that)" % (conv["launch_calls"], "1x" if args.single_bf16 else
                                                                 "3x (bf16 hi/lo products), 2x on the two-unit 3-tap convolutions (fp16 + e4m3 cross terms)"),
